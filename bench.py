@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the low-light hot path (BASELINE.json: "lowlight_recovery fwd+bwd
+images/sec @640^2 and % HBM roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE configs[1]): per GPU, batch 16x3x640x640 fp32 synthetic; one *step* =
+    synthesis clean -> dark (= clean ** 15) fused with the recovery-loss reduction
+    -> bilinear resize 256^2 -> predictor CNN forward -> fused filter chain forward (y)
+    -> fused filter chain backward (cotangent g, read from HBM) -> predictor backward (164 943 gradients)
+    -> [N > 1] one NCCL all-reduce(sum) of the flat predictor gradient.
+Weak scaling: every rank runs its own 16 images; the only collective is the gradient all-reduce.
+
+Timed numbers
+  value       images/s, whole job; inputs resident in HBM; K steps replayed from CUDA graphs; CUDA events on the
+              launching stream; barrier + synchronize on both sides; max over ranks.
+  e2e         same metric through the user-facing API (`preprocess_batch` + the `lowlight_recovery` nn.Module with
+              autograd) with the uint8 batch in pinned HOST memory: H2D copy of the batch and D2H of the recovery
+              loss + gradient norm inside the timed region, every step.
+  roofline    for the dominant kernel (largest stage time): algorithmic bytes per launch
+              / its mean duration, measured with CUDA events around each stage over a second eager pass of K steps.
+  cpu_baseline  the oracle's fp32 port (same op mix as the reference's PyTorch CPU path) on the host cores, on a
+              bounded sample.
+L2 hygiene: inputs rotate over a ring of sets much larger than the 126 MB L2 (see config.l2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "lowlight_recovery fwd+bwd images/sec @640x640 (synthesis + recovery loss + fwd + bwd)"
+UNIT = "images/s"
+B_PER_GPU, H, W = 16, 640, 640
+DARK_PARAM = 15.0
+N_PIX = H * W
+# algorithmic bytes per image
+BYTES_FWD = 12 * N_PIX + 12 * N_PIX          # read x, write y (filter-chain kernel only)
+BYTES_BWD = 12 * N_PIX + 12 * N_PIX          # read g, read x (no dx)
+BYTES_SYNTH = 12 * N_PIX + 12 * N_PIX        # fp32 clean in, dark out
+BYTES_RESIZE_TAPS = 3 * 256 * 256 * 4 * 4
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.004):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _sample(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        for k, bit in names.items():
+            if r & bit:
+                self.reasons.add(k)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        if self.ok and not self.samples:
+            try:
+                self._sample()
+            except Exception:
+                pass
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's fp32 port (dense 25x25 conv like the reference) on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_step(clean, g, weights, O, torch):
+    dark = O.synth_darken(clean, DARK_PARAM)
+    rec = O.recovery_mse(dark, clean)
+    y = O.recovery_forward(dark, weights, dense_blur=True)
+    (y * g).sum().backward()
+    return float(rec)
+
+
+def cpu_baseline(sample_images: int, reps: int):
+    import torch
+    from oracle import lowlight_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    weights = O.cast_weights(O.init_weights(0), torch.float32, requires_grad=True)
+    gen = torch.Generator().manual_seed(1234)
+    clean = torch.rand(sample_images, 3, H, W, generator=gen)
+    g = torch.randn(sample_images, 3, H, W, generator=gen)
+    times = []
+    for i in range(reps + 1):
+        for v in weights.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        cpu_step(clean, g, weights, O, torch)
+        if i > 0 or reps == 0:
+            times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    return {
+        "value": sample_images / t, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{sample_images} image(s) of the 16x3x640x640 workload per step (synthesis + fwd + bwd, fp32, "
+                  f"torch CPU, dense 25x25 blur as in the reference), median of {len(times)} after 1 warm-up",
+    }, t
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python and cannot travel to
+    the GPU box) on all host cores.  Each step is a bounded sample (2 images) of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import lowlight_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = 2
+    weights = O.cast_weights(O.init_weights(0), torch.float32, requires_grad=True)
+    gen = torch.Generator().manual_seed(1234)
+    clean = torch.rand(sample, 3, H, W, generator=gen)
+    g = torch.randn(sample, 3, H, W, generator=gen)
+    for _ in range(args.warmup):
+        cpu_step(clean, g, weights, O, torch)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for v in weights.values():
+            v.grad = None
+        cpu_step(clean, g, weights, O, torch)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{sample}-image sample per step of configs[1] (16x3x640x640 fp32: synthesis + recovery "
+                               "loss + lowlight_recovery fwd + bwd), reference algorithm on host CPU"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} images per step x {args.steps} steps"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import dedark_yolo_b200 as dd
+    from dedark_yolo_b200.dist import init_from_env, max_over_ranks
+
+    rank, local_rank, world = init_from_env("nccl")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B = B_PER_GPU
+    torch.manual_seed(0)
+    module = dd.lowlight_recovery(3).to(dev).train()
+    pipe = dd.RecoveryPipeline(module, B, H, W, dark_param=DARK_PARAM, allreduce=world > 1)
+
+    # input ring: RING distinct (clean, g) sets; one step touches ~390 MB, so a set is long gone from L2 when reused
+    RING = 4
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    cleans = [torch.rand(B, 3, H, W, generator=gen, device=dev) for _ in range(RING)]
+    gs = [torch.randn(B, 3, H, W, generator=gen, device=dev) for _ in range(RING)]
+
+    use_graph = not args.no_graph
+    launches_per_step = None
+    if use_graph:
+        try:
+            for i in range(RING):
+                n0 = dd.launch_count()
+                pipe.capture(i, cleans[i], gs[i])
+                launches_per_step = (dd.launch_count() - n0) // 2  # warm-up + captured pass
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] CUDA graph capture failed ({e!r}); falling back to eager launches", file=sys.stderr)
+            use_graph = False
+            pipe.graphs.clear()
+    if launches_per_step is None:
+        n0 = dd.launch_count()
+        pipe.step(cleans[0], gs[0])
+        launches_per_step = dd.launch_count() - n0
+
+    def one_step(i):
+        if use_graph:
+            pipe.replay(i % RING)
+        else:
+            pipe.step(cleans[i % RING], gs[i % RING])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one_step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- stage timing (eager, CUDA events around each C-ABI call, same stream) -> roofline of the dominant kernel
+    stages = ["synth", "resize+predictor_fwd", "filters_fwd", "filters_bwd", "predictor_bwd"]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(args.steps)]
+    st = torch.cuda.current_stream(dev).cuda_stream
+    import ctypes as C
+    from dedark_yolo_b200 import _lib
+    from dedark_yolo_b200.pipeline import _p
+    for i in range(3):
+        pipe.step(cleans[i % RING], gs[i % RING])
+    torch.cuda.synchronize(dev)
+    for i in range(args.steps):
+        src, g = cleans[i % RING], gs[i % RING]
+        ev[i][0].record()
+        pipe.synth(src, st)
+        ev[i][1].record()
+        _lib.check(_lib.lib.dd_resize256(_p(pipe.dark), _p(pipe.r), B, H, W, st))
+        _lib.check(_lib.lib.dd_predictor_fwd(_p(pipe.r), C.byref(pipe._w), _p(pipe.acts), _p(pipe.feat), B, st))
+        ev[i][2].record()
+        _lib.check(_lib.lib.dd_recovery_fwd(_p(pipe.dark), None, None, _p(pipe.feat), _p(pipe.y), B, H, W, st))
+        ev[i][3].record()
+        _lib.check(_lib.lib.dd_recovery_bwd(_p(pipe.dark), None, None, _p(pipe.feat), _p(g), _p(pipe.dfeat), None, B, H, W,
+                                            _p(pipe._ws_rb), pipe._ws_rb.numel(), st))
+        ev[i][4].record()
+        _lib.check(_lib.lib.dd_predictor_bwd(_p(pipe.r), C.byref(pipe._w), _p(pipe.acts), _p(pipe.dfeat), C.byref(pipe._g), None, B,
+                                             _p(pipe._ws_pb), pipe._ws_pb.numel(), st))
+        ev[i][5].record()
+    torch.cuda.synchronize(dev)
+    stage_us = {s: 1e3 * statistics.mean(ev[i][k].elapsed_time(ev[i][k + 1]) for i in range(args.steps))
+                for k, s in enumerate(stages)}
+    peak, peak_src = load_peaks()
+    alg = {"filters_fwd": BYTES_FWD * B, "filters_bwd": BYTES_BWD * B, "synth": BYTES_SYNTH * B}
+    dominant = max(("filters_fwd", "filters_bwd"), key=lambda s: stage_us[s])
+    achieved = alg[dominant] / (stage_us[dominant] * 1e-6) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": {"filters_fwd": "recovery_fwd_kernel", "filters_bwd": "recovery_bwd_kernel (+finalize)"}[dominant],
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dominant],
+        "kernel_us": stage_us[dominant],
+        "all_stages_us": stage_us,
+        "frac_by_stage": {s: alg[s] / (stage_us[s] * 1e-6) / 1e9 / peak for s in alg},
+        "frac_vs_nominal_8TBs": achieved / 8000.0,
+    }
+
+    # ---- e2e: user-facing API, uint8 batch in pinned host memory, H2D + D2H inside the timed region
+    cpu_gen = torch.Generator().manual_seed(4321 + rank)
+    host_u8 = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=cpu_gen).pin_memory() for _ in range(2)]
+    host_out = torch.empty(2, dtype=torch.float32).pin_memory()
+    params = [p for p in module.parameters()]
+
+    def e2e_step(i):
+        for p in params:
+            p.grad = None
+        batch = dd.preprocess_batch({"img": host_u8[i % 2]}, dev, dark_param=DARK_PARAM)
+        y = module(batch["img"])
+        y.backward(gs[i % RING])
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        if world > 1:
+            dist.all_reduce(flat)
+        res = torch.stack([batch["recovery_loss_batch"], flat.norm()])
+        host_out.copy_(res, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()  # the step's result is on the host
+        return host_out
+
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    e2e = {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 3 * H * W,
+           "d2h_bytes_per_step": 8, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "api": "preprocess_batch(uint8 pinned host batch) -> lowlight_recovery(nn.Module) fwd -> autograd bwd -> "
+                  "D2H(recovery loss, grad norm)"}
+
+    if rank == 0:
+        cpu = None
+        if not args.skip_cpu and world == 1:
+            cpu, _ = cpu_baseline(sample_images=2, reps=3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": "configs[1]: lowlight_recovery fwd+bwd + recovery_loss, batch 16x3x640x640 fp32 synthetic per GPU "
+                            "(synthesis clean**15 + mse, resize, predictor fwd, fused filters fwd, fused filters bwd, predictor bwd"
+                            + (", NCCL all-reduce of 164943 grads)" if world > 1 else ")"),
+                "global_batch": world * B, "parallelism": f"dp{world}", "launch": "cuda_graph" if use_graph else "eager",
+                "l2": f"inputs rotate over a ring of {RING} (clean, g) sets = {RING * 2 * B * 3 * H * W * 4 / 1e6:.0f} MB + "
+                      f"{2 * B * 3 * H * W * 4 / 1e6:.0f} MB of outputs per step (L2 = 126 MB); no explicit flush",
+                "e2e_input": "uint8 batch (train.py:72) in pinned host memory",
+            },
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step, "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 200 and args.warmup == 20:  # defaults are sized for the GPU arm
+            args.steps, args.warmup = 5, 1
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,99 @@
+// dd_common.cuh -- shared helpers for the sm_100a kernels of libdedark_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dedark_b200.h"
+
+namespace dd {
+
+// ---- frozen constants of the reference (filter_cfg.py:17-44, filtersB.py:156,163,247) ------------
+constexpr int kFeat = DD_NUM_FEATURES;
+constexpr int kSlotDedark = 0, kSlotWb = 1, kSlotGamma = 4, kSlotContrast = 13, kSlotUsm = 14;
+constexpr float kLumR = 0.27f, kLumG = 0.67f, kLumB = 0.06f;
+constexpr float kWbEps = 1e-5f, kContrastEps = 1e-6f, kTxMin = 0.01f, kGammaClamp = 1e-4f;
+constexpr float kDefaultA = 0.8f, kDefaultIcA = 0.5f;
+constexpr float kLeaky = 0.1f;
+constexpr int kRadius = 12;
+constexpr int kTaps = 25;
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kLn3 = 1.09861228866810969140f;
+
+// k1[i] = exp(-0.5 ((i-12)/5)^2) / sum, evaluated in fp32 exactly as filtersB.py:158-160 does
+// (values recorded from torch; checked by tests/test_oracle.py::test_blur_dense_equals_separable_fp64
+// and by the GPU parity tests).  Index = |offset|.
+#define DD_K0 0.08077993243932724f  // 0x1.4adfe60000000p-4
+#define DD_K1 0.07918038219213486f  // 0x1.4452a60000000p-4
+#define DD_K2 0.07456927001476288f  // 0x1.316f8c0000000p-4
+#define DD_K3 0.06747306883335114f  // 0x1.145ea40000000p-4
+#define DD_K4 0.05865826830267906f  // 0x1.e0874e0000000p-5
+#define DD_K5 0.04899550601840019f  // 0x1.915f060000000p-5
+#define DD_K6 0.03931981325149536f  // 0x1.421ba00000000p-5
+#define DD_K7 0.030317604541778564f  // 0x1.f0b9400000000p-6
+#define DD_K8 0.022459832951426506f  // 0x1.6ffb5e0000000p-6
+#define DD_K9 0.01598624512553215f  // 0x1.05eb2c0000000p-6
+#define DD_K10 0.010932374745607376f  // 0x1.663b680000000p-7
+#define DD_K11 0.007183081936091185f  // 0x1.d6c01e0000000p-8
+#define DD_K12 0.004534561652690172f  // 0x1.292d520000000p-8
+
+__host__ __device__ __forceinline__ constexpr float tap(int a) {  // a = |offset| in 0..12
+    return a == 0 ? DD_K0 : a == 1 ? DD_K1 : a == 2 ? DD_K2 : a == 3 ? DD_K3 : a == 4 ? DD_K4
+         : a == 5 ? DD_K5 : a == 6 ? DD_K6 : a == 7 ? DD_K7 : a == 8 ? DD_K8 : a == 9 ? DD_K9
+         : a == 10 ? DD_K10 : a == 11 ? DD_K11 : a == 12 ? DD_K12 : 0.0f;
+}
+
+// ---- host-side error plumbing --------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(unsigned n = 1);
+int check_launch(const char* what);  // cudaGetLastError -> DD_OK / DD_ERR_CUDA
+
+#define DD_REQUIRE(cond, code, ...)      \
+    do {                                 \
+        if (!(cond)) {                   \
+            dd::set_error(__VA_ARGS__);  \
+            return (code);               \
+        }                                \
+    } while (0)
+
+// ---- device helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum in a fixed order (warp shuffles, then warp 0 adds the per-warp values in index
+// order): deterministic for a given block size.  `scratch` holds >= 32 values.  Result valid in
+// thread 0.  Ends with a barrier so scratch can be reused immediately.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    T r = T(0);
+    if (wid == 0) {
+        r = lane < nw ? scratch[lane] : T(0);
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : kLeaky * v; }
+__device__ __forceinline__ float leaky_grad(float act, float g) { return act > 0.f ? g : kLeaky * g; }
+
+// reflect index of F.pad(mode='reflect'): -i -> i, (n-1)+i -> (n-1)-i   (valid for |overhang| <= n-1)
+__device__ __forceinline__ int reflect(int i, int n) {
+    i = i < 0 ? -i : i;
+    return i > n - 1 ? 2 * (n - 1) - i : i;
+}
+
+}  // namespace dd

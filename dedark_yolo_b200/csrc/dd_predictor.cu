@@ -1,0 +1,495 @@
+// dd_predictor.cu -- a4 + a5: bilinear resize to 256x256 and the parameter-predictor CNN, forward and
+// backward, in fp32 on the CUDA cores (exact-parity path: the 1e-5 output gate does not survive
+// TF32/bf16 operand rounding in these GEMMs).
+//
+// Reference: nn/modules/llie.py:43 (F.interpolate bilinear, align_corners=False),
+//            nn/modules/common.py:9-23 (ConvBlock: Conv2d k3 s2 p1 + LeakyReLU 0.1),
+//            nn/modules/common.py:52-78 (ExtractParameters2: 5 conv blocks, fc1 2048->64, fc2 64->15).
+//
+// Layout: every tensor NCHW fp32.  Activations live in the caller's workspace (dd_layout.cuh).  All
+// reductions are fixed-order (per-thread serial loops, block_sum, split partials summed in index
+// order): bit-reproducible run to run.
+#include "dd_common.cuh"
+#include "dd_layout.cuh"
+
+namespace dd {
+
+// -------------------------------------------------------------------------------------------------
+// bilinear source index, ATen upsample_bilinear2d semantics (align_corners=False)
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int n, int& i0, int& i1, float& lam) {
+    float s = scale * ((float)dst + 0.5f) - 0.5f;
+    s = s < 0.f ? 0.f : s;
+    i0 = (int)s;
+    i0 = i0 > n - 1 ? n - 1 : i0;
+    i1 = i0 < n - 1 ? i0 + 1 : i0;
+    lam = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(256)
+resize256_kernel(const float* __restrict__ x, float* __restrict__ r, int B, int H, int W) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;  // output column (256 per row)
+    const int i = blockIdx.y;                              // output row
+    const int plane = blockIdx.z;                          // b*3 + ch
+    if (j >= DD_RESIZE) return;
+    const float sh = (float)H / (float)DD_RESIZE, sw = (float)W / (float)DD_RESIZE;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(i, sh, H, y0, y1, ly);
+    bilinear_src(j, sw, W, x0, x1, lx);
+    const float* p = x + (size_t)plane * H * W;
+    const float v00 = __ldg(p + (size_t)y0 * W + x0), v01 = __ldg(p + (size_t)y0 * W + x1);
+    const float v10 = __ldg(p + (size_t)y1 * W + x0), v11 = __ldg(p + (size_t)y1 * W + x1);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    r[((size_t)plane * DD_RESIZE + i) * DD_RESIZE + j] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+}
+
+// adjoint as a gather (deterministic): every source pixel sums the output pixels that sampled it
+__global__ void __launch_bounds__(256)
+resize256_bwd_kernel(const float* __restrict__ dr, float* __restrict__ dx, int B, int H, int W) {
+    const int xs = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ys = blockIdx.y;
+    const int plane = blockIdx.z;
+    if (xs >= W) return;
+    const float sh = (float)H / (float)DD_RESIZE, sw = (float)W / (float)DD_RESIZE;
+    int ilo = (int)floorf(((float)ys - 0.5f) / sh - 0.5f) - 1, ihi = (int)ceilf(((float)ys + 1.5f) / sh - 0.5f) + 1;
+    int jlo = (int)floorf(((float)xs - 0.5f) / sw - 0.5f) - 1, jhi = (int)ceilf(((float)xs + 1.5f) / sw - 0.5f) + 1;
+    ilo = ilo < 0 ? 0 : ilo; jlo = jlo < 0 ? 0 : jlo;
+    ihi = ihi > DD_RESIZE - 1 ? DD_RESIZE - 1 : ihi; jhi = jhi > DD_RESIZE - 1 ? DD_RESIZE - 1 : jhi;
+    const float* d = dr + (size_t)plane * DD_RESIZE * DD_RESIZE;
+    float acc = 0.f;
+    for (int i = ilo; i <= ihi; ++i) {
+        int y0, y1; float ly;
+        bilinear_src(i, sh, H, y0, y1, ly);
+        const float wy = (y0 == ys ? 1.f - ly : 0.f) + (y1 == ys ? ly : 0.f);
+        if (wy == 0.f) continue;
+        float racc = 0.f;
+        for (int j = jlo; j <= jhi; ++j) {
+            int x0, x1; float lx;
+            bilinear_src(j, sw, W, x0, x1, lx);
+            const float wx = (x0 == xs ? 1.f - lx : 0.f) + (x1 == xs ? lx : 0.f);
+            racc = fmaf(wx, __ldg(d + (size_t)i * DD_RESIZE + j), racc);
+        }
+        acc = fmaf(wy, racc, acc);
+    }
+    dx[((size_t)plane * H + ys) * W + xs] += acc;
+}
+
+// -------------------------------------------------------------------------------------------------
+// conv 3x3, stride 2, pad 1, + bias + LeakyReLU(0.1): direct convolution, register-tiled
+//   thread = PX horizontally adjacent output pixels x CO_T output channels
+//   weights staged once per CTA in shared memory as [ci*9 + kh*3 + kw][co] (broadcast 128-bit reads)
+// -------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, int HIN, int PX, int CO_T>
+__global__ void __launch_bounds__(256)
+conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                float* __restrict__ out, int B) {
+    constexpr int HO = HIN / 2;
+    constexpr int PXG = HO * HO / PX;   // pixel groups per image
+    constexpr int COG = COUT / CO_T;    // channel groups
+    __shared__ __align__(16) float sw[CIN * 9 * COUT];
+    for (int i = threadIdx.x; i < CIN * 9 * COUT; i += blockDim.x) {
+        const int co = i / (CIN * 9), rem = i % (CIN * 9);  // w is [co][ci][kh][kw]
+        sw[rem * COUT + co] = w[i];
+    }
+    __syncthreads();
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= (long long)B * PXG * COG) return;
+    const int pg = (int)(item % PXG);
+    const int cog = (int)((item / PXG) % COG);
+    const int b = (int)(item / ((long long)PXG * COG));
+    const int oh = pg / (HO / PX), ow0 = (pg % (HO / PX)) * PX;
+
+    float acc[PX][CO_T];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int c = 0; c < CO_T; ++c) acc[p][c] = 0.f;
+
+    const float* inb = in + (size_t)b * CIN * HIN * HIN;
+    for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int ih = 2 * oh + kh - 1;
+            if (ih < 0 || ih >= HIN) continue;
+            const float* row = inb + ((size_t)ci * HIN + ih) * HIN;
+            float v[2 * PX + 1];
+#pragma unroll
+            for (int t = 0; t < 2 * PX + 1; ++t) {
+                const int iw = 2 * ow0 - 1 + t;
+                v[t] = (iw >= 0) ? __ldg(row + iw) : 0.f;   // iw <= HIN-1 always
+            }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const float* wp = sw + (ci * 9 + kh * 3 + kw) * COUT + cog * CO_T;
+#pragma unroll
+                for (int c4 = 0; c4 < CO_T; c4 += 4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + c4);
+#pragma unroll
+                    for (int p = 0; p < PX; ++p) {
+                        const float a = v[2 * p + kw];
+                        acc[p][c4 + 0] = fmaf(a, wv.x, acc[p][c4 + 0]);
+                        acc[p][c4 + 1] = fmaf(a, wv.y, acc[p][c4 + 1]);
+                        acc[p][c4 + 2] = fmaf(a, wv.z, acc[p][c4 + 2]);
+                        acc[p][c4 + 3] = fmaf(a, wv.w, acc[p][c4 + 3]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) {
+        const int co = cog * CO_T + c;
+        const float bv = __ldg(bias + co);
+        float* o = out + (((size_t)b * COUT + co) * HO + oh) * HO + ow0;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) o[p] = leaky(acc[p][c] + bv);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// data gradient of the same conv.  thread = one 2x2 quad of INPUT pixels x CI_T input channels; the four
+// parities of a stride-2 3x3 conv touch exactly the 2x2 output neighbourhood (a..a+1, c..c+1):
+//   (even,even): w11 d(a,c)                    (even,odd): w10 d(a,c+1) + w12 d(a,c)
+//   (odd,even):  w01 d(a+1,c) + w21 d(a,c)     (odd,odd):  w00 d(a+1,c+1) + w02 d(a+1,c) + w20 d(a,c+1) + w22 d(a,c)
+// The result is multiplied by LeakyReLU'(act_in) so the stored tensor is the gradient w.r.t. the previous
+// layer's PRE-activation (act_in == nullptr for the network input).
+// -------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, int HIN, int CI_T>
+__global__ void __launch_bounds__(256)
+conv_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, const float* __restrict__ act_in,
+                  float* __restrict__ din, int B) {
+    constexpr int HO = HIN / 2;
+    constexpr int CIG = CIN / CI_T;
+    __shared__ float sw[COUT * 9 * CIN];  // [co][k][ci]
+    for (int i = threadIdx.x; i < COUT * 9 * CIN; i += blockDim.x) {
+        const int co = i / (CIN * 9), rem = i % (CIN * 9), ci = rem / 9, k = rem % 9;
+        sw[(co * 9 + k) * CIN + ci] = w[i];
+    }
+    __syncthreads();
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= (long long)B * HO * HO * CIG) return;
+    const int q = (int)(item % (HO * HO));
+    const int cig = (int)((item / (HO * HO)) % CIG);
+    const int b = (int)(item / ((long long)HO * HO * CIG));
+    const int a = q / HO, c = q % HO;
+    const bool a1 = a + 1 < HO, c1 = c + 1 < HO;
+
+    float acc[4][CI_T];  // quad order: ee, eo, oe, oo
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < CI_T; ++j) acc[i][j] = 0.f;
+
+    const float* db = dpre + (size_t)b * COUT * HO * HO;
+    for (int co = 0; co < COUT; ++co) {
+        const float* dp = db + ((size_t)co * HO + a) * HO + c;
+        const float d00 = __ldg(dp);
+        const float d01 = c1 ? __ldg(dp + 1) : 0.f;
+        const float d10 = a1 ? __ldg(dp + HO) : 0.f;
+        const float d11 = (a1 && c1) ? __ldg(dp + HO + 1) : 0.f;
+        const float* wp = sw + co * 9 * CIN + cig * CI_T;
+#pragma unroll
+        for (int j = 0; j < CI_T; ++j) {
+            const float w00 = wp[0 * CIN + j], w01 = wp[1 * CIN + j], w02 = wp[2 * CIN + j];
+            const float w10 = wp[3 * CIN + j], w11 = wp[4 * CIN + j], w12 = wp[5 * CIN + j];
+            const float w20 = wp[6 * CIN + j], w21 = wp[7 * CIN + j], w22 = wp[8 * CIN + j];
+            acc[0][j] = fmaf(w11, d00, acc[0][j]);
+            acc[1][j] = fmaf(w10, d01, fmaf(w12, d00, acc[1][j]));
+            acc[2][j] = fmaf(w01, d10, fmaf(w21, d00, acc[2][j]));
+            acc[3][j] = fmaf(w00, d11, fmaf(w02, d10, fmaf(w20, d01, fmaf(w22, d00, acc[3][j]))));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CI_T; ++j) {
+        const int ci = cig * CI_T + j;
+        const size_t base = (((size_t)b * CIN + ci) * HIN + 2 * a) * HIN + 2 * c;
+        float2 top = make_float2(acc[0][j], acc[1][j]), bot = make_float2(acc[2][j], acc[3][j]);
+        if (act_in) {
+            const float2 at = *reinterpret_cast<const float2*>(act_in + base);
+            const float2 ab = *reinterpret_cast<const float2*>(act_in + base + HIN);
+            top.x = leaky_grad(at.x, top.x); top.y = leaky_grad(at.y, top.y);
+            bot.x = leaky_grad(ab.x, bot.x); bot.y = leaky_grad(ab.y, bot.y);
+        }
+        *reinterpret_cast<float2*>(din + base) = top;
+        *reinterpret_cast<float2*>(din + base + HIN) = bot;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// weight (+bias) gradient.  CTA = (tile of 4 output channels, one input channel, one slice of the
+// (b, oh) rows).  Each thread keeps 4x9 accumulators; block_sum -> partial[slice][...]; a second kernel
+// adds the slices in index order.
+// -------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, int HIN>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dpre, float* __restrict__ partial,
+                  int B, int split) {
+    constexpr int HO = HIN / 2;
+    constexpr int NW = COUT * CIN * 9;
+    __shared__ float s_red[32];
+    const int cot = blockIdx.x / CIN, ci = blockIdx.x % CIN;  // cot: tile of 4 output channels
+    const int slice = blockIdx.y;
+    const int rows = B * HO;
+    const int per = (rows + split - 1) / split;
+    const int r0 = slice * per, r1 = min(rows, r0 + per);
+
+    float acc[4][9];
+    float accb[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        accb[t] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[t][k] = 0.f;
+    }
+    for (int idx = threadIdx.x; idx < (r1 - r0) * HO; idx += blockDim.x) {
+        const int row = r0 + idx / HO, ow = idx % HO;
+        const int b = row / HO, oh = row % HO;
+        float v[9];
+        const float* ip = in + ((size_t)b * CIN + ci) * HIN * HIN;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int ih = 2 * oh + kh - 1;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int iw = 2 * ow + kw - 1;
+                v[kh * 3 + kw] = (ih >= 0 && ih < HIN && iw >= 0) ? __ldg(ip + (size_t)ih * HIN + iw) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float d = __ldg(dpre + (((size_t)b * COUT + cot * 4 + t) * HO + oh) * HO + ow);
+            accb[t] += d;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[t][k] = fmaf(d, v[k], acc[t][k]);
+        }
+    }
+    float* out = partial + (size_t)slice * (NW + COUT);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int co = cot * 4 + t;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float s = block_sum<float>(acc[t][k], s_red);
+            if (threadIdx.x == 0) out[(co * CIN + ci) * 9 + k] = s;
+        }
+        if (ci == 0) {
+            const float s = block_sum<float>(accb[t], s_red);
+            if (threadIdx.x == 0) out[NW + co] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int split, int nw, int nb, float* __restrict__ dw,
+                    float* __restrict__ db) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nw + nb) return;
+    float a = 0.f;
+    for (int s = 0; s < split; ++s) a += partial[(size_t)s * (nw + nb) + i];
+    if (i < nw) dw[i] = a; else db[i - nw] = a;
+}
+
+// -------------------------------------------------------------------------------------------------
+// fully connected layers
+// -------------------------------------------------------------------------------------------------
+// h[b][o] = leaky(flat[b] . W1[o] + b1[o]); one warp per (b, o)
+__global__ void __launch_bounds__(256)
+fc1_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w1, const float* __restrict__ b1,
+               float* __restrict__ h, int B) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B * kFc1Out) return;
+    const int b = warp / kFc1Out, o = warp % kFc1Out;
+    const float4* f = reinterpret_cast<const float4*>(flat + (size_t)b * kFc1In);
+    const float4* w = reinterpret_cast<const float4*>(w1 + (size_t)o * kFc1In);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = lane; i < kFc1In / 4; i += 32) {
+        const float4 a = __ldg(f + i), c = __ldg(w + i);
+        acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) h[warp] = leaky(acc + __ldg(b1 + o));
+}
+
+// feat[b][j] = h[b] . W2[j] + b2[j]
+__global__ void __launch_bounds__(256)
+fc2_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2,
+               float* __restrict__ feat, int B) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * kFeat) return;
+    const int b = t / kFeat, j = t % kFeat;
+    float acc = 0.f;
+    for (int o = 0; o < kFc1Out; ++o) acc = fmaf(__ldg(h + b * kFc1Out + o), __ldg(w2 + j * kFc1Out + o), acc);
+    feat[t] = acc + __ldg(b2 + j);
+}
+
+// dW2, db2 and dhpre = leaky'(h) * (dfeat . W2); single CTA
+__global__ void __launch_bounds__(1024)
+fc2_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, const float* __restrict__ w2,
+               float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dhpre, int B) {
+    const int t = threadIdx.x;
+    if (t < kFeat * kFc1Out) {
+        const int j = t / kFc1Out, o = t % kFc1Out;
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc = fmaf(dfeat[b * kFeat + j], h[b * kFc1Out + o], acc);
+        dw2[t] = acc;
+    }
+    if (t < kFeat) {
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc += dfeat[b * kFeat + t];
+        db2[t] = acc;
+    }
+    for (int i = t; i < B * kFc1Out; i += blockDim.x) {
+        const int b = i / kFc1Out, o = i % kFc1Out;
+        float acc = 0.f;
+        for (int j = 0; j < kFeat; ++j) acc = fmaf(dfeat[b * kFeat + j], w2[j * kFc1Out + o], acc);
+        dhpre[i] = leaky_grad(h[i], acc);
+    }
+}
+
+// dW1[o][i] = sum_b dhpre[b][o] flat[b][i];  db1[o] = sum_b dhpre[b][o]
+__global__ void __launch_bounds__(256)
+fc1_wgrad_kernel(const float* __restrict__ dhpre, const float* __restrict__ flat, float* __restrict__ dw1,
+                 float* __restrict__ db1, int B) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < kFc1Out * kFc1In) {
+        const int o = t / kFc1In, i = t % kFc1In;
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc = fmaf(__ldg(dhpre + b * kFc1Out + o), __ldg(flat + (size_t)b * kFc1In + i), acc);
+        dw1[t] = acc;
+    }
+    if (t < kFc1Out) {
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc += dhpre[b * kFc1Out + t];
+        db1[t] = acc;
+    }
+}
+
+// dpre5[b][i] = leaky'(a5[b][i]) * sum_o dhpre[b][o] W1[o][i]
+__global__ void __launch_bounds__(256)
+fc1_dgrad_kernel(const float* __restrict__ dhpre, const float* __restrict__ w1, const float* __restrict__ a5,
+                 float* __restrict__ dpre5, int B) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * kFc1In) return;
+    const int b = t / kFc1In, i = t % kFc1In;
+    float acc = 0.f;
+    for (int o = 0; o < kFc1Out; ++o) acc = fmaf(__ldg(dhpre + b * kFc1Out + o), __ldg(w1 + (size_t)o * kFc1In + i), acc);
+    dpre5[t] = leaky_grad(a5[t], acc);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-side launch helpers
+// -------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, int HIN, int PX, int CO_T>
+static void launch_conv_fwd(const float* in, const float* w, const float* b, float* out, int B, cudaStream_t st) {
+    constexpr int HO = HIN / 2;
+    const long long items = (long long)B * (HO * HO / PX) * (COUT / CO_T);
+    conv_fwd_kernel<CIN, COUT, HIN, PX, CO_T><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(in, w, b, out, B);
+    count_launch();
+}
+
+template <int CIN, int COUT, int HIN, int CI_T>
+static void launch_conv_dgrad(const float* dpre, const float* w, const float* act_in, float* din, int B,
+                              cudaStream_t st) {
+    constexpr int HO = HIN / 2;
+    const long long items = (long long)B * HO * HO * (CIN / CI_T);
+    conv_dgrad_kernel<CIN, COUT, HIN, CI_T><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(dpre, w, act_in, din, B);
+    count_launch();
+}
+
+template <int CIN, int COUT, int HIN>
+static void launch_conv_wgrad(const float* in, const float* dpre, float* partial, float* dw, float* db, int B,
+                              cudaStream_t st) {
+    constexpr int HO = HIN / 2;
+    constexpr int NW = COUT * CIN * 9;
+    // slices of the (b, oh) rows: aim at ~4096 reduction elements per CTA
+    int split = (int)(((long long)B * HO * HO + 4095) / 4096);
+    split = split < 1 ? 1 : (split > kWgradMaxSplit ? kWgradMaxSplit : split);
+    dim3 grid((COUT / 4) * CIN, split);
+    conv_wgrad_kernel<CIN, COUT, HIN><<<grid, 256, 0, st>>>(in, dpre, partial, B, split);
+    wgrad_reduce_kernel<<<(NW + COUT + 255) / 256, 256, 0, st>>>(partial, split, NW, COUT, dw, db);
+    count_launch(2);
+}
+
+static bool tensors_ok(const dd_predictor_tensors* t) {
+    if (!t) return false;
+    for (int i = 0; i < 5; ++i)
+        if (!t->conv_w[i] || !t->conv_b[i]) return false;
+    return t->fc1_w && t->fc1_b && t->fc2_w && t->fc2_b;
+}
+
+}  // namespace dd
+
+extern "C" int dd_resize256(const float* x, float* r, int B, int H, int W, void* stream_) {
+    using namespace dd;
+    DD_REQUIRE(x && r && B > 0 && H > 0 && W > 0, DD_ERR_INVALID, "dd_resize256: bad arguments");
+    DD_REQUIRE((long long)B * 3 <= 65535, DD_ERR_INVALID, "dd_resize256: B too large (%d)", B);
+    dim3 grid(1, DD_RESIZE, B * 3);
+    resize256_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(x, r, B, H, W);
+    count_launch();
+    return check_launch("dd_resize256");
+}
+
+extern "C" int dd_resize256_bwd(const float* dr, float* dx, int B, int H, int W, void* stream_) {
+    using namespace dd;
+    DD_REQUIRE(dr && dx && B > 0 && H > 0 && W > 0, DD_ERR_INVALID, "dd_resize256_bwd: bad arguments");
+    DD_REQUIRE((long long)B * 3 <= 65535 && H <= 65535, DD_ERR_INVALID, "dd_resize256_bwd: shape too large");
+    dim3 grid((W + 255) / 256, H, B * 3);
+    resize256_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(dr, dx, B, H, W);
+    count_launch();
+    return check_launch("dd_resize256_bwd");
+}
+
+extern "C" int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, float* acts, float* feat, int B,
+                                void* stream_) {
+    using namespace dd;
+    cudaStream_t st = (cudaStream_t)stream_;
+    DD_REQUIRE(r && acts && feat && B > 0 && tensors_ok(w), DD_ERR_INVALID, "dd_predictor_fwd: bad arguments");
+    float* a[6];
+    for (int l = 0; l < 6; ++l) a[l] = acts + pred_act_offset(l, B);
+    launch_conv_fwd<3, 16, 256, 2, 16>(r, w->conv_w[0], w->conv_b[0], a[0], B, st);
+    launch_conv_fwd<16, 32, 128, 2, 16>(a[0], w->conv_w[1], w->conv_b[1], a[1], B, st);
+    launch_conv_fwd<32, 32, 64, 1, 8>(a[1], w->conv_w[2], w->conv_b[2], a[2], B, st);
+    launch_conv_fwd<32, 32, 32, 1, 8>(a[2], w->conv_w[3], w->conv_b[3], a[3], B, st);
+    launch_conv_fwd<32, 32, 16, 1, 4>(a[3], w->conv_w[4], w->conv_b[4], a[4], B, st);
+    fc1_fwd_kernel<<<(B * kFc1Out * 32 + 255) / 256, 256, 0, st>>>(a[4], w->fc1_w, w->fc1_b, a[5], B);
+    fc2_fwd_kernel<<<(B * kFeat + 255) / 256, 256, 0, st>>>(a[5], w->fc2_w, w->fc2_b, feat, B);
+    count_launch(2);
+    return check_launch("dd_predictor_fwd");
+}
+
+extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, const float* acts,
+                                const float* dfeat, const dd_predictor_tensors* g, float* dr, int B, void* ws,
+                                size_t ws_bytes, void* stream_) {
+    using namespace dd;
+    cudaStream_t st = (cudaStream_t)stream_;
+    DD_REQUIRE(r && acts && dfeat && B > 0 && tensors_ok(w) && tensors_ok(g), DD_ERR_INVALID,
+               "dd_predictor_bwd: bad arguments");
+    DD_REQUIRE(ws && ws_bytes >= predictor_bwd_ws_bytes(B), DD_ERR_WORKSPACE, "dd_predictor_bwd: workspace %zu < %zu",
+               ws_bytes, predictor_bwd_ws_bytes(B));
+    const float* a[6];
+    float* d[6];
+    for (int l = 0; l < 6; ++l) {
+        a[l] = acts + pred_act_offset(l, B);
+        d[l] = reinterpret_cast<float*>(ws) + pred_act_offset(l, B);
+    }
+    float* partial = reinterpret_cast<float*>(ws) + predictor_acts_elems(B);
+
+    fc2_bwd_kernel<<<1, 1024, 0, st>>>(dfeat, a[5], w->fc2_w, g->fc2_w, g->fc2_b, d[5], B);
+    fc1_wgrad_kernel<<<(kFc1Out * kFc1In + 255) / 256, 256, 0, st>>>(d[5], a[4], g->fc1_w, g->fc1_b, B);
+    fc1_dgrad_kernel<<<(B * kFc1In + 255) / 256, 256, 0, st>>>(d[5], w->fc1_w, a[4], d[4], B);
+    count_launch(3);
+    // conv5 .. conv1: weight gradient from (input act, dpre), then data gradient into the previous layer
+    launch_conv_wgrad<32, 32, 16>(a[3], d[4], partial, g->conv_w[4], g->conv_b[4], B, st);
+    launch_conv_dgrad<32, 32, 16, 8>(d[4], w->conv_w[4], a[3], d[3], B, st);
+    launch_conv_wgrad<32, 32, 32>(a[2], d[3], partial, g->conv_w[3], g->conv_b[3], B, st);
+    launch_conv_dgrad<32, 32, 32, 8>(d[3], w->conv_w[3], a[2], d[2], B, st);
+    launch_conv_wgrad<32, 32, 64>(a[1], d[2], partial, g->conv_w[2], g->conv_b[2], B, st);
+    launch_conv_dgrad<32, 32, 64, 8>(d[2], w->conv_w[2], a[1], d[1], B, st);
+    launch_conv_wgrad<16, 32, 128>(a[0], d[1], partial, g->conv_w[1], g->conv_b[1], B, st);
+    launch_conv_dgrad<16, 32, 128, 8>(d[1], w->conv_w[1], a[0], d[0], B, st);
+    launch_conv_wgrad<3, 16, 256>(r, d[0], partial, g->conv_w[0], g->conv_b[0], B, st);
+    if (dr) launch_conv_dgrad<3, 16, 256, 3>(d[0], w->conv_w[0], nullptr, dr, B, st);
+    return check_launch("dd_predictor_bwd");
+}

@@ -1,0 +1,69 @@
+"""Low-light synthesis and the recovery-loss term around the module (host-side mirrors of the reference).
+
+  preprocess_batch   <- DetectionTrainer.preprocess_batch   (models/yolo/detect/train.py:70-111)
+  apply_lowlight     <- apply_lowlight_and_save, pre-encode  (utils/lowlight_process.py:57-74)
+  add_recovery_term  <- RcoveryDetectionLoss.__call__        (utils/loss.py:393-416)
+
+The arithmetic (``/255``, ``pow``, ``mse``, truncating uint8 writer) is one CUDA pass (``dd_synth_fwd``).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+def preprocess_batch(batch: dict, device, dark_param: float = 15.0, lowlight_FLAG: bool = True,
+                     dedark_FLAG: bool = False, lut: Optional[torch.Tensor] = None) -> dict:
+    """Same keys and semantics as the reference trainer hook:
+
+    ``batch['img']`` uint8 NCHW  ->  ``clean_img`` (= u8/255), ``img`` (= clean ** dark_param when
+    ``lowlight_FLAG``) and ``recovery_loss_batch`` (= mse(img, clean_img), a constant without grad).
+    With ``dedark_FLAG and lowlight_FLAG`` the reference overwrites clean_img with the darkened image, so
+    img is clean_img and the loss is exactly 0 (train.py:79,100,108); that branch's CPU dark-channel loop
+    (train.py:81-97) produces ``dedark_A``/``IcA`` that no consumer reads and is not
+    reproduced here.
+    """
+    src = batch["img"].to(device, non_blocking=True)
+    if not lowlight_FLAG:
+        clean, _, _, _ = ops.synth_forward(src, 1.0, want_dark=False, want_rec=False) if src.dtype == torch.uint8 \
+            else (src.float(), None, None, None)
+        batch["clean_img"] = clean
+        batch["img"] = clean
+        batch["recovery_loss_batch"] = torch.zeros((), dtype=torch.float32, device=src.device)
+        return batch
+    clean, dark, _, rec = ops.synth_forward(src, dark_param, lut=lut)
+    if dedark_FLAG:
+        batch["clean_img"] = dark
+        batch["img"] = dark
+        batch["recovery_loss_batch"] = torch.zeros((), dtype=torch.float32, device=src.device)
+    else:
+        batch["clean_img"] = clean
+        batch["img"] = dark
+        batch["recovery_loss_batch"] = rec
+    return batch
+
+
+def apply_lowlight(u8: torch.Tensor, lowlight_param: float = 7.5, lut: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 RGB NCHW -> darkened uint8 (``(pow(u8/255, p) * 255).astype(uint8)``, truncation).  This is the array
+    the reference hands to ``cv2.imwrite`` (before the RGB->BGR flip and the JPEG encoder)."""
+    _, _, q, _ = ops.synth_forward(u8, lowlight_param, lut=lut, want_clean=False, want_dark=False, want_u8=True,
+                                   want_rec=False)
+    return q
+
+
+def add_recovery_term(loss: torch.Tensor, loss_items: torch.Tensor, batch: dict, lrl: float = 2.0):
+    """utils/loss.py:393-416: ``loss += lrl * rec`` and the same amount is folded into the cls column, keeping
+    ``loss_items`` at shape [3].  ``rec`` is a constant (no gradient flows through it)."""
+    box, cls, dfl = loss_items
+    rec = batch.get("recovery_loss_batch")
+    if rec is not None:
+        if rec.ndim > 0:
+            rec = rec.mean()
+        rec = rec.to(loss.device)
+        cls = cls + lrl * rec
+        loss = loss + lrl * rec
+    items = torch.stack([box.detach(), cls.detach(), dfl.detach()]).to(loss.device)
+    return loss, items

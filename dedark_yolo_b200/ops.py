@@ -1,0 +1,197 @@
+"""Thin PyTorch host layer over the C-ABI: tensors in, raw pointers + current stream out.
+
+torch is used for device memory, streams and autograd bookkeeping only; every arithmetic step is a
+kernel of ``libdedark_b200.so``.  All functions require CUDA tensors and raise otherwise (there is
+no CPU path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import PredictorTensors, check, lib
+
+NUM_FEATURES = 15
+RESIZE = 256
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dedark_yolo_b200: CUDA tensor required (no CPU fallback in this build)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ---- a1 + a2 ---------------------------------------------------------------------------------------
+def synth_forward(src: torch.Tensor, p: float, lut: Optional[torch.Tensor] = None, want_clean: bool = True,
+                  want_dark: bool = True, want_u8: bool = False, want_rec: bool = True):
+    """Low-light synthesis + recovery-loss scalar in one pass (train.py:72,79,103,108-109).
+
+    ``src``: uint8 or float32 CUDA tensor of any shape.  Returns ``(clean, dark, dark_u8, rec)``; entries not
+    requested are None.  For a float32 source ``clean`` is ``src`` itself."""
+    _need_cuda(src, lut)
+    if src.dtype not in (torch.uint8, torch.float32):
+        raise TypeError(f"synth_forward: uint8 or float32 source expected, got {src.dtype}")
+    src = src.contiguous()
+    is_u8 = src.dtype == torch.uint8
+    dev, n = src.device, src.numel()
+    with torch.cuda.device(dev):
+        clean = torch.empty(src.shape, dtype=torch.float32, device=dev) if (is_u8 and want_clean) else None
+        dark = torch.empty(src.shape, dtype=torch.float32, device=dev) if want_dark else None
+        dark_u8 = torch.empty(src.shape, dtype=torch.uint8, device=dev) if want_u8 else None
+        rec = torch.empty((), dtype=torch.float32, device=dev) if want_rec else None
+        ws_bytes = _lib.workspace_bytes(_lib.WS_SYNTH, 1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if want_rec else None
+        if lut is not None:
+            lut = _f32c(lut)
+            if lut.numel() != 256:
+                raise ValueError("lut must have 256 entries")
+        check(lib.dd_synth_fwd(_ptr(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, float(p), _ptr(lut), _ptr(clean),
+                               _ptr(dark), _ptr(dark_u8), _ptr(rec), n, _ptr(ws), ws_bytes if want_rec else 0,
+                               _stream(dev)))
+    if not is_u8 and want_clean:
+        clean = src
+    return clean, dark, dark_u8, rec
+
+
+# ---- a4 / a5 ---------------------------------------------------------------------------------------
+def resize256(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    x = _f32c(x)
+    B, Cc, H, W = x.shape
+    assert Cc == 3
+    r = torch.empty(B, 3, RESIZE, RESIZE, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.dd_resize256(_ptr(x), _ptr(r), B, H, W, _stream(x.device)))
+    return r
+
+
+def predictor_forward(r: torch.Tensor, params: Sequence[torch.Tensor]):
+    """``r`` [B,3,256,256] -> (feat [B,15], acts workspace).  ``params``: the 14 tensors in state-dict order."""
+    _need_cuda(r, *params)
+    B = r.shape[0]
+    dev = r.device
+    acts = torch.empty(_lib.workspace_bytes(_lib.WS_PREDICTOR_ACTS, B) // 4, dtype=torch.float32, device=dev)
+    feat = torch.empty(B, NUM_FEATURES, dtype=torch.float32, device=dev)
+    w = PredictorTensors.from_tensors(params)
+    with torch.cuda.device(dev):
+        check(lib.dd_predictor_fwd(_ptr(r), C.byref(w), _ptr(acts), _ptr(feat), B, _stream(dev)))
+    return feat, acts
+
+
+def predictor_backward(r, params, acts, dfeat, need_dr: bool = False, flat_grad: Optional[torch.Tensor] = None):
+    """Returns (list of 14 gradient tensors -- views into one flat buffer, dr or None)."""
+    _need_cuda(r, acts, dfeat, *params)
+    B, dev = r.shape[0], r.device
+    sizes = [p.numel() for p in params]
+    if flat_grad is None:
+        flat_grad = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+    grads, off = [], 0
+    for p, n in zip(params, sizes):
+        grads.append(flat_grad[off:off + n].view(p.shape))
+        off += n
+    dr = torch.empty_like(r) if need_dr else None
+    ws_bytes = _lib.workspace_bytes(_lib.WS_PREDICTOR_BWD, B)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    w, g = PredictorTensors.from_tensors(params), PredictorTensors.from_tensors(grads)
+    with torch.cuda.device(dev):
+        check(lib.dd_predictor_bwd(_ptr(r), C.byref(w), _ptr(acts), _ptr(dfeat), C.byref(g), _ptr(dr), B, _ptr(ws),
+                                   ws_bytes, _stream(dev)))
+    return grads, dr
+
+
+# ---- a6..a12, a14 ----------------------------------------------------------------------------------
+def filters_forward(x, feat, A=None, IcA=None) -> torch.Tensor:
+    _need_cuda(x, feat, A, IcA)
+    B, _, H, W = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.dd_recovery_fwd(_ptr(x), _ptr(A), _ptr(IcA), _ptr(feat), _ptr(y), B, H, W, _stream(x.device)))
+    return y
+
+
+def filters_backward(x, feat, g, A=None, IcA=None, need_dx: bool = False):
+    """Returns (dfeat [B,15], dx or None)."""
+    _need_cuda(x, feat, g, A, IcA)
+    B, _, H, W = x.shape
+    dev = x.device
+    dfeat = torch.empty(B, NUM_FEATURES, dtype=torch.float32, device=dev)
+    dx = torch.empty_like(x) if need_dx else None
+    ws_bytes = _lib.workspace_bytes(_lib.WS_RECOVERY_BWD, B, H, W)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dd_recovery_bwd(_ptr(x), _ptr(A), _ptr(IcA), _ptr(feat), _ptr(g), _ptr(dfeat), _ptr(dx), B, H, W,
+                                  _ptr(ws), ws_bytes, _stream(dev)))
+    return dfeat, dx
+
+
+def resize256_backward_(dr: torch.Tensor, dx: torch.Tensor) -> None:
+    """dx += resize^T(dr), in place."""
+    B, _, H, W = dx.shape
+    with torch.cuda.device(dx.device):
+        check(lib.dd_resize256_bwd(_ptr(dr), _ptr(dx), B, H, W, _stream(dx.device)))
+
+
+def check_image_shape(x: torch.Tensor) -> None:
+    """Raise what the reference raises for the same input (SURVEY.md section 8(b) 'Error conventions')."""
+    if x.dim() != 4:
+        raise RuntimeError(f"lowlight_recovery expects a 4-D NCHW tensor, got {tuple(x.shape)}")
+    B, Cc, H, W = x.shape
+    if Cc != 3:
+        raise RuntimeError(f"lowlight_recovery expects 3 channels (common.py:59 Conv2d(3, 16)), got {Cc}")
+    if x.dtype == torch.float64:
+        raise RuntimeError("lowlight_recovery: float64 input is not supported (filtersB.py:155 builds a float32 kernel)")
+    if W < 3:
+        raise IndexError(f"index 2 is out of bounds for dimension 3 with size {W} (rgb2lum, util_filters.py:270-273)")
+    if H <= 12 or W <= 12:
+        raise RuntimeError(f"reflect padding of 12 needs H, W > 12, got {H} x {W} (filtersB.py:167)")
+
+
+class RecoveryFunction(torch.autograd.Function):
+    """lowlight_recovery.forward as one autograd node: resize -> predictor -> fused filter chain.
+
+    Inputs may live on the CPU (DetectionModel.__init__ probes the model with CPU zeros, nn/tasks.py:290-291):
+    they are staged through ``device`` and the result is returned on x's device.  The work itself always runs on
+    the GPU through the C-ABI."""
+
+    @staticmethod
+    def forward(ctx, device, x, A, IcA, *params):
+        out_dev = x.device
+        xd = _f32c(x.to(device))
+        Ad = None if A is None else _f32c(A.to(device)).reshape(xd.shape[0], 3)
+        Id = None if IcA is None else _f32c(IcA.to(device)).expand(xd.shape[0], 1, xd.shape[2], xd.shape[3]).contiguous()
+        pd = [_f32c(p.to(device)) for p in params]
+        r = resize256(xd)
+        feat, acts = predictor_forward(r, pd)
+        y = filters_forward(xd, feat, Ad, Id)
+        ctx.save_for_backward(xd, Ad, Id, r, acts, feat, *pd)
+        ctx.out_dev = out_dev
+        ctx.param_devs = [(p.device, p.dtype) for p in params]
+        return y.to(out_dev)
+
+    @staticmethod
+    def backward(ctx, g):
+        xd, Ad, Id, r, acts, feat, *pd = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[1]
+        gd = _f32c(g.to(xd.device))
+        dfeat, dx = filters_backward(xd, feat, gd, Ad, Id, need_dx)
+        grads, dr = predictor_backward(r, pd, acts, dfeat, need_dr=need_dx)
+        if need_dx:
+            resize256_backward_(dr, dx)
+            dx = dx.to(ctx.out_dev)
+        grads = [gr.to(device=d, dtype=t) for gr, (d, t) in zip(grads, ctx.param_devs)]
+        return (None, dx, None, None, *grads)

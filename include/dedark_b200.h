@@ -1,0 +1,119 @@
+/*
+ * dedark_b200.h -- C-ABI of libdedark_b200.so: the B200 (sm_100a) implementation of the
+ * Dedark-YOLO low-light hot path.
+ *
+ * The reference (cvYouTian/Dedark-YOLO) is pure Python: it has no FFI for this path.  The seam this
+ * header defines is the one its host code would bind: plain pointers,
+ * sizes and a CUDA stream; no torch types.  Each entry point names the reference code it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its comment says "host";
+ *   - the caller owns every buffer (the library never allocates or frees device memory, creates no
+ *     streams, keeps no mutable global state apart from the launch counter and the last-error
+ *     string, which is thread-local);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises;
+ *   - images are contiguous NCHW fp32 with C == 3;
+ *   - return value: DD_OK or a DD_ERR_* code; `dd_last_error()` then describes the failure.  The
+ *     codes mirror the reference's own failure modes (reflect pad needs H,W > 12; the rgb2lum quirk
+ *     needs W >= 3).  The library never calls exit/abort.
+ */
+#ifndef DEDARK_B200_H
+#define DEDARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD_OK 0
+#define DD_ERR_INVALID 1      /* null pointer, B/H/W <= 0, bad enum                                */
+#define DD_ERR_REFLECT_PAD 2  /* H <= 12 or W <= 12: F.pad(mode='reflect', 12) fails (filtersB.py:167) */
+#define DD_ERR_WIDTH_LT3 3    /* W < 3: rgb2lum indexes columns 0..2 (util_filters.py:270-273)     */
+#define DD_ERR_WORKSPACE 4    /* workspace too small (see dd_workspace_bytes)                     */
+#define DD_ERR_CUDA 5         /* a CUDA runtime/driver call failed                                */
+
+#define DD_NUM_FEATURES 15    /* filter_cfg.py:17 */
+#define DD_RESIZE 256         /* llie.py:43       */
+
+/* workspace kinds for dd_workspace_bytes */
+#define DD_WS_SYNTH 0          /* dd_synth_fwd partial sums                                        */
+#define DD_WS_PREDICTOR_ACTS 1 /* activations kept from dd_predictor_fwd for dd_predictor_bwd     */
+#define DD_WS_PREDICTOR_BWD 2  /* scratch of dd_predictor_bwd                                      */
+#define DD_WS_RECOVERY_BWD 3   /* partial sums of dd_recovery_bwd                                  */
+
+/* source dtypes for dd_synth_fwd */
+#define DD_SRC_U8 0
+#define DD_SRC_F32 1
+
+int dd_version(void);
+const char* dd_last_error(void);             /* host string, valid until the next failing call on this thread */
+unsigned long long dd_launch_count(void);    /* kernels launched by this library since load (monotonic)       */
+size_t dd_workspace_bytes(int kind, int B, int H, int W);
+
+/* ---- a1 + a2: low-light synthesis and the recovery-loss scalar ---------------------------------
+ * Replaces models/yolo/detect/train.py:72,79,103,108-109 (`clean = u8.float()/255`,
+ * `dark = torch.pow(clean, p)`, `rec = F.mse_loss(dark, clean)`) and the offline writer
+ * utils/lowlight_process.py:57,68,74 (`(dark*255).astype(uint8)`, truncation).
+ *   src        n elements, uint8 (DD_SRC_U8) or fp32 in [0,1] (DD_SRC_F32)
+ *   lut256     optional 256-entry table dark = lut256[u8] (u8 source only).  NULL: the kernel fills
+ *              the table itself with powf(k/255, p) -- bit-identical to torch.pow on CUDA.  A host-
+ *              computed table makes the result bit-identical to the reference's CPU path.
+ *   clean_out  optional fp32 clean image (u8 source only; ignored for fp32 source)
+ *   dark_out   optional fp32 darkened image
+ *   dark_u8    optional truncated uint8 darkened image (offline writer)
+ *   rec_out    optional: one float, mean((dark-clean)^2) over the n elements
+ *   ws         DD_WS_SYNTH bytes (only needed when rec_out != NULL)
+ */
+int dd_synth_fwd(const void* src, int src_dtype, float p, const float* lut256, float* clean_out,
+                 float* dark_out, uint8_t* dark_u8, float* rec_out, long long n, void* ws,
+                 size_t ws_bytes, void* stream);
+
+/* ---- a4: bilinear resize to 256x256 (llie.py:43; align_corners=False, no antialias) ----------- */
+int dd_resize256(const float* x, float* r, int B, int H, int W, void* stream);
+/* adjoint of the above: dx += resize^T(dr)  (only used when the caller wants dL/dx) */
+int dd_resize256_bwd(const float* dr, float* dx, int B, int H, int W, void* stream);
+
+/* ---- a5: the parameter predictor (nn/modules/common.py:9-23,52-78) -----------------------------
+ * Weights in the reference's state-dict layout: conv_w[i] is [Cout,Cin,3,3], fc1_w [64,2048],
+ * fc2_w [15,64].  The same struct with writable pointers receives the gradients (overwritten). */
+typedef struct dd_predictor_tensors {
+    float* conv_w[5];
+    float* conv_b[5];
+    float* fc1_w;
+    float* fc1_b;
+    float* fc2_w;
+    float* fc2_b;
+} dd_predictor_tensors;
+
+/* r [B,3,256,256] -> feat [B,15]; acts: DD_WS_PREDICTOR_ACTS bytes, kept by the caller for bwd. */
+int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, float* acts, float* feat, int B,
+                     void* stream);
+/* dfeat [B,15] -> grads (all 14 tensors overwritten) and, if dr != NULL, dL/dr [B,3,256,256]. */
+int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, const float* acts,
+                     const float* dfeat, const dd_predictor_tensors* grads, float* dr, int B,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a6..a12: regressors + DeDark -> WB -> Gamma -> Contrast -> USM, one fused pass -------------
+ * Replaces the body of lowlight_recovery.forward after the predictor (llie.py:34-40,49-52;
+ * filtersB.py:32-37,144-259,289-303; util_filters.py:270-273,295-304,316-317).
+ *   x    [B,3,H,W]      A  [B,3] or NULL (=> 0.8)      IcA [B,1,H,W] or NULL (=> 0.5)
+ *   feat [B,15] raw fc2 output      y [B,3,H,W] (must not alias x)                                 */
+int dd_recovery_fwd(const float* x, const float* A, const float* IcA, const float* feat, float* y,
+                    int B, int H, int W, void* stream);
+
+/* ---- a14: backward of the fused pass ------------------------------------------------------------
+ * g = dL/dy [B,3,H,W]  ->  dfeat [B,15] (columns 1 and 5..12 are written as exact zeros) and, if
+ * dx != NULL, dL/dx through the filter chain (overwritten).  Nothing is saved by the forward: the
+ * chain is recomputed from x.  ws: DD_WS_RECOVERY_BWD bytes.  Reductions are fixed-order
+ * (deterministic; no float atomics). */
+int dd_recovery_bwd(const float* x, const float* A, const float* IcA, const float* feat,
+                    const float* g, float* dfeat, float* dx, int B, int H, int W, void* ws,
+                    size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEDARK_B200_H */
