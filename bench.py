@@ -66,7 +66,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self._sample()
             except Exception:
@@ -107,7 +107,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         if self.ok and not self.samples:
             try:

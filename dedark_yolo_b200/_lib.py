@@ -48,7 +48,7 @@ def _load():
     lib.dd_launch_count.restype = C.c_ulonglong
     lib.dd_workspace_bytes.restype = sz
     lib.dd_workspace_bytes.argtypes = [i, i, i, i]
-    lib.dd_synth_fwd.argtypes = [vp, i, f, vp, vp, vp, vp, vp, ll, vp, sz, vp]
+    lib.dd_synth_fwd.argtypes = [vp, i, f, vp, vp, vp, vp, vp, vp, ll, vp, sz, vp]
     lib.dd_resize256.argtypes = [vp, vp, i, i, i, vp]
     lib.dd_resize256_bwd.argtypes = [vp, vp, i, i, i, vp]
     lib.dd_predictor_fwd.argtypes = [vp, C.POINTER(PredictorTensors), vp, vp, i, vp]

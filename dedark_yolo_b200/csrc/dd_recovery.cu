@@ -86,12 +86,21 @@ struct RowLum {
     float lraw, lum, cl, denom, q;
 };
 
-// the rgb2lum quirk (util_filters.py:270-273 on an NCHW tensor): per (b, ch, row), from x3 at columns 0..2
+// the rgb2lum quirk (util_filters.py:270-273 on an NCHW tensor): per (b, ch, row), from x3 at columns 0..2.
+// LITERAL = the reference's expression -cos(pi lum)*0.5+0.5 (filtersB.py:301), used by the forward so that its
+// fp32 rounding matches the reference's; it cancels badly for lum << 1, so the backward (graded against the fp64
+// truth) evaluates the same quantity as sin^2(pi lum / 2).
+template <bool LITERAL>
 __device__ __forceinline__ RowLum row_lum(float x3_0, float x3_1, float x3_2) {
     RowLum r;
     r.lraw = kLumR * x3_0 + kLumG * x3_1 + kLumB * x3_2;
     r.lum = fminf(fmaxf(r.lraw, 0.f), 1.f);
-    r.cl = -cosf(kPi * r.lum) * 0.5f + 0.5f;
+    if (LITERAL) {
+        r.cl = -cosf(kPi * r.lum) * 0.5f + 0.5f;
+    } else {
+        const float sn = sinf(0.5f * kPi * r.lum);
+        r.cl = sn * sn;
+    }
     r.denom = r.lum + kContrastEps;
     r.q = r.cl / r.denom;
     return r;
@@ -181,7 +190,7 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
             const float ica = HAS_ICA ? __ldg(ip + (size_t)row * W + k) : kDefaultIcA;
             x3[k] = chain(__ldg(xp + (size_t)row * W + k), a, ica, pw, ps, pg).x3;
         }
-        const RowLum rl = row_lum(x3[0], x3[1], x3[2]);
+        const RowLum rl = row_lum<true>(x3[0], x3[1], x3[2]);
         MS[v] = (1.f - pc) + pc * rl.q;
     }
 
@@ -289,7 +298,7 @@ recovery_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
                 const float ica = HAS_ICA ? __ldg(ip + (size_t)row * W + k) : kDefaultIcA;
                 x3[k] = chain(__ldg(xp + (size_t)row * W + k), a, ica, pw, ps, pg).x3;
             }
-            const RowLum rl = row_lum(x3[0], x3[1], x3[2]);
+            const RowLum rl = row_lum<false>(x3[0], x3[1], x3[2]);
             q = rl.q;
             m = (1.f - pc) + pc * rl.q;
         }
@@ -442,7 +451,7 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
             ica[k] = HAS_ICA ? __ldg(IcA + ((size_t)b * H + row) * W + k) : kDefaultIcA;
             c[k] = chain(x0[k], a, ica[k], pw, ps, pg);
         }
-        const RowLum rl = row_lum(c[0].x3, c[1].x3, c[2].x3);
+        const RowLum rl = row_lum<false>(c[0].x3, c[1].x3, c[2].x3);
         if (rl.lraw >= 0.f && rl.lraw <= 1.f) {
             const float dq = 0.5f * kPi * sinf(kPi * rl.lum) / rl.denom - rl.cl / (rl.denom * rl.denom);
             const float glum = pc * dq * S;

@@ -16,7 +16,8 @@ from . import ops
 
 
 def preprocess_batch(batch: dict, device, dark_param: float = 15.0, lowlight_FLAG: bool = True,
-                     dedark_FLAG: bool = False, lut: Optional[torch.Tensor] = None) -> dict:
+                     dedark_FLAG: bool = False, lut: Optional[torch.Tensor] = None,
+                     clean_lut: Optional[torch.Tensor] = None) -> dict:
     """Same keys and semantics as the reference trainer hook:
 
     ``batch['img']`` uint8 NCHW  ->  ``clean_img`` (= u8/255), ``img`` (= clean ** dark_param when
@@ -28,13 +29,13 @@ def preprocess_batch(batch: dict, device, dark_param: float = 15.0, lowlight_FLA
     """
     src = batch["img"].to(device, non_blocking=True)
     if not lowlight_FLAG:
-        clean, _, _, _ = ops.synth_forward(src, 1.0, want_dark=False, want_rec=False) if src.dtype == torch.uint8 \
+        clean, _, _, _ = ops.synth_forward(src, 1.0, clean_lut=clean_lut, want_dark=False, want_rec=False) if src.dtype == torch.uint8 \
             else (src.float(), None, None, None)
         batch["clean_img"] = clean
         batch["img"] = clean
         batch["recovery_loss_batch"] = torch.zeros((), dtype=torch.float32, device=src.device)
         return batch
-    clean, dark, _, rec = ops.synth_forward(src, dark_param, lut=lut)
+    clean, dark, _, rec = ops.synth_forward(src, dark_param, lut=lut, clean_lut=clean_lut)
     if dedark_FLAG:
         batch["clean_img"] = dark
         batch["img"] = dark

@@ -37,11 +37,13 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # ---- a1 + a2 ---------------------------------------------------------------------------------------
-def synth_forward(src: torch.Tensor, p: float, lut: Optional[torch.Tensor] = None, want_clean: bool = True,
+def synth_forward(src: torch.Tensor, p: float, lut: Optional[torch.Tensor] = None,
+                  clean_lut: Optional[torch.Tensor] = None, want_clean: bool = True,
                   want_dark: bool = True, want_u8: bool = False, want_rec: bool = True):
     """Low-light synthesis + recovery-loss scalar in one pass (train.py:72,79,103,108-109).
 
-    ``src``: uint8 or float32 CUDA tensor of any shape.  Returns ``(clean, dark, dark_u8, rec)``; entries not
+    ``src``: uint8 or float32 CUDA tensor of any shape.  ``lut`` / ``clean_lut``: optional 256-entry tables that
+    override the device-computed ``pow(k/255, p)`` / ``k/255`` (see ``reference_cpu_tables``).  Returns ``(clean, dark, dark_u8, rec)``; entries not
     requested are None.  For a float32 source ``clean`` is ``src`` itself."""
     _need_cuda(src, lut)
     if src.dtype not in (torch.uint8, torch.float32):
@@ -56,16 +58,30 @@ def synth_forward(src: torch.Tensor, p: float, lut: Optional[torch.Tensor] = Non
         rec = torch.empty((), dtype=torch.float32, device=dev) if want_rec else None
         ws_bytes = _lib.workspace_bytes(_lib.WS_SYNTH, 1)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if want_rec else None
-        if lut is not None:
-            lut = _f32c(lut)
-            if lut.numel() != 256:
-                raise ValueError("lut must have 256 entries")
-        check(lib.dd_synth_fwd(_ptr(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, float(p), _ptr(lut), _ptr(clean),
+        luts = []
+        for t in (lut, clean_lut):
+            if t is not None:
+                _need_cuda(t)
+                t = _f32c(t)
+                if t.numel() != 256:
+                    raise ValueError("lookup tables must have 256 entries")
+            luts.append(t)
+        lut, clean_lut = luts
+        check(lib.dd_synth_fwd(_ptr(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, float(p), _ptr(lut), _ptr(clean_lut), _ptr(clean),
                                _ptr(dark), _ptr(dark_u8), _ptr(rec), n, _ptr(ws), ws_bytes if want_rec else 0,
                                _stream(dev)))
     if not is_u8 and want_clean:
         clean = src
     return clean, dark, dark_u8, rec
+
+
+def reference_cpu_tables(p: float, device):
+    """The reference's CPU bits for uint8-sourced data: ``clean = k / 255`` (true division) and
+    ``dark = torch.pow(clean, p)`` evaluated by torch on the host for k = 0..255 (train.py:72,79 run on CPU).
+    Pass them as ``clean_lut`` / ``lut`` to make the GPU synthesis bit-identical to a CPU run of the reference."""
+    k = torch.arange(256, dtype=torch.uint8)
+    clean = k.float() / 255
+    return torch.pow(clean, float(p)).to(device), clean.to(device)
 
 
 # ---- a4 / a5 ---------------------------------------------------------------------------------------

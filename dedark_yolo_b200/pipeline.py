@@ -63,7 +63,7 @@ class RecoveryPipeline:
     # -- individual stages (each is one C-ABI call) -------------------------------------------------------
     def synth(self, src, st):
         is_u8 = src.dtype == torch.uint8
-        check(lib.dd_synth_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, _p(self.clean) if is_u8 else None,
+        check(lib.dd_synth_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None, _p(self.clean) if is_u8 else None,
                                _p(self.dark), None, _p(self.rec), src.numel(), _p(self._ws_syn), self._ws_syn.numel(), st))
 
     def forward(self, st, A=None, IcA=None):

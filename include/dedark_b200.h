@@ -59,16 +59,19 @@ size_t dd_workspace_bytes(int kind, int B, int H, int W);
  * utils/lowlight_process.py:57,68,74 (`(dark*255).astype(uint8)`, truncation).
  *   src        n elements, uint8 (DD_SRC_U8) or fp32 in [0,1] (DD_SRC_F32)
  *   lut256     optional 256-entry table dark = lut256[u8] (u8 source only).  NULL: the kernel fills
- *              the table itself with powf(k/255, p) -- bit-identical to torch.pow on CUDA.  A host-
+ *              the table itself with powf(clean[k], p) -- bit-identical to torch.pow on CUDA.  A host-
  *              computed table makes the result bit-identical to the reference's CPU path.
+ *   clean_lut256  optional 256-entry table clean = clean_lut256[u8].  NULL: k * (1.f/255.f), which is
+ *              what `u8.float() / 255` evaluates to on CUDA (ATen multiplies by the reciprocal); the
+ *              CPU kernel performs a true division, so a host table reproduces those bits.
  *   clean_out  optional fp32 clean image (u8 source only; ignored for fp32 source)
  *   dark_out   optional fp32 darkened image
  *   dark_u8    optional truncated uint8 darkened image (offline writer)
  *   rec_out    optional: one float, mean((dark-clean)^2) over the n elements
  *   ws         DD_WS_SYNTH bytes (only needed when rec_out != NULL)
  */
-int dd_synth_fwd(const void* src, int src_dtype, float p, const float* lut256, float* clean_out,
-                 float* dark_out, uint8_t* dark_u8, float* rec_out, long long n, void* ws,
+int dd_synth_fwd(const void* src, int src_dtype, float p, const float* lut256,
+                 const float* clean_lut256, float* clean_out, float* dark_out, uint8_t* dark_u8, float* rec_out, long long n, void* ws,
                  size_t ws_bytes, void* stream);
 
 /* ---- a4: bilinear resize to 256x256 (llie.py:43; align_corners=False, no antialias) ----------- */

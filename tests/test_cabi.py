@@ -52,7 +52,7 @@ def test_shape_errors_mirror_reference_without_touching_the_gpu():
     with pytest.raises(ValueError):
         _lib.check(_lib.lib.dd_recovery_fwd(None, None, None, one, one, 1, 32, 32, None))
     with pytest.raises(ValueError):
-        _lib.check(_lib.lib.dd_synth_fwd(one, 7, 1.0, None, None, one, None, None, 16, None, 0, None))
+        _lib.check(_lib.lib.dd_synth_fwd(one, 7, 1.0, None, None, None, one, None, None, 16, None, 0, None))
     with pytest.raises(RuntimeError, match="workspace"):
         _lib.check(_lib.lib.dd_recovery_bwd(one, None, None, one, one, one, None, 1, 64, 64, one, 8, None))
     assert b"workspace" in _lib.lib.dd_last_error()
