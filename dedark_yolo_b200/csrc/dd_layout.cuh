@@ -36,38 +36,42 @@ inline size_t predictor_bwd_ws_bytes(int B) {
 }
 
 // ---- fused filter chain --------------------------------------------------------------------------
-// Work decomposition of dd_recovery_fwd/bwd: a *unit* is (image plane b*3+ch, column strip, row segment).
-constexpr int kStripW = 128;       // output columns per strip
-constexpr int kMaxSegRows = 512;   // max output rows per segment (bounds the per-CTA row-scalar table)
-constexpr int kBwdSums = 5;        // per-unit partial sums: dp, dc, dgamma, ds_ch, dw
+// Work space of dd_recovery_fwd/bwd: every (image plane b*3+ch, 128-column strip) -- a "plane-strip" -- is cut
+// into row-blocks of 32 output rows.  The N = nPS * nRB row-blocks are dealt out in contiguous, equal ranges to
+// G persistent CTAs (2 per SM); a CTA marches down consecutive row-blocks of one plane-strip without re-staging
+// the 24 halo rows, so load balance is +-1 row-block at any batch size and the halo is paid once per CTA.
+constexpr int kStripW = 128;        // output columns per strip
+constexpr int kRowBlock = 32;       // output rows per row-block
+constexpr int kMaxSegRows = 640;    // longest run marched with one row-scalar table (multiple of kRowBlock)
+constexpr int kSchedCtas = 148 * 2; // persistent CTAs (B200: 148 SMs x 2 resident CTAs)
+constexpr int kBwdSums = 5;         // partial sums per (CTA, plane-strip): dp, dc, dgamma, ds_ch, dw
 
-struct RecoveryGrid {
-    int strips;     // column strips per plane
-    int segs;       // row segments per plane
-    int seg_rows;   // rows per segment (last one may be shorter)
-    int units;      // B * 3 * strips * segs
+struct Sched {
+    int strips;    // column strips per plane
+    int nRB;       // row-blocks per plane-strip
+    int nPS;       // plane-strips = B * 3 * strips
+    int G;         // CTAs
+    long long N;   // row-blocks in total
 };
 
-inline RecoveryGrid recovery_grid(int B, int H, int W) {
-    RecoveryGrid g;
-    g.strips = (W + kStripW - 1) / kStripW;
-    // enough units to fill 148 SMs a few times over, but keep segments tall (each costs 24 halo rows)
-    int segs = 1;
-    const long long planes_strips = (long long)B * 3 * g.strips;
-    while (planes_strips * segs < 148 * 4 && (H + segs - 1) / segs > 96) ++segs;
-    while ((H + segs - 1) / segs > kMaxSegRows) ++segs;
-    g.segs = segs;
-    g.seg_rows = (H + segs - 1) / segs;
-    g.segs = (H + g.seg_rows - 1) / g.seg_rows;
-    g.units = (int)(planes_strips * g.segs);
-    return g;
+__host__ __device__ inline Sched make_sched(int B, int H, int W) {
+    Sched s;
+    s.strips = (W + kStripW - 1) / kStripW;
+    s.nRB = (H + kRowBlock - 1) / kRowBlock;
+    s.nPS = B * 3 * s.strips;
+    s.N = (long long)s.nPS * s.nRB;
+    s.G = (int)(s.N < kSchedCtas ? s.N : kSchedCtas);
+    return s;
 }
+// first row-block of CTA c (c == G gives N)
+__host__ __device__ inline long long sched_begin(const Sched& s, int c) { return s.N * c / s.G; }
 
-// backward workspace: [units][kBwdSums] floats of per-unit partial sums, then [B*3][H][strips] floats of
+// backward workspace: [G + nPS][kBwdSums] floats of partial sums -- slot (c + ps) belongs to the pair (CTA c,
+// plane-strip ps), which is injective because CTA ranges are ordered -- then [B*3][H][strips] floats of
 // per-row partial sums S (the row-coupled contrast term).
 inline size_t recovery_bwd_ws_bytes(int B, int H, int W) {
-    const RecoveryGrid g = recovery_grid(B, H, W);
-    return ((size_t)g.units * kBwdSums + (size_t)B * 3 * H * g.strips) * sizeof(float);
+    const Sched s = make_sched(B, H, W);
+    return ((size_t)(s.G + s.nPS) * kBwdSums + (size_t)B * 3 * H * s.strips) * sizeof(float);
 }
 
 }  // namespace dd
