@@ -1,0 +1,445 @@
+// dd_recovery_bwd.cu -- a14: backward of the fused filter chain.  g = dL/dy -> dfeat [B,15] (+ optional dL/dx).
+//
+// Closed form (checked against autograd): with x1..x4 the chain intermediates,
+//   g4 = g5 (1+p) - p B^T g5        dp = sum x4 (g5 - B^T g5)        dc = sum g4 x3 (q - 1)
+//   g3 = g4 m (+ row-coupled term)  dgamma = sum g3 x3 ln x2c        g2 = g3 gamma x3 / x2c [x2 >= 1e-4]
+//   ds_c = sum g2 x1                g1 = g2 s_c                      dw = sum g1 (x0 - A) IcA / tx^2 [tx >= 0.01]
+// where B^T is the ADJOINT of the reflect-padded 25x25 blur: a zero-padded correlation plus the reflect fold-back,
+// written as a gather  W(i,j) = k[j-i] + [j>=1] k[j+i] + [j<=n-2] k[2(n-1)-j-i]  (only rows/columns within 12 of the
+// image border see the extra terms).  Nothing is saved by the forward: the chain is recomputed from x.
+//
+// Same marching-strip skeleton as the forward (dd_recovery_fwd.cu), per 32-row block:
+//   0. g block n+1 streams into the 80-row ring XS with cp.async (16 B, zero-fill outside the image) while block n
+//      is processed; the x0 values of this block's output rows are prefetched into registers
+//   1. H adjoint pass (FFMA2)                                                                        -> ring HS
+//   2. V adjoint pass (FFMA2) -> B^T g5 for 32 rows x 128 columns                                   -> tile BT
+//   3. pointwise: one warp per output row (float4 per lane): chain recompute, the five parameter sums in registers,
+//      the row sum S = sum_w g4 x3 (the rgb2lum quirk couples every pixel of a row to columns 0..2) by warp shuffle.
+// Per (CTA, plane-strip) partial sums and per-row S go to the workspace; a fixed-order finalize kernel (one CTA per
+// image, no float atomics) adds them up, applies the column 0..2 fix-up and the regressor Jacobians.
+#include "dd_recovery.cuh"
+
+namespace dd {
+
+constexpr int kXRingB = 80;   // XS ring depth of the backward kernel: 32 (H pass) + 12 (lagging centre rows) + 32 in flight
+constexpr int kBP = kStripW;  // BT pitch (floats)
+constexpr int kPW4 = (kRB * kStripW / 4) / kThreads;  // float4 per thread in the pointwise phase (4)
+
+__constant__ float c_tap[13] = {DD_K0, DD_K1, DD_K2, DD_K3, DD_K4, DD_K5, DD_K6,
+                                DD_K7, DD_K8, DD_K9, DD_K10, DD_K11, DD_K12};
+
+struct BwdAcc {
+    float p, c, g, s, w;
+};
+
+// one pixel of the pointwise backward; returns dL/dx0 through the chain, adds g4*x3 to srow
+template <bool HAS_ICA, bool FAST>
+__device__ __forceinline__ float px_bwd(float x0, float ica, float g5, float bt, float m, float q1, const ChainK& ck,
+                                        float pp, BwdAcc& acc, float& srow) {
+    float inv, icaw = 0.f;
+    bool pass_tx = true;
+    const float xa = x0 - ck.a;
+    float x1;
+    if (HAS_ICA) {
+        const float tx = fmaf(-ck.w, ica, 1.f);
+        pass_tx = tx >= kTxMin;
+        const float txc = fmaxf(tx, kTxMin);
+        inv = __fdiv_rn(1.f, txc);
+        x1 = __fdiv_rn(xa, txc) + ck.a;
+        icaw = ica * inv * inv;
+    } else {
+        inv = ck.inv;
+        x1 = fmaf(xa, inv, ck.a);
+    }
+    const float x2 = x1 * ck.s;
+    const float x2c = fmaxf(x2, kGammaClamp);
+    float l2;
+    const float x3 = gamma_pow<FAST>(x2c, ck.gamma, &l2);
+    const float g4 = fmaf(g5, 1.f + pp, -pp * bt);
+    acc.p = fmaf(x3 * m, g5 - bt, acc.p);
+    const float u3 = g4 * x3;  // g4 * x3
+    srow += u3;
+    acc.c = fmaf(u3, q1, acc.c);
+    const float g3x3 = u3 * m;  // g3 * x3
+    acc.g = fmaf(g3x3, l2, acc.g);  // log2: * ln 2 applied in finalize
+    const float g2 = x2 >= kGammaClamp ? g3x3 * ck.gamma * rcp_fast(x2c) : 0.f;
+    acc.s = fmaf(g2, x1, acc.s);
+    const float g1 = g2 * ck.s;
+    // d x1 / d w = (x0 - a) * ica / txc^2   (tx = 1 - w ica, only where tx >= 0.01)
+    if (HAS_ICA) {
+        if (pass_tx) acc.w = fmaf(g1 * xa, icaw, acc.w);
+    } else {
+        acc.w = fmaf(g1, xa, acc.w);  // * ica / txc^2 applied in finalize
+    }
+    return g1 * inv;
+}
+
+template <bool HAS_ICA, bool FAST, bool ALIGNED>
+__global__ void __launch_bounds__(kThreads, 2)
+recovery_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
+                    const float* __restrict__ feat, const float* __restrict__ g, float* __restrict__ part,
+                    float* __restrict__ Spart, float* __restrict__ dx, int B, int H, int W) {
+    extern __shared__ __align__(16) float smem[];
+    float* XS = smem;                   // g, zero outside the image
+    float* HS = XS + kXRingB * kXP;
+    float* BT = HS + kHRing * kHP;      // B^T g5 for the 32 output rows of the current block
+    float* MSm = BT + kRB * kBP;        // per virtual row: m = (1-c) + c*q
+    float* MSq = MSm + kMaxU;           // per virtual row: q - 1
+    __shared__ ImgParams sp;
+    __shared__ float s_red[32];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const Sched sc = make_sched(B, H, W);
+    const long long blk_end = sched_begin(sc, blockIdx.x + 1);
+
+    BwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f};
+    int cur_ps = -1;
+    auto flush = [&]() {  // per (CTA, plane-strip) partial sums -> slot (cta + ps)
+        float* out = part + (size_t)(blockIdx.x + cur_ps) * kBwdSums;
+        float s;
+        s = block_sum<float>(acc.p, s_red); if (tid == 0) out[0] = s;
+        s = block_sum<float>(acc.c, s_red); if (tid == 0) out[1] = s;
+        s = block_sum<float>(acc.g, s_red); if (tid == 0) out[2] = s;
+        s = block_sum<float>(acc.s, s_red); if (tid == 0) out[3] = s;
+        s = block_sum<float>(acc.w, s_red); if (tid == 0) out[4] = s;
+        acc.p = acc.c = acc.g = acc.s = acc.w = 0.f;
+    };
+
+    for (long long blk = sched_begin(sc, blockIdx.x); blk < blk_end;) {
+        const Seg u = next_seg(blk, blk_end, sc, H);
+        blk += seg_blocks(u);
+        if (cur_ps >= 0 && u.ps != cur_ps) flush();
+        cur_ps = u.ps;
+        __syncthreads();
+        if (tid == 0) regress(feat + u.b * kFeat, sp);
+        __syncthreads();
+        const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
+        const float pc = sp.c, pp = sp.p;
+        const float* xp = x + (size_t)u.plane * H * W;
+        const float* gp = g + (size_t)u.plane * H * W;
+        const float* ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
+
+        // g block n -> ring XS (rows outside the image and columns outside [0, W) are zero)
+        auto stage = [&](int n) {
+#pragma unroll
+            for (int k = 0; k < kStage4; ++k) {
+                const int f = tid + k * kThreads;
+                const int rr = f / kXW4, c4 = f - rr * kXW4;
+                if (f < kRB * kXW4) {
+                    const int v = n * kRB + rr;
+                    const int row = u.r0 - kRadius + v;
+                    const int gc = u.c0 - kRadius + 4 * c4;
+                    float* dst = XS + (v % kXRingB) * kXP + 4 * c4;
+                    const bool rok = row >= 0 && row < H;
+                    if (ALIGNED) {
+                        const bool ok = rok && gc >= 0 && gc < W;
+                        cp_async16(dst, ok ? gp + (size_t)row * W + gc : gp, ok);
+                    } else {
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rok) {
+                            const float* rp = gp + (size_t)row * W;
+                            if (gc >= 0 && gc < W) t.x = __ldg(rp + gc);
+                            if (gc + 1 >= 0 && gc + 1 < W) t.y = __ldg(rp + gc + 1);
+                            if (gc + 2 >= 0 && gc + 2 < W) t.z = __ldg(rp + gc + 2);
+                            if (gc + 3 >= 0 && gc + 3 < W) t.w = __ldg(rp + gc + 3);
+                        }
+                        *reinterpret_cast<float4*>(dst) = t;
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+        stage(0);
+
+        for (int v = tid; v < u.nU; v += kThreads) {
+            const int row = u.r0 - kRadius + v;
+            float m = 0.f, q1 = 0.f;
+            if (row >= 0 && row < H) {
+                float x3[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float ica = HAS_ICA ? __ldg(ip + (size_t)row * W + k) : kDefaultIcA;
+                    x3[k] = chain_x3<HAS_ICA, FAST>(ck, __ldg(xp + (size_t)row * W + k), ica);
+                }
+                const RowLum rl = row_lum<false>(x3[0], x3[1], x3[2]);
+                q1 = rl.q - 1.f;
+                m = (1.f - pc) + pc * rl.q;
+            }
+            MSm[v] = m;
+            MSq[v] = q1;
+        }
+
+        for (int n = 0; n < u.nB; ++n) {
+            cp_async_wait_all();
+            __syncthreads();  // g block n visible; previous pointwise phase done with BT / XS centre rows / MS
+            if (n + 1 < u.nB) stage(n + 1);
+
+            {   // horizontal adjoint pass
+                const int rr = tid & 31, cg = tid >> 5;
+                const int v = n * kRB + rr;
+                const float* xrow = XS + (v % kXRingB) * kXP;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int cb = 64 * half + 8 * cg;
+                    float o[8];
+                    hpass8(xrow + cb, o);
+                    const int j0 = u.c0 + cb;  // global column of o[0]
+                    if (j0 <= kRadius || j0 + 7 >= W - 1 - kRadius) {  // reflect fold-back (image borders only)
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            const int j = j0 + t;
+                            if (j >= 1 && j <= kRadius)
+                                for (int i = 0; i <= kRadius - j; ++i) o[t] = fmaf(xrow[i - u.c0 + kRadius], c_tap[j + i], o[t]);
+                            if (j >= W - 1 - kRadius && j <= W - 2)
+                                for (int i = max(0, 2 * (W - 1) - j - kRadius); i <= W - 1; ++i)
+                                    o[t] = fmaf(xrow[i - u.c0 + kRadius], c_tap[abs(2 * (W - 1) - j - i)], o[t]);
+                        }
+                    }
+                    float4* dst = reinterpret_cast<float4*>(HS + (v & (kHRing - 1)) * kHP + cb);
+                    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                }
+            }
+            __syncthreads();
+            // prefetch x0 for this block's output rows (issued after the H pass to keep its register footprint down; consumed after the V pass)
+            float4 x0p[kPW4];
+#pragma unroll
+            for (int k = 0; k < kPW4; ++k) {
+                const int f = tid + k * kThreads;
+                const int rr = f >> 5, c4 = f & 31;
+                const int o = n * kRB - kRadius + rr;
+                const int gc = u.c0 + 4 * c4;
+                x0p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (o >= kRadius && o < kRadius + u.seg_len && gc < W) {
+                    const float* rp = xp + (size_t)(u.r0 + o - kRadius) * W + gc;
+                    if (ALIGNED) {
+                        x0p[k] = __ldg(reinterpret_cast<const float4*>(rp));
+                    } else {
+                        x0p[k].x = __ldg(rp);
+                        if (gc + 1 < W) x0p[k].y = __ldg(rp + 1);
+                        if (gc + 2 < W) x0p[k].z = __ldg(rp + 2);
+                        if (gc + 3 < W) x0p[k].w = __ldg(rp + 3);
+                    }
+                }
+            }
+
+            {   // vertical adjoint pass -> BT
+                const int col2 = 2 * (tid & 63), rg = tid >> 6;
+                const int o_first = n * kRB - kRadius + 8 * rg;
+                if (o_first >= kRadius && o_first < kRadius + u.seg_len) {
+                    u64 bt2[8];
+                    vpass8x2(HS, (o_first - kRadius) & (kHRing - 1), col2, bt2);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const int o = o_first + r;
+                        const int jr = u.r0 + o - kRadius;  // image row
+                        if (jr <= kRadius || jr >= H - 1 - kRadius) {  // reflect fold-back (top / bottom rows only)
+                            float2 bt = upk(bt2[r]);
+                            if (jr >= 1 && jr <= kRadius)
+                                for (int i = 0; i <= kRadius - jr; ++i) {
+                                    const float2 h = *reinterpret_cast<const float2*>(HS + ((i - u.r0 + kRadius) & (kHRing - 1)) * kHP + col2);
+                                    bt.x = fmaf(h.x, c_tap[jr + i], bt.x);
+                                    bt.y = fmaf(h.y, c_tap[jr + i], bt.y);
+                                }
+                            if (jr >= H - 1 - kRadius && jr <= H - 2)
+                                for (int i = max(0, 2 * (H - 1) - jr - kRadius); i <= H - 1; ++i) {
+                                    const float2 h = *reinterpret_cast<const float2*>(HS + ((i - u.r0 + kRadius) & (kHRing - 1)) * kHP + col2);
+                                    const float kk = c_tap[abs(2 * (H - 1) - jr - i)];
+                                    bt.x = fmaf(h.x, kk, bt.x);
+                                    bt.y = fmaf(h.y, kk, bt.y);
+                                }
+                            bt2[r] = pk(bt.x, bt.y);
+                        }
+                        *reinterpret_cast<u64*>(BT + (8 * rg + r) * kBP + col2) = bt2[r];
+                    }
+                }
+            }
+            __syncthreads();
+            // pointwise phase: warp <-> output row, lane <-> float4
+#pragma unroll
+            for (int k = 0; k < kPW4; ++k) {
+                const int f = tid + k * kThreads;
+                const int rr = f >> 5, c4 = f & 31;
+                const int o = n * kRB - kRadius + rr;
+                const bool row_ok = o >= kRadius && o < kRadius + u.seg_len;  // warp-uniform
+                if (!row_ok) continue;
+                const int jr = u.r0 + o - kRadius;
+                const int gc = u.c0 + 4 * c4;
+                float srow = 0.f;
+                if (gc < W) {
+                    const float4 g5 = *reinterpret_cast<const float4*>(XS + (o % kXRingB) * kXP + 4 * c4 + kRadius);
+                    const float4 bt = *reinterpret_cast<const float4*>(BT + rr * kBP + 4 * c4);
+                    const float m = MSm[o], q1 = MSq[o];
+                    const float4 x0 = x0p[k];
+                    const size_t off = (size_t)jr * W + gc;
+                    float4 ic = make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
+                    if (HAS_ICA) {
+                        ic.x = __ldg(ip + off);
+                        if (gc + 1 < W) ic.y = __ldg(ip + off + 1);
+                        if (gc + 2 < W) ic.z = __ldg(ip + off + 2);
+                        if (gc + 3 < W) ic.w = __ldg(ip + off + 3);
+                    }
+                    // columns beyond W - 1 (only when W % 4 != 0): g5 and bt are zero-padded there, but bt is not
+                    // (it is a blur of real data), so mask their cotangents explicitly
+                    const float l1 = gc + 1 < W ? 1.f : 0.f, l2 = gc + 2 < W ? 1.f : 0.f, l3 = gc + 3 < W ? 1.f : 0.f;
+                    float4 d;
+                    d.x = px_bwd<HAS_ICA, FAST>(x0.x, ic.x, g5.x, bt.x, m, q1, ck, pp, acc, srow);
+                    d.y = px_bwd<HAS_ICA, FAST>(x0.y, ic.y, g5.y * l1, bt.y * l1, m, q1, ck, pp, acc, srow);
+                    d.z = px_bwd<HAS_ICA, FAST>(x0.z, ic.z, g5.z * l2, bt.z * l2, m, q1, ck, pp, acc, srow);
+                    d.w = px_bwd<HAS_ICA, FAST>(x0.w, ic.w, g5.w * l3, bt.w * l3, m, q1, ck, pp, acc, srow);
+                    if (dx) {
+                        float* dp = dx + (size_t)u.plane * H * W + off;
+                        if (ALIGNED) {
+                            *reinterpret_cast<float4*>(dp) = d;
+                        } else {
+                            dp[0] = d.x;
+                            if (gc + 1 < W) dp[1] = d.y;
+                            if (gc + 2 < W) dp[2] = d.z;
+                            if (gc + 3 < W) dp[3] = d.w;
+                        }
+                    }
+                }
+                srow = warp_sum(srow);
+                if (lane == 0) Spart[((size_t)u.plane * H + jr) * sc.strips + u.strip] = srow;
+            }
+        }
+    }
+    if (cur_ps >= 0) flush();
+}
+
+// One CTA per image: fixed-order sum of the (CTA, plane-strip) partials, the row-coupled fix-up of columns 0..2
+// (d lum / d x3[:, :, :, 0..2]) and the regressor Jacobians -> dfeat[b, 0..14].
+template <bool HAS_ICA, bool FAST>
+__global__ void __launch_bounds__(kThreads)
+recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restrict__ A,
+                             const float* __restrict__ IcA, const float* __restrict__ feat,
+                             const float* __restrict__ part, const float* __restrict__ Spart,
+                             float* __restrict__ dfeat, float* __restrict__ dx, int B, int H, int W) {
+    __shared__ ImgParams sp;
+    __shared__ double s_red[32];
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const Sched sc = make_sched(B, H, W);
+    if (tid == 0) regress(feat + b * kFeat, sp);
+    __syncthreads();
+    const float pg = sp.gamma, pc = sp.c;
+    double dp = 0, dc = 0, dg = 0, dw = 0, ds[3] = {0, 0, 0};
+
+    // partial sums: plane-strip ps of this image was processed by CTAs c_of(first block) .. c_of(last block)
+    for (int i = tid; i < 3 * sc.strips; i += kThreads) {
+        const int ps = 3 * b * sc.strips + i;
+        const int ch = i / sc.strips;
+        const long long x0 = (long long)ps * sc.nRB, x1 = x0 + sc.nRB - 1;
+        const int c_first = (int)(((x0 + 1) * sc.G + sc.N - 1) / sc.N) - 1;
+        const int c_last = (int)(((x1 + 1) * sc.G + sc.N - 1) / sc.N) - 1;
+        // default-IcA constants folded out of the kernel's acc.w
+        const float txc = fmaxf(1.f - sp.w * kDefaultIcA, kTxMin);
+        const float wk = HAS_ICA ? 1.f : ((1.f - sp.w * kDefaultIcA >= kTxMin) ? kDefaultIcA / (txc * txc) : 0.f);
+        for (int c = c_first; c <= c_last; ++c) {
+            const float* q = part + (size_t)(c + ps) * kBwdSums;
+            dp += q[0]; dc += q[1]; dg += (double)q[2] * 0.69314718055994530942; ds[ch] += q[3]; dw += (double)q[4] * wk;
+        }
+    }
+    const float kappa[3] = {kLumR, kLumG, kLumB};
+    for (int i = tid; i < 3 * H; i += kThreads) {
+        const int ch = i / H, row = i - ch * H, plane = 3 * b + ch;
+        float S = 0.f;
+        for (int st = 0; st < sc.strips; ++st) S += Spart[((size_t)plane * H + row) * sc.strips + st];
+        const float a = A ? __ldg(A + b * 3 + ch) : kDefaultA;
+        const ChainK ck = make_chain(sp, ch, a);
+        const size_t off = ((size_t)plane * H + row) * W;
+        float x0[3], ica[3], tx[3], txc[3], x1[3], x2[3], x2c[3], x3[3], l2[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            x0[k] = __ldg(x + off + k);
+            ica[k] = HAS_ICA ? __ldg(IcA + ((size_t)b * H + row) * W + k) : kDefaultIcA;
+            tx[k] = 1.f - ck.w * ica[k];
+            txc[k] = fmaxf(tx[k], kTxMin);
+            x1[k] = (x0[k] - a) / txc[k] + a;
+            x2[k] = x1[k] * ck.s;
+            x2c[k] = fmaxf(x2[k], kGammaClamp);
+            x3[k] = gamma_pow<FAST>(x2c[k], pg, &l2[k]);
+        }
+        const RowLum rl = row_lum<false>(x3[0], x3[1], x3[2]);
+        if (rl.lraw >= 0.f && rl.lraw <= 1.f) {
+            const float dq = 0.5f * kPi * sinf(kPi * rl.lum) / rl.denom - rl.cl / (rl.denom * rl.denom);
+            const float glum = pc * dq * S;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float e3 = kappa[k] * glum;
+                dg += (double)(e3 * x3[k] * l2[k]) * 0.69314718055994530942;
+                const float e2 = x2[k] >= kGammaClamp ? e3 * pg * x3[k] / x2c[k] : 0.f;
+                ds[ch] += (double)(e2 * x1[k]);
+                const float e1 = e2 * ck.s;
+                if (tx[k] >= kTxMin) dw += (double)(e1 * (x0[k] - a) * ica[k] / (txc[k] * txc[k]));
+                if (dx) dx[off + k] += e1 / txc[k];
+            }
+        }
+    }
+    dp = block_sum<double>(dp, s_red);
+    dc = block_sum<double>(dc, s_red);
+    dg = block_sum<double>(dg, s_red);
+    dw = block_sum<double>(dw, s_red);
+    ds[0] = block_sum<double>(ds[0], s_red);
+    ds[1] = block_sum<double>(ds[1], s_red);
+    ds[2] = block_sum<double>(ds[2], s_red);
+    if (tid == 0) {
+        float* o = dfeat + b * kFeat;
+        for (int i = 0; i < kFeat; ++i) o[i] = 0.f;
+        const float* t = sp.t;
+        o[kSlotDedark] = (float)(dw * 0.45 * (1.0 - (double)t[0] * t[0]));
+        // WB: s_c = cs_c / Z, cs_j = exp(0.5 t_j), t_j = tanh(f_{1+j} m_j), m = (0,1,1)
+        const double Z = sp.Z;
+        double dot = 0.0;
+        for (int c2 = 0; c2 < 3; ++c2) dot += ds[c2] * (double)sp.cs[c2];
+        for (int j = 1; j < 3; ++j) {
+            const double dcs = ds[j] / Z - (double)kappa[j] * dot / (Z * Z);
+            o[kSlotWb + j] = (float)(dcs * (double)sp.cs[j] * 0.5 * (1.0 - (double)t[kSlotWb + j] * t[kSlotWb + j]));
+        }
+        o[kSlotGamma] = (float)(dg * (double)sp.gamma * (double)kLn3 * (1.0 - (double)t[kSlotGamma] * t[kSlotGamma]));
+        o[kSlotContrast] = (float)(dc * (1.0 - (double)t[kSlotContrast] * t[kSlotContrast]));
+        o[kSlotUsm] = (float)(dp * 2.5 * (1.0 - (double)t[kSlotUsm] * t[kSlotUsm]));
+    }
+}
+
+constexpr size_t kBwdSmem = (size_t)(kXRingB * kXP + kHRing * kHP + kRB * kBP + 2 * kMaxU) * sizeof(float);
+
+template <bool HAS_ICA, bool FAST, bool ALIGNED>
+static int launch_bwd3(const float* x, const float* A, const float* IcA, const float* feat, const float* g, float* dfeat,
+                       float* dx, int B, int H, int W, float* ws, cudaStream_t st) {
+    const Sched sc = make_sched(B, H, W);
+    float* part = ws;
+    float* Spart = part + (size_t)(sc.G + sc.nPS) * kBwdSums;
+    if (int e = set_smem(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED>, kBwdSmem)) return e;
+    recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED><<<sc.G, kThreads, kBwdSmem, st>>>(x, A, IcA, feat, g, part, Spart, dx, B, H, W);
+    recovery_bwd_finalize_kernel<HAS_ICA, FAST><<<B, kThreads, 0, st>>>(x, A, IcA, feat, part, Spart, dfeat, dx, B, H, W);
+    count_launch(2);
+    return check_launch("dd_recovery_bwd");
+}
+
+template <bool HAS_ICA, bool FAST>
+static int launch_bwd2(const float* x, const float* A, const float* IcA, const float* feat, const float* g, float* dfeat,
+                       float* dx, int B, int H, int W, float* ws, cudaStream_t st) {
+    const bool aligned = (W & 3) == 0 && (((uintptr_t)x | (uintptr_t)g | (uintptr_t)dx) & 15) == 0;
+    return aligned ? launch_bwd3<HAS_ICA, FAST, true>(x, A, IcA, feat, g, dfeat, dx, B, H, W, ws, st)
+                   : launch_bwd3<HAS_ICA, FAST, false>(x, A, IcA, feat, g, dfeat, dx, B, H, W, ws, st);
+}
+
+}  // namespace dd
+
+extern "C" int dd_recovery_bwd(const float* x, const float* A, const float* IcA, const float* feat, const float* g_,
+                               float* dfeat, float* dx, int B, int H, int W, void* ws, size_t ws_bytes,
+                               void* stream_) {
+    using namespace dd;
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (int e = check_recovery_shape("dd_recovery_bwd", B, H, W)) return e;
+    DD_REQUIRE(x && feat && g_ && dfeat, DD_ERR_INVALID, "dd_recovery_bwd: null pointer");
+    DD_REQUIRE(ws && ws_bytes >= recovery_bwd_ws_bytes(B, H, W), DD_ERR_WORKSPACE,
+               "dd_recovery_bwd: workspace %zu < %zu", ws_bytes, recovery_bwd_ws_bytes(B, H, W));
+    const bool fast = !precise_mode();
+    float* w = reinterpret_cast<float*>(ws);
+    if (IcA)
+        return fast ? launch_bwd2<true, true>(x, A, IcA, feat, g_, dfeat, dx, B, H, W, w, st)
+                    : launch_bwd2<true, false>(x, A, IcA, feat, g_, dfeat, dx, B, H, W, w, st);
+    return fast ? launch_bwd2<false, true>(x, A, nullptr, feat, g_, dfeat, dx, B, H, W, w, st)
+                : launch_bwd2<false, false>(x, A, nullptr, feat, g_, dfeat, dx, B, H, W, w, st);
+}
