@@ -203,6 +203,36 @@ __device__ __forceinline__ void vpass8x2(const float* __restrict__ HS, int base_
     }
 }
 
+// Generic 25-tap pass on packed pairs: 32 consecutive 64-bit pairs at p, p + stride, ... (stride in floats, a
+// compile-time constant so every load carries an immediate offset) -> 8 pair outputs, out[t] = sum_j k[j] P[t+j].
+// Both lanes of a pair share the tap (FFMA2 immediate).  Scatter form: a pair is consumed as soon as it is loaded.
+//   H pass of the forward: pairs = (row 2r, row 2r+1) of one column in the row-pair-interleaved ring, STRIDE = 2
+//   V pass:                pairs = (col 2c, col 2c+1) of one row in the row-major ring,               STRIDE = kHP
+template <int STRIDE>
+__device__ __forceinline__ void blur8_pairs(const float* __restrict__ p, u64 out[8]) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) out[r] = pk(0.f, 0.f);
+    if (STRIDE == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p + 2 * i);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                if (i - r >= 0 && i - r < kTaps) out[r] = fma2(q.x, pk(tapj(i - r), tapj(i - r)), out[r]);
+                if (i + 1 - r >= 0 && i + 1 - r < kTaps) out[r] = fma2(q.y, pk(tapj(i + 1 - r), tapj(i + 1 - r)), out[r]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const u64 q = *reinterpret_cast<const u64*>(p + i * STRIDE);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (i - r >= 0 && i - r < kTaps) out[r] = fma2(q, pk(tapj(i - r), tapj(i - r)), out[r]);
+        }
+    }
+}
+
 // ---- the work list of one CTA -----------------------------------------------------------------------------
 struct Seg {
     int ps, plane, b, ch, strip, r0, r1, c0, nU, nB, seg_len;

@@ -7,28 +7,34 @@
 // persistent CTAs (2 per SM, 256 threads) each own a contiguous, equal range of row-blocks and march down them:
 //   1. stage   x0 -> pointwise chain -> x4 for 32 rows x (128+24) columns.  Global loads are 128-bit and issued one
 //              block ahead (register prefetch); columns outside the image are not loaded at all -- the reflect
-//              halo is filled by mirroring the freshly computed x4 values inside shared memory.      -> ring XS
-//   2. H pass  25 taps, 8 outputs per thread from 8 LDS.128, FFMA2 with immediate taps.              -> ring HS
-//   3. V pass  25 taps, 2 columns x 8 rows per thread from 32 LDS.64, FFMA2, then y = (x4 - blur) p + x4 written
-//              with 64-bit coalesced stores.
-// The vertical halo (24 rows) is paid once per CTA range.  XS pitch 156 / HS pitch 132 floats make the 128-bit
-// shared accesses of pass 2 conflict-free (lanes map to rows).  The blur is FMA-pipe bound (50 FMA per pixel ~ 28 us
-// per 16x3x640^2 at the measured 35 TFMA/s); FFMA2 halves its issue slots so loads, MUFU and index arithmetic issue
-// in the shadow of the FMA pipe.
+//              halo is filled by mirroring the freshly computed x4 values inside shared memory.  x4 is stored with
+//              ROW PAIRS INTERLEAVED, XS2[row/2][col][row%2], so that                                -> ring XS2
+//   2. H pass  pairs (row 2r, row 2r+1) of one column are aligned 64-bit operands: every FFMA2 of the 25-tap pass
+//              takes its operand straight from an LDS.128 and the tap as an immediate (no shifted operand pairs).
+//              Thread = 2 rows x 8 columns, 16 LDS.128, 200 FFMA2.                                    -> ring HS
+//   3. V pass  row-major HS, pairs (col 2c, col 2c+1): thread = 2 columns x 8 rows, 32 LDS.64 with immediate offsets
+//              (the first 24 ring rows are stored twice so a 32-row window never wraps), 200 FFMA2, then
+//              y = (x4 - blur) p + x4 with 64-bit coalesced streaming stores.
+// The vertical halo (24 rows) is paid once per CTA range.  The blur is FMA-pipe bound (50 FMA per pixel ~ 28 us per
+// 16x3x640^2 at the measured 35 TFMA/s); FFMA2 halves its issue slots so loads, MUFU and index arithmetic issue in the
+// shadow of the FMA pipe.
 #include "dd_recovery.cuh"
 
 namespace dd {
 
-constexpr int kXRingF = 64;  // XS ring depth of the forward kernel (rows), power of two
+constexpr int kPairs = 32;              // XS2 ring depth in row pairs (64 rows)
+constexpr int kXP2 = 308;               // XS2 pitch (floats per row pair): 2*152 + 4, (kXP2/4) odd -> conflict-free LDS.128
+constexpr int kHRows = kHRing + 24;     // HS rows: 64-row ring + the first 24 rows mirrored behind it
+constexpr int kStage2 = (16 * kXW4 + kThreads - 1) / kThreads;  // (row pair, float4 column) items per thread per block (3)
 
 template <bool HAS_ICA, bool FAST, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads, 2)
 recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
                     const float* __restrict__ feat, float* __restrict__ y, int B, int H, int W) {
     extern __shared__ __align__(16) float smem[];
-    float* XS = smem;
-    float* HS = XS + kXRingF * kXP;
-    float* MS = HS + kHRing * kHP;  // per virtual row: m = (1-c) + c*q
+    float* XS2 = smem;
+    float* HS = XS2 + kPairs * kXP2;
+    float* MS = HS + kHRows * kHP;  // per virtual row: m = (1-c) + c*q
     __shared__ ImgParams sp;
 
     const int tid = threadIdx.x;
@@ -61,28 +67,33 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
             MS[v] = (1.f - pc) + pc * rl.q;
         }
 
-        float4 pre[kStage4], prei[kStage4];
+        // item (k) of a thread: row pair rp (2 rows) x float4 column c4; fixed across blocks
+        float4 pre[kStage2][2], prei[kStage2][2];
         auto stage = [&](int n) {
 #pragma unroll
-            for (int k = 0; k < kStage4; ++k) {
+            for (int k = 0; k < kStage2; ++k) {
                 const int f = tid + k * kThreads;
-                const int rr = f / kXW4, c4 = f - rr * kXW4;
-                const int v = n * kRB + rr;
+                const int rp = f / kXW4, c4 = f - rp * kXW4;
+                const int v0 = n * kRB + 2 * rp;
                 const int gc = u.c0 - kRadius + 4 * c4;
-                if (f < kRB * kXW4 && v < u.nU) {
-                    const size_t ro = (size_t)reflect(u.r0 - kRadius + v, H) * W;
-                    if (ALIGNED) {
-                        if (gc >= 0 && gc < W) {
-                            pre[k] = __ldg(reinterpret_cast<const float4*>(xp + ro + gc));
-                            if (HAS_ICA) prei[k] = __ldg(reinterpret_cast<const float4*>(ip + ro + gc));
-                        }
-                    } else {
-                        int g[4];
+                if (f < 16 * kXW4 && v0 < u.nU) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) g[e] = min(max(reflect(gc + e, W), 0), W - 1);
-                        pre[k] = make_float4(__ldg(xp + ro + g[0]), __ldg(xp + ro + g[1]), __ldg(xp + ro + g[2]), __ldg(xp + ro + g[3]));
-                        if (HAS_ICA)
-                            prei[k] = make_float4(__ldg(ip + ro + g[0]), __ldg(ip + ro + g[1]), __ldg(ip + ro + g[2]), __ldg(ip + ro + g[3]));
+                    for (int e = 0; e < 2; ++e) {
+                        const int row = min(max(reflect(u.r0 - kRadius + v0 + e, H), 0), H - 1);
+                        const size_t ro = (size_t)row * W;
+                        if (ALIGNED) {
+                            if (gc >= 0 && gc < W) {
+                                pre[k][e] = __ldg(reinterpret_cast<const float4*>(xp + ro + gc));
+                                if (HAS_ICA) prei[k][e] = __ldg(reinterpret_cast<const float4*>(ip + ro + gc));
+                            }
+                        } else {
+                            int g[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) g[i] = min(max(reflect(gc + i, W), 0), W - 1);
+                            pre[k][e] = make_float4(__ldg(xp + ro + g[0]), __ldg(xp + ro + g[1]), __ldg(xp + ro + g[2]), __ldg(xp + ro + g[3]));
+                            if (HAS_ICA)
+                                prei[k][e] = make_float4(__ldg(ip + ro + g[0]), __ldg(ip + ro + g[1]), __ldg(ip + ro + g[2]), __ldg(ip + ro + g[3]));
+                        }
                     }
                 }
             }
@@ -92,37 +103,44 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
         for (int n = 0; n < u.nB; ++n) {
             __syncthreads();  // MS ready (n == 0); ring slots of block n no longer read by the previous V pass
 #pragma unroll
-            for (int k = 0; k < kStage4; ++k) {
+            for (int k = 0; k < kStage2; ++k) {
                 const int f = tid + k * kThreads;
-                const int rr = f / kXW4, c4 = f - rr * kXW4;
-                const int v = n * kRB + rr;
+                const int rp = f / kXW4, c4 = f - rp * kXW4;
+                const int v0 = n * kRB + 2 * rp;
                 const int gc = u.c0 - kRadius + 4 * c4;
-                if (f < kRB * kXW4 && v < u.nU && (!ALIGNED || (gc >= 0 && gc < W))) {
-                    const float m = MS[v];
-                    const float4 in = pre[k];
-                    const float4 ic = HAS_ICA ? prei[k] : make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
-                    float o[4];
-                    o[0] = chain_x3<HAS_ICA, FAST>(ck, in.x, ic.x) * m;
-                    o[1] = chain_x3<HAS_ICA, FAST>(ck, in.y, ic.y) * m;
-                    o[2] = chain_x3<HAS_ICA, FAST>(ck, in.z, ic.z) * m;
-                    o[3] = chain_x3<HAS_ICA, FAST>(ck, in.w, ic.w) * m;
-                    float* xrow = XS + (v & (kXRingF - 1)) * kXP;
-                    *reinterpret_cast<float4*>(xrow + 4 * c4) = make_float4(o[0], o[1], o[2], o[3]);
+                if (f < 16 * kXW4 && v0 < u.nU && (!ALIGNED || (gc >= 0 && gc < W))) {
+                    float o[2][4];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float m = MS[min(v0 + e, u.nU - 1)];
+                        const float4 in = pre[k][e];
+                        const float4 ic = HAS_ICA ? prei[k][e] : make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
+                        o[e][0] = chain_x3<HAS_ICA, FAST>(ck, in.x, ic.x) * m;
+                        o[e][1] = chain_x3<HAS_ICA, FAST>(ck, in.y, ic.y) * m;
+                        o[e][2] = chain_x3<HAS_ICA, FAST>(ck, in.z, ic.z) * m;
+                        o[e][3] = chain_x3<HAS_ICA, FAST>(ck, in.w, ic.w) * m;
+                    }
+                    float* xrow = XS2 + ((v0 >> 1) & (kPairs - 1)) * kXP2;  // element (row e, staged col c) at xrow[2c + e]
+                    float4* dst = reinterpret_cast<float4*>(xrow + 8 * c4);
+                    dst[0] = make_float4(o[0][0], o[1][0], o[0][1], o[1][1]);
+                    dst[1] = make_float4(o[0][2], o[1][2], o[0][3], o[1][3]);
                     if (ALIGNED) {
                         // reflect halo (F.pad mode='reflect', filtersB.py:167): image col -j <- j, L+d <- L-d
                         if (gc <= kRadius) {  // only strip 0 has image columns 0..12 at gc <= 12
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int j = gc + e;
-                                if (j >= 1 && j <= kRadius) xrow[kRadius - j - u.c0] = o[e];
+                            for (int i = 0; i < 4; ++i) {
+                                const int j = gc + i;
+                                if (j >= 1 && j <= kRadius)
+                                    *reinterpret_cast<float2*>(xrow + 2 * (kRadius - j - u.c0)) = make_float2(o[0][i], o[1][i]);
                             }
                         }
                         if (gc + 3 >= L - kRadius) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int d = L - (gc + e);
+                            for (int i = 0; i < 4; ++i) {
+                                const int d = L - (gc + i);
                                 const int tc = L + d - u.c0 + kRadius;
-                                if (d >= 1 && d <= kRadius && tc < kXW) xrow[tc] = o[e];
+                                if (d >= 1 && d <= kRadius && tc < kXW)
+                                    *reinterpret_cast<float2*>(xrow + 2 * tc) = make_float2(o[0][i], o[1][i]);
                             }
                         }
                     }
@@ -130,41 +148,65 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
             }
             if (n + 1 < u.nB) stage(n + 1);
             __syncthreads();
-            {   // horizontal pass: lanes -> rows, each thread two groups of 8 columns
-                const int rr = tid & 31, cg = tid >> 5;
-                const int slot = (n * kRB + rr) & (kXRingF - 1);
+            {   // horizontal pass: thread = row pair x 8 columns; lanes 0..15 -> row pairs
+                const int rp = tid & 15, cg = tid >> 4;
+                const int v0 = n * kRB + 2 * rp;
+                u64 acc[8];
+                blur8_pairs<2>(XS2 + ((v0 >> 1) & (kPairs - 1)) * kXP2 + 16 * cg, acc);
+                float lo[8], hi[8];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int cb = 64 * half + 8 * cg;
-                    float o[8];
-                    hpass8(XS + slot * kXP + cb, o);
-                    float4* dst = reinterpret_cast<float4*>(HS + ((n * kRB + rr) & (kHRing - 1)) * kHP + cb);
-                    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                for (int t = 0; t < 8; ++t) {
+                    const float2 a = upk(acc[t]);
+                    lo[t] = a.x;
+                    hi[t] = a.y;
+                }
+                const int s0 = v0 & (kHRing - 1);  // even; rows s0, s0 + 1
+                float* h0 = HS + s0 * kHP + 8 * cg;
+                *reinterpret_cast<float4*>(h0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4*>(h0 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                *reinterpret_cast<float4*>(h0 + kHP) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(h0 + kHP + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                if (s0 < 24) {  // mirrored copy behind the ring: a 32-row window starting at slot <= 56 never wraps
+                    float* h1 = h0 + kHRing * kHP;
+                    *reinterpret_cast<float4*>(h1) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<float4*>(h1 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                    *reinterpret_cast<float4*>(h1 + kHP) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(h1 + kHP + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
                 }
             }
             __syncthreads();
             {   // vertical pass + USM epilogue: lanes -> column pairs, 8 rows per thread
                 const int col2 = 2 * (tid & 63), rg = tid >> 6;
-                const int o_first = n * kRB - kRadius + 8 * rg;  // virtual row of the first output
+                const int o_first = n * kRB - kRadius + 8 * rg;  // virtual row of the first output (even)
                 if (o_first >= kRadius && o_first < kRadius + u.seg_len) {
                     u64 bl[8];
-                    vpass8x2(HS, (o_first - kRadius) & (kHRing - 1), col2, bl);
+                    blur8_pairs<kHP>(HS + ((o_first - kRadius) & (kHRing - 1)) * kHP + col2, bl);
                     const int gc = u.c0 + col2;
-                    const u64 p2 = pk(pp, pp), m1 = pk(-1.f, -1.f);
+                    if (gc < W) {
+                        const u64 p2 = pk(pp, pp), m1 = pk(-1.f, -1.f);
+                        float* drow = yp + (size_t)(u.r0 + o_first - kRadius) * W + gc;
+                        const int rows_left = kRadius + u.seg_len - o_first;  // >= 1
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const int o = o_first + r;
-                        if (o < kRadius + u.seg_len && gc < W) {
-                            const u64 x4 = *reinterpret_cast<const u64*>(XS + (o & (kXRingF - 1)) * kXP + col2 + kRadius);
-                            const u64 yv = fma2(fma2(bl[r], m1, x4), p2, x4);  // (x4 - blur) * p + x4
-                            float* dst = yp + (size_t)(u.r0 + o - kRadius) * W + gc;
+                        for (int r = 0; r < 8; r += 2) {
+                            // centre x4 of rows (o, o+1), columns (c, c+1): one LDS.128 from the interleaved ring
+                            const float4 c4v = *reinterpret_cast<const float4*>(
+                                XS2 + (((o_first + r) >> 1) & (kPairs - 1)) * kXP2 + 2 * (col2 + kRadius));
+                            const u64 xa = pk(c4v.x, c4v.z), xb = pk(c4v.y, c4v.w);
+                            const u64 ya = fma2(fma2(bl[r], m1, xa), p2, xa);      // (x4 - blur) * p + x4
+                            const u64 yb = fma2(fma2(bl[r + 1], m1, xb), p2, xb);
                             if (w2) {
-                                __stcs(reinterpret_cast<float2*>(dst), upk(yv));
+                                if (r < rows_left) __stcs(reinterpret_cast<float2*>(drow + (size_t)r * W), upk(ya));
+                                if (r + 1 < rows_left) __stcs(reinterpret_cast<float2*>(drow + (size_t)(r + 1) * W), upk(yb));
                             } else {
-                                const float2 t = upk(yv);
-                                dst[0] = t.x;
-                                if (gc + 1 < W) dst[1] = t.y;
+                                const float2 ta = upk(ya), tb = upk(yb);
+                                if (r < rows_left) {
+                                    drow[(size_t)r * W] = ta.x;
+                                    if (gc + 1 < W) drow[(size_t)r * W + 1] = ta.y;
+                                }
+                                if (r + 1 < rows_left) {
+                                    drow[(size_t)(r + 1) * W] = tb.x;
+                                    if (gc + 1 < W) drow[(size_t)(r + 1) * W + 1] = tb.y;
+                                }
                             }
                         }
                     }
@@ -174,7 +216,7 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
     }
 }
 
-constexpr size_t kFwdSmem = (size_t)(kXRingF * kXP + kHRing * kHP + kMaxU) * sizeof(float);
+constexpr size_t kFwdSmem = (size_t)(kPairs * kXP2 + kHRows * kHP + kMaxU) * sizeof(float);
 
 template <bool HAS_ICA, bool FAST, bool ALIGNED>
 static int launch_fwd3(const float* x, const float* A, const float* IcA, const float* feat, float* y, int B, int H,
