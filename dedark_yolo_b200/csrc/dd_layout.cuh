@@ -30,9 +30,10 @@ inline size_t predictor_acts_bytes(int B) { return predictor_acts_elems(B) * siz
 // backward scratch: gradients w.r.t. the pre-activations of every layer (same layout as acts) followed by
 // the split-K partial buffer of the weight-gradient kernels.
 constexpr int kWgradMaxSplit = 32;
-constexpr size_t kWgradPartialElems = (size_t)kWgradMaxSplit * (32 * 32 * 9 + 32);
+// per image: the largest slice set of the tiled weight-gradient kernels is conv2's, 32 tiles x (32*16*9 + 32) sums
+constexpr size_t kWgradPartialElemsPerImage = (size_t)32 * (32 * 16 * 9 + 32);
 inline size_t predictor_bwd_ws_bytes(int B) {
-    return (predictor_acts_elems(B) + kWgradPartialElems) * sizeof(float);
+    return (predictor_acts_elems(B) + kWgradPartialElemsPerImage * B) * sizeof(float);
 }
 
 // ---- fused filter chain --------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 // reductions are fixed-order (per-thread serial loops, block_sum, split partials summed in index
 // order): bit-reproducible run to run.
 #include "dd_common.cuh"
+#include "dd_conv_tiled.cuh"
 #include "dd_layout.cuh"
 
 namespace dd {
@@ -88,9 +89,11 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const
     constexpr int PXG = HO * HO / PX;   // pixel groups per image
     constexpr int COG = COUT / CO_T;    // channel groups
     __shared__ __align__(16) float sw[CIN * 9 * COUT];
+    // w is [co][ci][kh][kw]; co runs fastest over the lanes so the shared-memory writes are conflict-free (the
+    // strided global reads come out of L2)
     for (int i = threadIdx.x; i < CIN * 9 * COUT; i += blockDim.x) {
-        const int co = i / (CIN * 9), rem = i % (CIN * 9);  // w is [co][ci][kh][kw]
-        sw[rem * COUT + co] = w[i];
+        const int co = i % COUT, rem = i / COUT;
+        sw[i] = __ldg(w + co * (CIN * 9) + rem);
     }
     __syncthreads();
     const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,9 +165,9 @@ conv_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, c
     constexpr int HO = HIN / 2;
     constexpr int CIG = CIN / CI_T;
     __shared__ float sw[COUT * 9 * CIN];  // [co][k][ci]
-    for (int i = threadIdx.x; i < COUT * 9 * CIN; i += blockDim.x) {
-        const int co = i / (CIN * 9), rem = i % (CIN * 9), ci = rem / 9, k = rem % 9;
-        sw[(co * 9 + k) * CIN + ci] = w[i];
+    for (int i = threadIdx.x; i < COUT * 9 * CIN; i += blockDim.x) {  // ci fastest: conflict-free smem writes
+        const int ci = i % CIN, t = i / CIN, k = t % 9, co = t / 9;
+        sw[i] = __ldg(w + (co * CIN + ci) * 9 + k);
     }
     __syncthreads();
     const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,14 +283,34 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dpre, 
     }
 }
 
-__global__ void __launch_bounds__(256)
+// sum of the slices of a partial buffer [split][nw + nb]: block = 32 consecutive outputs x 32 warps; warp w adds the
+// slices s = w, w + 32, ... (4 loads in flight), then the 32 per-warp sums are added in index order: deterministic.
+__global__ void __launch_bounds__(1024)
 wgrad_reduce_kernel(const float* __restrict__ partial, int split, int nw, int nb, float* __restrict__ dw,
                     float* __restrict__ db) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nw + nb) return;
-    float a = 0.f;
-    for (int s = 0; s < split; ++s) a += partial[(size_t)s * (nw + nb) + i];
-    if (i < nw) dw[i] = a; else db[i - nw] = a;
+    __shared__ float s_part[32][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const size_t stride = (size_t)(nw + nb);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (i < nw + nb) {
+        int s = wid;
+        for (; s + 96 < split; s += 128) {
+            a0 += __ldg(partial + (size_t)s * stride + i);
+            a1 += __ldg(partial + (size_t)(s + 32) * stride + i);
+            a2 += __ldg(partial + (size_t)(s + 64) * stride + i);
+            a3 += __ldg(partial + (size_t)(s + 96) * stride + i);
+        }
+        for (; s < split; s += 32) a0 += __ldg(partial + (size_t)s * stride + i);
+    }
+    s_part[wid][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (wid == 0 && i < nw + nb) {
+        float r = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r += s_part[k][lane];
+        if (i < nw) dw[i] = r; else db[i - nw] = r;
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -408,8 +431,47 @@ static void launch_conv_wgrad(const float* in, const float* dpre, float* partial
     split = split < 1 ? 1 : (split > kWgradMaxSplit ? kWgradMaxSplit : split);
     dim3 grid((COUT / 4) * CIN, split);
     conv_wgrad_kernel<CIN, COUT, HIN><<<grid, 256, 0, st>>>(in, dpre, partial, B, split);
-    wgrad_reduce_kernel<<<(NW + COUT + 255) / 256, 256, 0, st>>>(partial, split, NW, COUT, dw, db);
+    wgrad_reduce_kernel<<<(NW + COUT + 31) / 32, 1024, 0, st>>>(partial, split, NW, COUT, dw, db);
     count_launch(2);
+}
+
+// ---- tiled kernels (dd_conv_tiled.cuh) -----------------------------------------------------------
+template <int CIN, int COUT, int HIN, int TH, int TW, int CICH, int PY>
+static void launch_fwd_tiled(const float* in, const float* w, const float* b, float* out, int B, cudaStream_t st) {
+    constexpr int HO = HIN / 2;
+    constexpr size_t smem = conv_fwd_smem<CIN, COUT, TH, TW, CICH>();
+    cudaFuncSetAttribute(conv_fwd_tiled<CIN, COUT, HIN, TH, TW, CICH, PY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    conv_fwd_tiled<CIN, COUT, HIN, TH, TW, CICH, PY>
+        <<<B * (HO / TH) * (HO / TW), TW * (TH / PY) * (COUT / 8), smem, st>>>(in, w, b, out);
+    count_launch();
+}
+
+template <int CIN, int COUT, int HIN, int TQH, int TQW, int COCH, int QY>
+static void launch_dgrad_tiled(const float* dpre, const float* w, const float* act_in, float* din, int B, cudaStream_t st) {
+    constexpr int HO = HIN / 2;
+    constexpr size_t smem = conv_dgrad_smem<CIN, COUT, TQH, TQW, COCH>();
+    cudaFuncSetAttribute(conv_dgrad_tiled<CIN, COUT, HIN, TQH, TQW, COCH, QY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    conv_dgrad_tiled<CIN, COUT, HIN, TQH, TQW, COCH, QY>
+        <<<B * (HO / TQH) * (HO / TQW), TQW * (TQH / QY) * (CIN / 8), smem, st>>>(dpre, w, act_in, din);
+    count_launch();
+}
+
+template <int CIN, int COUT, int HIN, int TH, int TW, int CO_T>
+static int launch_wgrad_tiled(const float* in, const float* dpre, float* partial, float* dw, float* db, int B,
+                              cudaStream_t st) {
+    constexpr int HO = HIN / 2, NW = COUT * CIN * 9;
+    constexpr size_t smem = (size_t)(CIN * InTile<TH, TW>::PLANE + COUT * TH * TW) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tiled<CIN, COUT, HIN, TH, TW, CO_T>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(conv_wgrad_tiled): %s", cudaGetErrorString(e));
+        return DD_ERR_CUDA;
+    }
+    const int slices = B * (HO / TH) * (HO / TW);
+    conv_wgrad_tiled<CIN, COUT, HIN, TH, TW, CO_T><<<slices, CIN * (COUT / CO_T), smem, st>>>(in, dpre, partial);
+    wgrad_reduce_kernel<<<(NW + COUT + 31) / 32, 1024, 0, st>>>(partial, slices, NW, COUT, dw, db);
+    count_launch(2);
+    return DD_OK;
 }
 
 static bool tensors_ok(const dd_predictor_tensors* t) {
@@ -448,11 +510,11 @@ extern "C" int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, f
     DD_REQUIRE(r && acts && feat && B > 0 && tensors_ok(w), DD_ERR_INVALID, "dd_predictor_fwd: bad arguments");
     float* a[6];
     for (int l = 0; l < 6; ++l) a[l] = acts + pred_act_offset(l, B);
-    launch_conv_fwd<3, 16, 256, 2, 16>(r, w->conv_w[0], w->conv_b[0], a[0], B, st);
-    launch_conv_fwd<16, 32, 128, 2, 16>(a[0], w->conv_w[1], w->conv_b[1], a[1], B, st);
-    launch_conv_fwd<32, 32, 64, 1, 8>(a[1], w->conv_w[2], w->conv_b[2], a[2], B, st);
-    launch_conv_fwd<32, 32, 32, 1, 8>(a[2], w->conv_w[3], w->conv_b[3], a[3], B, st);
-    launch_conv_fwd<32, 32, 16, 1, 4>(a[3], w->conv_w[4], w->conv_b[4], a[4], B, st);
+    launch_fwd_tiled<3, 16, 256, 16, 32, 3, 4>(r, w->conv_w[0], w->conv_b[0], a[0], B, st);
+    launch_fwd_tiled<16, 32, 128, 8, 32, 8, 4>(a[0], w->conv_w[1], w->conv_b[1], a[1], B, st);
+    launch_fwd_tiled<32, 32, 64, 4, 32, 8, 2>(a[1], w->conv_w[2], w->conv_b[2], a[2], B, st);
+    launch_fwd_tiled<32, 32, 32, 4, 16, 8, 1>(a[2], w->conv_w[3], w->conv_b[3], a[3], B, st);
+    launch_fwd_tiled<32, 32, 16, 8, 8, 8, 1>(a[3], w->conv_w[4], w->conv_b[4], a[4], B, st);
     fc1_fwd_kernel<<<(B * kFc1Out * 32 + 255) / 256, 256, 0, st>>>(a[4], w->fc1_w, w->fc1_b, a[5], B);
     fc2_fwd_kernel<<<(B * kFeat + 255) / 256, 256, 0, st>>>(a[5], w->fc2_w, w->fc2_b, feat, B);
     count_launch(2);
@@ -481,15 +543,20 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     fc1_dgrad_kernel<<<(B * kFc1In + 255) / 256, 256, 0, st>>>(d[5], w->fc1_w, a[4], d[4], B);
     count_launch(3);
     // conv5 .. conv1: weight gradient from (input act, dpre), then data gradient into the previous layer
-    launch_conv_wgrad<32, 32, 16>(a[3], d[4], partial, g->conv_w[4], g->conv_b[4], B, st);
-    launch_conv_dgrad<32, 32, 16, 8>(d[4], w->conv_w[4], a[3], d[3], B, st);
-    launch_conv_wgrad<32, 32, 32>(a[2], d[3], partial, g->conv_w[3], g->conv_b[3], B, st);
-    launch_conv_dgrad<32, 32, 32, 8>(d[3], w->conv_w[3], a[2], d[2], B, st);
-    launch_conv_wgrad<32, 32, 64>(a[1], d[2], partial, g->conv_w[2], g->conv_b[2], B, st);
-    launch_conv_dgrad<32, 32, 64, 8>(d[2], w->conv_w[2], a[1], d[1], B, st);
-    launch_conv_wgrad<16, 32, 128>(a[0], d[1], partial, g->conv_w[1], g->conv_b[1], B, st);
-    launch_conv_dgrad<16, 32, 128, 8>(d[1], w->conv_w[1], a[0], d[0], B, st);
-    launch_conv_wgrad<3, 16, 256>(r, d[0], partial, g->conv_w[0], g->conv_b[0], B, st);
+    if (int e = launch_wgrad_tiled<32, 32, 16, 8, 8, 4>(a[3], d[4], partial, g->conv_w[4], g->conv_b[4], B, st)) return e;
+    launch_dgrad_tiled<32, 32, 16, 8, 8, 8, 1>(d[4], w->conv_w[4], a[3], d[3], B, st);
+    if (int e = launch_wgrad_tiled<32, 32, 32, 4, 16, 4>(a[2], d[3], partial, g->conv_w[3], g->conv_b[3], B, st)) return e;
+    launch_dgrad_tiled<32, 32, 32, 4, 16, 8, 1>(d[3], w->conv_w[3], a[2], d[2], B, st);
+    if (int e = launch_wgrad_tiled<32, 32, 64, 4, 32, 4>(a[1], d[2], partial, g->conv_w[2], g->conv_b[2], B, st)) return e;
+    launch_dgrad_tiled<32, 32, 64, 4, 32, 8, 2>(d[2], w->conv_w[2], a[1], d[1], B, st);
+    if (int e = launch_wgrad_tiled<16, 32, 128, 4, 32, 2>(a[0], d[1], partial, g->conv_w[1], g->conv_b[1], B, st)) return e;
+    launch_dgrad_tiled<16, 32, 128, 8, 32, 8, 2>(d[1], w->conv_w[1], a[0], d[0], B, st);
+    {   // first layer (CIN = 3): position-parallel weight gradient
+        constexpr int slices_per_img = (128 / 8) * (128 / 32);
+        conv_wgrad_tiled_c3<16, 256, 8, 32><<<B * slices_per_img, 32 * 8, 0, st>>>(r, d[0], partial);
+        wgrad_reduce_kernel<<<(432 + 16 + 31) / 32, 1024, 0, st>>>(partial, B * slices_per_img, 432, 16, g->conv_w[0], g->conv_b[0]);
+        count_launch(2);
+    }
     if (dr) launch_conv_dgrad<3, 16, 256, 3>(d[0], w->conv_w[0], nullptr, dr, B, st);
     return check_launch("dd_predictor_bwd");
 }
