@@ -55,13 +55,13 @@ struct Sched {
     long long N;   // row-blocks in total
 };
 
-__host__ __device__ inline Sched make_sched(int B, int H, int W) {
+__host__ __device__ inline Sched make_sched(int B, int H, int W, int ctas = kSchedCtas) {
     Sched s;
     s.strips = (W + kStripW - 1) / kStripW;
     s.nRB = (H + kRowBlock - 1) / kRowBlock;
     s.nPS = B * 3 * s.strips;
     s.N = (long long)s.nPS * s.nRB;
-    s.G = (int)(s.N < kSchedCtas ? s.N : kSchedCtas);
+    s.G = (int)(s.N < ctas ? s.N : ctas);
     return s;
 }
 // first row-block of CTA c (c == G gives N)

@@ -63,6 +63,12 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
     const int sz = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "r"(sz) : "memory");
 }
+// 4-byte variant (any alignment); used where the shared-memory layout interleaves rows
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem_src), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 

@@ -28,6 +28,37 @@ constexpr int kPW4 = (kRB * kStripW / 4) / kThreads;  // float4 per thread in th
 __constant__ float c_tap[13] = {DD_K0, DD_K1, DD_K2, DD_K3, DD_K4, DD_K5, DD_K6,
                                 DD_K7, DD_K8, DD_K9, DD_K10, DD_K11, DD_K12};
 
+// Reflect fold-back of the adjoint blur, W(i,j) = k[j-i] + [j>=1] k[j+i] + [j<=n-2] k[2(n-1)-j-i]: the extra two terms,
+// only for outputs within 12 of an image border.  Kept out of line so the hot loop stays small (instruction cache).
+__device__ __noinline__ void hfold8(float* o, const float* __restrict__ xrow, int j0, int c0, int W) {
+    for (int t = 0; t < 8; ++t) {
+        const int j = j0 + t;
+        float a = o[t];
+        if (j >= 1 && j <= kRadius)
+            for (int i = 0; i <= kRadius - j; ++i) a = fmaf(xrow[i - c0 + kRadius], c_tap[j + i], a);
+        if (j >= W - 1 - kRadius && j <= W - 2)
+            for (int i = max(0, 2 * (W - 1) - j - kRadius); i <= W - 1; ++i)
+                a = fmaf(xrow[i - c0 + kRadius], c_tap[abs(2 * (W - 1) - j - i)], a);
+        o[t] = a;
+    }
+}
+__device__ __noinline__ float2 vfold(float2 bt, const float* __restrict__ HS, int col2, int jr, int r0, int H) {
+    if (jr >= 1 && jr <= kRadius)
+        for (int i = 0; i <= kRadius - jr; ++i) {
+            const float2 h = *reinterpret_cast<const float2*>(HS + ((i - r0 + kRadius) & (kHRing - 1)) * kHP + col2);
+            bt.x = fmaf(h.x, c_tap[jr + i], bt.x);
+            bt.y = fmaf(h.y, c_tap[jr + i], bt.y);
+        }
+    if (jr >= H - 1 - kRadius && jr <= H - 2)
+        for (int i = max(0, 2 * (H - 1) - jr - kRadius); i <= H - 1; ++i) {
+            const float2 h = *reinterpret_cast<const float2*>(HS + ((i - r0 + kRadius) & (kHRing - 1)) * kHP + col2);
+            const float kk = c_tap[abs(2 * (H - 1) - jr - i)];
+            bt.x = fmaf(h.x, kk, bt.x);
+            bt.y = fmaf(h.y, kk, bt.y);
+        }
+    return bt;
+}
+
 struct BwdAcc {
     float p, c, g, s, w;
 };
@@ -178,22 +209,19 @@ recovery_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
                 const int rr = tid & 31, cg = tid >> 5;
                 const int v = n * kRB + rr;
                 const float* xrow = XS + (v % kXRingB) * kXP;
-#pragma unroll
+#pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     const int cb = 64 * half + 8 * cg;
                     float o[8];
                     hpass8(xrow + cb, o);
                     const int j0 = u.c0 + cb;  // global column of o[0]
                     if (j0 <= kRadius || j0 + 7 >= W - 1 - kRadius) {  // reflect fold-back (image borders only)
+                        float tmp[8];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const int j = j0 + t;
-                            if (j >= 1 && j <= kRadius)
-                                for (int i = 0; i <= kRadius - j; ++i) o[t] = fmaf(xrow[i - u.c0 + kRadius], c_tap[j + i], o[t]);
-                            if (j >= W - 1 - kRadius && j <= W - 2)
-                                for (int i = max(0, 2 * (W - 1) - j - kRadius); i <= W - 1; ++i)
-                                    o[t] = fmaf(xrow[i - u.c0 + kRadius], c_tap[abs(2 * (W - 1) - j - i)], o[t]);
-                        }
+                        for (int t = 0; t < 8; ++t) tmp[t] = o[t];
+                        hfold8(tmp, xrow, j0, u.c0, W);
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) o[t] = tmp[t];
                     }
                     float4* dst = reinterpret_cast<float4*>(HS + (v & (kHRing - 1)) * kHP + cb);
                     dst[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -234,20 +262,7 @@ recovery_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
                         const int o = o_first + r;
                         const int jr = u.r0 + o - kRadius;  // image row
                         if (jr <= kRadius || jr >= H - 1 - kRadius) {  // reflect fold-back (top / bottom rows only)
-                            float2 bt = upk(bt2[r]);
-                            if (jr >= 1 && jr <= kRadius)
-                                for (int i = 0; i <= kRadius - jr; ++i) {
-                                    const float2 h = *reinterpret_cast<const float2*>(HS + ((i - u.r0 + kRadius) & (kHRing - 1)) * kHP + col2);
-                                    bt.x = fmaf(h.x, c_tap[jr + i], bt.x);
-                                    bt.y = fmaf(h.y, c_tap[jr + i], bt.y);
-                                }
-                            if (jr >= H - 1 - kRadius && jr <= H - 2)
-                                for (int i = max(0, 2 * (H - 1) - jr - kRadius); i <= H - 1; ++i) {
-                                    const float2 h = *reinterpret_cast<const float2*>(HS + ((i - u.r0 + kRadius) & (kHRing - 1)) * kHP + col2);
-                                    const float kk = c_tap[abs(2 * (H - 1) - jr - i)];
-                                    bt.x = fmaf(h.x, kk, bt.x);
-                                    bt.y = fmaf(h.y, kk, bt.y);
-                                }
+                            const float2 bt = vfold(upk(bt2[r]), HS, col2, jr, u.r0, H);
                             bt2[r] = pk(bt.x, bt.y);
                         }
                         *reinterpret_cast<u64*>(BT + (8 * rg + r) * kBP + col2) = bt2[r];
