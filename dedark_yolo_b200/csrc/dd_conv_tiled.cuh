@@ -167,14 +167,13 @@ conv_fwd_tiled(const float* __restrict__ in, const float* __restrict__ w, const 
 // multiplied by LeakyReLU'(act_in): the stored tensor is the gradient w.r.t. the previous layer's PRE-activation.
 // -------------------------------------------------------------------------------------------------------------
 template <int CIN, int COUT, int HIN, int TQH, int TQW, int COCH, int QY>
-__global__ void __launch_bounds__(TQW*(TQH / QY) * (CIN / 8))
-conv_dgrad_tiled(const float* __restrict__ dpre, const float* __restrict__ w, const float* __restrict__ act_in,
-                 float* __restrict__ din) {
+__device__ __forceinline__ void conv_dgrad_body(const int bid, const float* __restrict__ dpre, const float* __restrict__ w,
+                                                const float* __restrict__ act_in, float* __restrict__ din) {
     constexpr int HO = HIN / 2, TX = HO / TQW, TY = HO / TQH, NCHUNK = COUT / COCH;
     constexpr int DP = TQW + 2, DPLANE = (TQH + 1) * DP;
     constexpr int D_F = (COCH * DPLANE + 3) & ~3, W_F = COCH * 9 * CIN, CH_F = D_F + W_F;  // floats per chunk
     extern __shared__ __align__(16) float smem_f[];
-    const int tile = blockIdx.x % (TX * TY), b = blockIdx.x / (TX * TY);
+    const int tile = bid % (TX * TY), b = bid / (TX * TY);
     const int a0 = (tile / TX) * TQH, c0q = (tile % TX) * TQW;
     const int qc = threadIdx.x % TQW, qr = (threadIdx.x / TQW) % (TQH / QY), cig = threadIdx.x / (TQW * (TQH / QY));
 
@@ -261,14 +260,14 @@ conv_dgrad_tiled(const float* __restrict__ dpre, const float* __restrict__ w, co
 // them as one slice of the partial buffer [slice][COUT*CIN*9 + COUT]; wgrad_reduce_kernel adds the slices in index order.
 // -------------------------------------------------------------------------------------------------------------
 template <int CIN, int COUT, int HIN, int TH, int TW, int CO_T>
-__global__ void __launch_bounds__(CIN*(COUT / CO_T))
-conv_wgrad_tiled(const float* __restrict__ in, const float* __restrict__ dpre, float* __restrict__ partial) {
+__device__ __forceinline__ void conv_wgrad_body(const int bid, const float* __restrict__ in, const float* __restrict__ dpre,
+                                                float* __restrict__ partial) {
     using T = InTile<TH, TW>;
     constexpr int HO = HIN / 2, TX = HO / TW, TY = HO / TH, NW = COUT * CIN * 9;
     extern __shared__ __align__(16) float smem_w[];
     float* s_in = smem_w;                   // [CIN] planes, parity-split columns
     float* s_d = s_in + CIN * T::PLANE;     // [COUT][TH][TW]
-    const int tile = blockIdx.x % (TX * TY), b = blockIdx.x / (TX * TY);
+    const int tile = bid % (TX * TY), b = bid / (TX * TY);
     const int oh0 = (tile / TX) * TH, ow0 = (tile % TX) * TW;
     stage_input_tile_async<TH, TW, CIN, HIN>(s_in, in + (size_t)b * CIN * HIN * HIN, 0, oh0, ow0);
     for (int idx = threadIdx.x; idx < COUT * TH * TW; idx += blockDim.x) {
@@ -307,7 +306,7 @@ conv_wgrad_tiled(const float* __restrict__ in, const float* __restrict__ dpre, f
                 for (int k = 0; k < 9; ++k) acc[t][k] = fmaf(d, v[k], acc[t][k]);
             }
         }
-    float* out = partial + (size_t)blockIdx.x * (NW + COUT);
+    float* out = partial + (size_t)bid * (NW + COUT);
 #pragma unroll
     for (int t = 0; t < CO_T; ++t) {
         const int co = cog * CO_T + t;
@@ -378,6 +377,60 @@ conv_wgrad_tiled_c3(const float* __restrict__ in, const float* __restrict__ dpre
     }
 }
 
+// One launch per layer of the backward: the weight gradient (CTAs 0 .. n_wgrad-1) and the data gradient (the rest) of a
+// layer are independent given dpre, so they share a grid (more CTAs per launch, half the dependent launches).
+template <int CIN, int COUT, int HIN, int WTH, int WTW, int CO_T, int TQH, int TQW, int COCH, int QY>
+__global__ void __launch_bounds__(256)
+conv_bwd_layer(const float* __restrict__ in, const float* __restrict__ dpre, const float* __restrict__ w,
+               const float* __restrict__ act_in, float* __restrict__ partial, float* __restrict__ din, int n_wgrad) {
+    static_assert(CIN * (COUT / CO_T) == 256 && TQW * (TQH / QY) * (CIN / 8) == 256, "both halves run with 256 threads");
+    if ((int)blockIdx.x < n_wgrad)
+        conv_wgrad_body<CIN, COUT, HIN, WTH, WTW, CO_T>(blockIdx.x, in, dpre, partial);
+    else
+        conv_dgrad_body<CIN, COUT, HIN, TQH, TQW, COCH, QY>(blockIdx.x - n_wgrad, dpre, w, act_in, din);
+}
+
+// all five layers' slice sums in one launch (deferred to the end of the backward)
+struct ReduceJob {
+    const float* partial;
+    float* dw;
+    float* db;
+    int split, nw, nb, block0;  // block0: first CTA of this job
+};
+struct ReduceJobs {
+    ReduceJob j[5];
+};
+__global__ void __launch_bounds__(1024) wgrad_reduce_all_kernel(const ReduceJobs jobs) {
+    __shared__ float s_part[32][33];
+    int l = 4;
+#pragma unroll
+    for (int q = 3; q >= 0; --q)
+        if ((int)blockIdx.x < jobs.j[q + 1].block0) l = q;
+    const ReduceJob jb = jobs.j[l];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n = jb.nw + jb.nb;
+    const int i = ((int)blockIdx.x - jb.block0) * 32 + lane;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (i < n) {
+        int s = wid;
+        for (; s + 96 < jb.split; s += 128) {
+            a0 += __ldg(jb.partial + (size_t)s * n + i);
+            a1 += __ldg(jb.partial + (size_t)(s + 32) * n + i);
+            a2 += __ldg(jb.partial + (size_t)(s + 64) * n + i);
+            a3 += __ldg(jb.partial + (size_t)(s + 96) * n + i);
+        }
+        for (; s < jb.split; s += 32) a0 += __ldg(jb.partial + (size_t)s * n + i);
+    }
+    s_part[wid][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (wid == 0 && i < n) {
+        float r = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r += s_part[k][lane];
+        if (i < jb.nw) jb.dw[i] = r; else jb.db[i - jb.nw] = r;
+    }
+}
+
 template <int CIN, int COUT, int TH, int TW, int CICH>
 constexpr size_t conv_fwd_smem() {
     return (size_t)(CIN / CICH) * (((CICH * InTile<TH, TW>::PLANE + 3) & ~3) + CICH * 9 * COUT) * sizeof(float);
@@ -385,6 +438,11 @@ constexpr size_t conv_fwd_smem() {
 template <int CIN, int COUT, int TQH, int TQW, int COCH>
 constexpr size_t conv_dgrad_smem() {
     return (size_t)(COUT / COCH) * (((COCH * (TQH + 1) * (TQW + 2) + 3) & ~3) + COCH * 9 * CIN) * sizeof(float);
+}
+
+template <int CIN, int COUT, int TH, int TW>
+constexpr size_t conv_wgrad_smem() {
+    return (size_t)(CIN * InTile<TH, TW>::PLANE + COUT * TH * TW) * sizeof(float);
 }
 
 }  // namespace dd

@@ -30,8 +30,10 @@ inline size_t predictor_acts_bytes(int B) { return predictor_acts_elems(B) * siz
 // backward scratch: gradients w.r.t. the pre-activations of every layer (same layout as acts) followed by
 // the split-K partial buffer of the weight-gradient kernels.
 constexpr int kWgradMaxSplit = 32;
-// per image: the largest slice set of the tiled weight-gradient kernels is conv2's, 32 tiles x (32*16*9 + 32) sums
-constexpr size_t kWgradPartialElemsPerImage = (size_t)32 * (32 * 16 * 9 + 32);
+// per image: the slice buffers of all five layers' weight-gradient kernels (tiles x (weights + biases)); they are
+// all kept until the single deferred reduction at the end of the backward
+constexpr size_t kWgradPartialElemsPerImage =
+    (size_t)64 * (432 + 16) + 32 * (4608 + 32) + 8 * (9216 + 32) + 4 * (9216 + 32) + 1 * (9216 + 32);
 inline size_t predictor_bwd_ws_bytes(int B) {
     return (predictor_acts_elems(B) + kWgradPartialElemsPerImage * B) * sizeof(float);
 }

@@ -446,31 +446,22 @@ static void launch_fwd_tiled(const float* in, const float* w, const float* b, fl
     count_launch();
 }
 
-template <int CIN, int COUT, int HIN, int TQH, int TQW, int COCH, int QY>
-static void launch_dgrad_tiled(const float* dpre, const float* w, const float* act_in, float* din, int B, cudaStream_t st) {
+// weight gradient (slices -> `partial`) and data gradient of one layer in one launch
+template <int CIN, int COUT, int HIN, int WTH, int WTW, int CO_T, int TQH, int TQW, int COCH, int QY>
+static int launch_bwd_layer(const float* in, const float* dpre, const float* w, const float* act_in, float* partial,
+                            float* din, int B, cudaStream_t st) {
     constexpr int HO = HIN / 2;
-    constexpr size_t smem = conv_dgrad_smem<CIN, COUT, TQH, TQW, COCH>();
-    cudaFuncSetAttribute(conv_dgrad_tiled<CIN, COUT, HIN, TQH, TQW, COCH, QY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    conv_dgrad_tiled<CIN, COUT, HIN, TQH, TQW, COCH, QY>
-        <<<B * (HO / TQH) * (HO / TQW), TQW * (TQH / QY) * (CIN / 8), smem, st>>>(dpre, w, act_in, din);
-    count_launch();
-}
-
-template <int CIN, int COUT, int HIN, int TH, int TW, int CO_T>
-static int launch_wgrad_tiled(const float* in, const float* dpre, float* partial, float* dw, float* db, int B,
-                              cudaStream_t st) {
-    constexpr int HO = HIN / 2, NW = COUT * CIN * 9;
-    constexpr size_t smem = (size_t)(CIN * InTile<TH, TW>::PLANE + COUT * TH * TW) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tiled<CIN, COUT, HIN, TH, TW, CO_T>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    constexpr size_t sm_w = conv_wgrad_smem<CIN, COUT, WTH, WTW>(), sm_d = conv_dgrad_smem<CIN, COUT, TQH, TQW, COCH>();
+    constexpr size_t smem = sm_w > sm_d ? sm_w : sm_d;
+    auto kern = conv_bwd_layer<CIN, COUT, HIN, WTH, WTW, CO_T, TQH, TQW, COCH, QY>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(conv_wgrad_tiled): %s", cudaGetErrorString(e));
+        set_error("cudaFuncSetAttribute(conv_bwd_layer): %s", cudaGetErrorString(e));
         return DD_ERR_CUDA;
     }
-    const int slices = B * (HO / TH) * (HO / TW);
-    conv_wgrad_tiled<CIN, COUT, HIN, TH, TW, CO_T><<<slices, CIN * (COUT / CO_T), smem, st>>>(in, dpre, partial);
-    wgrad_reduce_kernel<<<(NW + COUT + 31) / 32, 1024, 0, st>>>(partial, slices, NW, COUT, dw, db);
-    count_launch(2);
+    const int n_w = B * (HO / WTH) * (HO / WTW), n_d = B * (HO / TQH) * (HO / TQW);
+    kern<<<n_w + n_d, 256, smem, st>>>(in, dpre, w, act_in, partial, din, n_w);
+    count_launch();
     return DD_OK;
 }
 
@@ -543,20 +534,32 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     fc1_dgrad_kernel<<<(B * kFc1In + 255) / 256, 256, 0, st>>>(d[5], w->fc1_w, a[4], d[4], B);
     count_launch(3);
     // conv5 .. conv1: weight gradient from (input act, dpre), then data gradient into the previous layer
-    if (int e = launch_wgrad_tiled<32, 32, 16, 8, 8, 4>(a[3], d[4], partial, g->conv_w[4], g->conv_b[4], B, st)) return e;
-    launch_dgrad_tiled<32, 32, 16, 8, 8, 8, 1>(d[4], w->conv_w[4], a[3], d[3], B, st);
-    if (int e = launch_wgrad_tiled<32, 32, 32, 4, 16, 4>(a[2], d[3], partial, g->conv_w[3], g->conv_b[3], B, st)) return e;
-    launch_dgrad_tiled<32, 32, 32, 4, 16, 8, 1>(d[3], w->conv_w[3], a[2], d[2], B, st);
-    if (int e = launch_wgrad_tiled<32, 32, 64, 4, 32, 4>(a[1], d[2], partial, g->conv_w[2], g->conv_b[2], B, st)) return e;
-    launch_dgrad_tiled<32, 32, 64, 4, 32, 8, 2>(d[2], w->conv_w[2], a[1], d[1], B, st);
-    if (int e = launch_wgrad_tiled<16, 32, 128, 4, 32, 2>(a[0], d[1], partial, g->conv_w[1], g->conv_b[1], B, st)) return e;
-    launch_dgrad_tiled<16, 32, 128, 8, 32, 8, 2>(d[1], w->conv_w[1], a[0], d[0], B, st);
-    {   // first layer (CIN = 3): position-parallel weight gradient
-        constexpr int slices_per_img = (128 / 8) * (128 / 32);
-        conv_wgrad_tiled_c3<16, 256, 8, 32><<<B * slices_per_img, 32 * 8, 0, st>>>(r, d[0], partial);
-        wgrad_reduce_kernel<<<(432 + 16 + 31) / 32, 1024, 0, st>>>(partial, B * slices_per_img, 432, 16, g->conv_w[0], g->conv_b[0]);
-        count_launch(2);
+    // per-layer slice buffers (all kept until the single deferred reduction at the end)
+    constexpr int kSlices[5] = {64, 32, 8, 4, 1};                       // weight-gradient tiles per image, layers 1..5
+    constexpr int kNw[5] = {432, 4608, 9216, 9216, 9216}, kNb[5] = {16, 32, 32, 32, 32};
+    float* pl[5];
+    {
+        size_t off = 0;
+        for (int l = 0; l < 5; ++l) {
+            pl[l] = partial + off;
+            off += (size_t)B * kSlices[l] * (kNw[l] + kNb[l]);
+        }
     }
+    if (int e = launch_bwd_layer<32, 32, 16, 8, 8, 4, 8, 8, 8, 1>(a[3], d[4], w->conv_w[4], a[3], pl[4], d[3], B, st)) return e;
+    if (int e = launch_bwd_layer<32, 32, 32, 4, 16, 4, 4, 16, 8, 1>(a[2], d[3], w->conv_w[3], a[2], pl[3], d[2], B, st)) return e;
+    if (int e = launch_bwd_layer<32, 32, 64, 4, 32, 4, 4, 32, 8, 2>(a[1], d[2], w->conv_w[2], a[1], pl[2], d[1], B, st)) return e;
+    if (int e = launch_bwd_layer<16, 32, 128, 4, 32, 2, 8, 32, 8, 2>(a[0], d[1], w->conv_w[1], a[0], pl[1], d[0], B, st)) return e;
+    conv_wgrad_tiled_c3<16, 256, 8, 32><<<B * kSlices[0], 32 * 8, 0, st>>>(r, d[0], pl[0]);  // first layer (CIN = 3)
+    {
+        ReduceJobs jobs;
+        int block0 = 0;
+        for (int l = 0; l < 5; ++l) {
+            jobs.j[l] = ReduceJob{pl[l], g->conv_w[l], g->conv_b[l], B * kSlices[l], kNw[l], kNb[l], block0};
+            block0 += (kNw[l] + kNb[l] + 31) / 32;
+        }
+        wgrad_reduce_all_kernel<<<block0, 1024, 0, st>>>(jobs);
+    }
+    count_launch(2);
     if (dr) launch_conv_dgrad<3, 16, 256, 3>(d[0], w->conv_w[0], nullptr, dr, B, st);
     return check_launch("dd_predictor_bwd");
 }

@@ -23,6 +23,7 @@ namespace dd {
 
 constexpr int kXRingB = 80;   // XS ring depth of the backward kernel: 32 (H pass) + 12 (lagging centre rows) + 32 in flight
 constexpr int kBP = kStripW;  // BT pitch (floats)
+constexpr int kFinThreads = 1024;  // finalize: one CTA per image, ~2 rows of the column 0..2 fix-up per thread
 constexpr int kPW4 = (kRB * kStripW / 4) / kThreads;  // float4 per thread in the pointwise phase (4)
 
 __constant__ float c_tap[13] = {DD_K0, DD_K1, DD_K2, DD_K3, DD_K4, DD_K5, DD_K6,
@@ -325,7 +326,7 @@ recovery_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
 // One CTA per image: fixed-order sum of the (CTA, plane-strip) partials, the row-coupled fix-up of columns 0..2
 // (d lum / d x3[:, :, :, 0..2]) and the regressor Jacobians -> dfeat[b, 0..14].
 template <bool HAS_ICA, bool FAST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kFinThreads)
 recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restrict__ A,
                              const float* __restrict__ IcA, const float* __restrict__ feat,
                              const float* __restrict__ part, const float* __restrict__ Spart,
@@ -340,7 +341,7 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
     double dp = 0, dc = 0, dg = 0, dw = 0, ds[3] = {0, 0, 0};
 
     // partial sums: plane-strip ps of this image was processed by CTAs c_of(first block) .. c_of(last block)
-    for (int i = tid; i < 3 * sc.strips; i += kThreads) {
+    for (int i = tid; i < 3 * sc.strips; i += kFinThreads) {
         const int ps = 3 * b * sc.strips + i;
         const int ch = i / sc.strips;
         const long long x0 = (long long)ps * sc.nRB, x1 = x0 + sc.nRB - 1;
@@ -355,7 +356,7 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
         }
     }
     const float kappa[3] = {kLumR, kLumG, kLumB};
-    for (int i = tid; i < 3 * H; i += kThreads) {
+    for (int i = tid; i < 3 * H; i += kFinThreads) {
         const int ch = i / H, row = i - ch * H, plane = 3 * b + ch;
         float S = 0.f;
         for (int st = 0; st < sc.strips; ++st) S += Spart[((size_t)plane * H + row) * sc.strips + st];
@@ -426,7 +427,7 @@ static int launch_bwd3(const float* x, const float* A, const float* IcA, const f
     float* Spart = part + (size_t)(sc.G + sc.nPS) * kBwdSums;
     if (int e = set_smem(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED>, kBwdSmem)) return e;
     recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED><<<sc.G, kThreads, kBwdSmem, st>>>(x, A, IcA, feat, g, part, Spart, dx, B, H, W);
-    recovery_bwd_finalize_kernel<HAS_ICA, FAST><<<B, kThreads, 0, st>>>(x, A, IcA, feat, part, Spart, dfeat, dx, B, H, W);
+    recovery_bwd_finalize_kernel<HAS_ICA, FAST><<<B, kFinThreads, 0, st>>>(x, A, IcA, feat, part, Spart, dfeat, dx, B, H, W);
     count_launch(2);
     return check_launch("dd_recovery_bwd");
 }
