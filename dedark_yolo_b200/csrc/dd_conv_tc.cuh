@@ -1,0 +1,612 @@
+// dd_conv_tc.cuh -- the predictor's dense conv GEMMs (layers 2..5 of ExtractParameters2, nn/modules/common.py:52-78)
+// on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM, operands staged in shared
+// memory in the canonical no-swizzle core-matrix layouts, one elected thread issuing the MMAs, completion through
+// tcgen05.commit -> mbarrier, epilogue through tcgen05.ld.
+//
+// Precision.  The 1e-5 output gate of the module does not survive TF32 operand rounding, so every operand is split
+// on the fly into  x = hi + lo  (hi = rna_tf32(x), lo = rna_tf32(x - hi); both exactly representable in TF32) and
+// every product is issued as three MMAs  lo*hi + hi*lo + hi*hi  with fp32 accumulation in TMEM ("3xTF32"): the
+// dropped lo*lo term and the rounding of lo are each <= 2^-22 relative.
+//
+// Three GEMMs per layer (3x3 / stride 2 / pad 1 conv, Cin -> Cout, input HIN x HIN, output HO = HIN/2):
+//   forward  D[pixel][co]        = sum_{tap,ci}  im2col[pixel][tap,ci] * W[co][ci][tap]            (M=128, N=Cout)
+//   dgrad    D[quad][ci,parity]  = sum_{co,nb}   dOut[co][quad + nb]   * Wq[ci,parity][co,nb]      (M=128, N=4*Cin)
+//            a "quad" (a,c) is the 2x2 block of input pixels (2a+py, 2c+px); nb = (da,dc) in {0,1}^2 runs over
+//            the 2x2 neighbourhood of OUTPUT pixels (a+da, c+dc) it touches; Wq holds w[kh][kw] with
+//            kh = py - 2*da + 1, kw = px - 2*dc + 1 where that is a valid tap and 0 elsewhere
+//   wgrad    D[tap,ci | 1][co]   = sum_{pixel}   im2col^T[tap,ci | 1][pixel] * dOut^T[co][pixel]   (M=128 blocks, N=Cout)
+//            (both operands K-major with K = pixels: 16-byte chunks hold 4 consecutive pixels of one row; the extra
+//             row of ones yields the bias gradient)
+// M index = 128 consecutive pixels (or quads) in (b, row, col) raster order, so any batch size works.
+#pragma once
+#include "dd_common.cuh"
+
+namespace dd {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded spin: a lost arrival traps (the launch fails with an error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 24)) __trap();
+}
+
+// ---- tensor memory -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // one full warp; ncols = 2^k >= 32
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // the same warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (the tensor core reads operands through it)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 16 consecutive fp32 columns of this warp's 32 TMEM lanes: thread i gets lane (lane base + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors -------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64)).
+//   K-major  operand [rows][K]:  core matrix = 8 rows x 16 B (4 tf32 of K) stored as 128 contiguous bytes;
+//            SBO = byte distance between 8-row groups, LBO = byte distance between the two 16 B K-chunks of one MMA.
+//   MN-major operand [rows][K]:  16 B = 4 consecutive rows at one k; 8 consecutive k are 128 contiguous bytes;
+//            SBO = byte distance between 4-row groups, LBO = byte distance between 8-k groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=B=tf32 [7,10)=[10,13)=2,
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all MMAs issued so far by this thread -> one arrival on `bar` when they have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 3xTF32: lo*hi + hi*lo + hi*hi (small terms first)
+__device__ __forceinline__ void mma_3x(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                       uint32_t accumulate) {
+    mma_tf32(d, a_lo, b_hi, idesc, accumulate);
+    mma_tf32(d, a_hi, b_lo, idesc, 1u);
+    mma_tf32(d, a_hi, b_hi, idesc, 1u);
+}
+
+// ---- operand split -----------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split4(const float v0, const float v1, const float v2, const float v3, float4& hi, float4& lo) {
+    hi.x = tf32_rna(v0); hi.y = tf32_rna(v1); hi.z = tf32_rna(v2); hi.w = tf32_rna(v3);
+    lo.x = tf32_rna(v0 - hi.x); lo.y = tf32_rna(v1 - hi.y); lo.z = tf32_rna(v2 - hi.z); lo.w = tf32_rna(v3 - hi.w);
+}
+
+// ---- prepared weights (one launch per forward; the weights change every optimizer step) ----------------------
+// per layer l = 1..4 (conv2..conv5), floats:
+//   fwd  : [stage c = ci/8][hi|lo][slot s = 2*tap + (ci%8)/4][co][e = ci%4]                = 2 * 9*CIN*COUT
+//   dgrad: [stage c = co/8][hi|lo][slot s = co%8][n = ci*4 + py*2 + px][e = da*2 + dc]     = 2 * 16*CIN*COUT
+__host__ __device__ constexpr int prep_fwd_elems(int cin, int cout) { return 2 * 9 * cin * cout; }
+__host__ __device__ constexpr int prep_dgrad_elems(int cin, int cout) { return 2 * 16 * cin * cout; }
+
+struct PrepJob {
+    const float* w;  // [COUT][CIN][3][3]
+    float* fwd;
+    float* dgrad;
+    int cin, cout;
+};
+struct PrepJobs {
+    PrepJob j[4];
+};
+
+__global__ void __launch_bounds__(256)
+prep_weights_kernel(PrepJobs jobs) {
+    const PrepJob jb = jobs.j[blockIdx.y];
+    const int cin = jb.cin, cout = jb.cout;
+    const int nf = 9 * cin * cout, nd = 16 * cin * cout;  // hi elements of each table
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += gridDim.x * blockDim.x) {
+        float v;
+        float *hi, *lo;
+        if (i < nf) {
+            const int e = i & 3, co = (i >> 2) % cout, s = (i / (4 * cout)) % 18, c = i / (4 * cout * 18);
+            const int tap = s >> 1, ci = 8 * c + 4 * (s & 1) + e;
+            v = __ldg(jb.w + ((size_t)co * cin + ci) * 9 + tap);
+            hi = jb.fwd + (size_t)c * (2 * 18 * cout * 4) + (size_t)(s * cout + co) * 4 + e;
+            lo = hi + 18 * cout * 4;
+        } else {
+            const int k = i - nf, N = 4 * cin;
+            const int e = k & 3, n = (k >> 2) % N, s = (k / (4 * N)) % 8, c = k / (4 * N * 8);
+            const int co = 8 * c + s, ci = n >> 2, py = (n >> 1) & 1, px = n & 1, da = e >> 1, dc = e & 1;
+            const int kh = py - 2 * da + 1, kw = px - 2 * dc + 1;
+            v = (kh >= 0 && kw >= 0) ? __ldg(jb.w + ((size_t)co * cin + ci) * 9 + kh * 3 + kw) : 0.f;  // kh, kw <= 2 always
+            hi = jb.dgrad + (size_t)c * (2 * 8 * N * 4) + (size_t)(s * N + n) * 4 + e;
+            lo = hi + 8 * N * 4;
+        }
+        const float h = tf32_rna(v);
+        *hi = h;
+        *lo = tf32_rna(v - h);
+    }
+}
+
+// ---- shared bookkeeping of the three kernels -----------------------------------------------------------------
+struct TcCtl {
+    uint64_t bar;        // MMA-completion barrier (one arrival per commit)
+    uint32_t tmem_base;  // written by tcgen05.alloc
+};
+
+template <int TMEM_COLS>
+__device__ __forceinline__ uint32_t tc_setup(TcCtl* ctl) {
+    if (threadIdx.x < 32) tmem_alloc(&ctl->tmem_base, TMEM_COLS);
+    if (threadIdx.x == 32) {
+        mbar_init(&ctl->bar, 1);
+        fence_mbar_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    return ctl->tmem_base;
+}
+template <int TMEM_COLS>
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
+    fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// =============================================================================================================
+// forward:  out = leaky(conv(in, W) + bias)
+//   CTA = 128 output pixels x all COUT channels, 256 threads; the K = 9*CIN reduction runs in stages of 8 input
+//   channels (72 k = 9 MMA k-steps, one per tap): thread (pixel m = t%128, half h = t/128) gathers the 3x3 windows of
+//   4 channels (36 loads in flight, issued one stage ahead), splits them and stores 9 + 9 16-byte chunks.
+// =============================================================================================================
+template <int CIN, int COUT>
+constexpr size_t conv_tc_fwd_smem() { return (size_t)(2 * 18 * 128 * 4 + 2 * 18 * COUT * 4) * sizeof(float); }
+
+template <int CIN, int COUT, int HIN>
+__global__ void __launch_bounds__(256, 2)
+conv_tc_fwd(const float* __restrict__ in, const float* __restrict__ wprep, const float* __restrict__ bias,
+            float* __restrict__ out, int total_px) {
+    constexpr int HO = HIN / 2, NST = CIN / 8;
+    constexpr int A_HALF = 18 * 128 * 4, B_HALF = 18 * COUT * 4;  // floats
+    constexpr int TMEM_COLS = 32;
+    static_assert(COUT == 32, "epilogue assumes 32 output channels");
+    extern __shared__ __align__(128) float smem_tc[];
+    __shared__ TcCtl ctl;
+    float* sA = smem_tc;               // [hi|lo][18 slots][128 px][4]
+    float* sB = smem_tc + 2 * A_HALF;  // [hi|lo][18 slots][COUT][4]
+    const int t = threadIdx.x, m = t & 127, h = t >> 7;
+    const uint32_t tmem = tc_setup<TMEM_COLS>(&ctl);
+
+    const int gp = blockIdx.x * 128 + m;
+    const bool valid = gp < total_px;
+    const int b = gp / (HO * HO), rem = gp % (HO * HO), oh = rem / HO, ow = rem % HO;
+    const float* in_img = in + (size_t)b * CIN * HIN * HIN;
+    const int ih0 = 2 * oh - 1, iw0 = 2 * ow - 1;
+
+    float v[9][4];
+    auto gather = [&](int c) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float* p = in_img + (size_t)(8 * c + 4 * h + e) * HIN * HIN;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int ih = ih0 + kh, iw = iw0 + kw;
+                    v[kh * 3 + kw][e] = (valid && ih >= 0 && iw >= 0) ? __ldg(p + ih * HIN + iw) : 0.f;
+                }
+        }
+    };
+    gather(0);
+    constexpr uint32_t idesc = make_idesc(128, COUT, 0, 0);
+#pragma unroll 1
+    for (int c = 0; c < NST; ++c) {
+        if (c > 0) mbar_wait(&ctl.bar, (uint32_t)(c - 1) & 1u);  // the MMAs of the previous stage have read the buffers
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            float4 hi, lo;
+            split4(v[j][0], v[j][1], v[j][2], v[j][3], hi, lo);
+            const int off = ((2 * j + h) * 128 + m) * 4;
+            *reinterpret_cast<float4*>(sA + off) = hi;
+            *reinterpret_cast<float4*>(sA + A_HALF + off) = lo;
+        }
+        {
+            const float4* src = reinterpret_cast<const float4*>(wprep + (size_t)c * 2 * B_HALF);
+            float4* dst = reinterpret_cast<float4*>(sB);
+            for (int i = t; i < 2 * B_HALF / 4; i += 256) dst[i] = __ldg(src + i);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (t == 0) {
+            fence_after_sync();
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const uint32_t ao = a0 + (uint32_t)(2 * j) * 2048u, bo = b0 + (uint32_t)(2 * j) * (COUT * 16u);
+                mma_3x(tmem, make_desc(ao, 2048u, 128u), make_desc(ao + A_HALF * 4u, 2048u, 128u),
+                       make_desc(bo, COUT * 16u, 128u), make_desc(bo + B_HALF * 4u, COUT * 16u, 128u), idesc,
+                       (c > 0 || j > 0) ? 1u : 0u);
+            }
+            mma_commit(&ctl.bar);
+        }
+        if (c + 1 < NST) gather(c + 1);  // overlaps the MMAs
+    }
+    mbar_wait(&ctl.bar, (uint32_t)(NST - 1) & 1u);
+    fence_after_sync();
+    {
+        const int w = t >> 5, lane = t & 31, q = w & 3, half = w >> 2;
+        float r[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 16), r);
+        const int gpe = blockIdx.x * 128 + q * 32 + lane;
+        if (gpe < total_px) {
+            const int be = gpe / (HO * HO), reme = gpe % (HO * HO);
+            float* o = out + ((size_t)be * COUT + half * 16) * (HO * HO) + reme;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[(size_t)i * (HO * HO)] = leaky(r[i] + __ldg(bias + half * 16 + i));
+        }
+    }
+    tc_teardown<TMEM_COLS>(tmem);
+}
+
+// =============================================================================================================
+// data gradient:  din = leaky'(act_in) * conv_transpose(dpre, W)      (gradient w.r.t. the previous PRE-activation)
+//   CTA = 128 quads x all 4*CIN (channel, parity) columns; K = 4*COUT runs in stages of 8 output channels
+//   (32 k = 4 MMA k-steps): thread (quad m, half h) loads the 2x2 neighbourhoods of 4 channels.
+// =============================================================================================================
+template <int CIN, int COUT>
+constexpr size_t conv_tc_dgrad_smem() { return (size_t)(2 * 8 * 128 * 4 + 2 * 8 * 4 * CIN * 4) * sizeof(float); }
+
+template <int CIN, int COUT, int HIN>
+__device__ __forceinline__ void conv_tc_dgrad_body(const int bid, const float* __restrict__ dpre, const float* __restrict__ wprep,
+                                                   const float* __restrict__ act_in, float* __restrict__ din, int total_q,
+                                                   float* smem, TcCtl* ctl) {
+    constexpr int HO = HIN / 2, NST = COUT / 8, N = 4 * CIN;
+    constexpr int A_HALF = 8 * 128 * 4, B_HALF = 8 * N * 4;  // floats
+    constexpr int TMEM_COLS = N < 32 ? 32 : N;
+    float* sA = smem;               // [hi|lo][8 slots][128 quads][4]
+    float* sB = smem + 2 * A_HALF;  // [hi|lo][8 slots][N][4]
+    const int t = threadIdx.x, m = t & 127, h = t >> 7;
+    const uint32_t tmem = tc_setup<TMEM_COLS>(ctl);
+
+    const int gq = bid * 128 + m;
+    const bool valid = gq < total_q;
+    const int b = gq / (HO * HO), rem = gq % (HO * HO), a = rem / HO, cq = rem % HO;
+    const bool a1 = valid && (a + 1 < HO), c1 = cq + 1 < HO;
+    const float* dimg = dpre + (size_t)b * COUT * HO * HO + rem;
+
+    float v[4][4];
+    auto gather = [&](int c) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float* p = dimg + (size_t)(8 * c + 4 * h + e) * HO * HO;
+            v[e][0] = valid ? __ldg(p) : 0.f;
+            v[e][1] = (valid && c1) ? __ldg(p + 1) : 0.f;
+            v[e][2] = a1 ? __ldg(p + HO) : 0.f;
+            v[e][3] = (a1 && c1) ? __ldg(p + HO + 1) : 0.f;
+        }
+    };
+    gather(0);
+    constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
+#pragma unroll 1
+    for (int c = 0; c < NST; ++c) {
+        if (c > 0) mbar_wait(&ctl->bar, (uint32_t)(c - 1) & 1u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float4 hi, lo;
+            split4(v[e][0], v[e][1], v[e][2], v[e][3], hi, lo);
+            const int off = ((4 * h + e) * 128 + m) * 4;
+            *reinterpret_cast<float4*>(sA + off) = hi;
+            *reinterpret_cast<float4*>(sA + A_HALF + off) = lo;
+        }
+        {
+            const float4* src = reinterpret_cast<const float4*>(wprep + (size_t)c * 2 * B_HALF);
+            float4* dst = reinterpret_cast<float4*>(sB);
+            for (int i = t; i < 2 * B_HALF / 4; i += 256) dst[i] = __ldg(src + i);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (t == 0) {
+            fence_after_sync();
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t ao = a0 + (uint32_t)(2 * j) * 2048u, bo = b0 + (uint32_t)(2 * j) * (N * 16u);
+                mma_3x(tmem, make_desc(ao, 2048u, 128u), make_desc(ao + A_HALF * 4u, 2048u, 128u),
+                       make_desc(bo, N * 16u, 128u), make_desc(bo + B_HALF * 4u, N * 16u, 128u), idesc,
+                       (c > 0 || j > 0) ? 1u : 0u);
+            }
+            mma_commit(&ctl->bar);
+        }
+        if (c + 1 < NST) gather(c + 1);
+    }
+    mbar_wait(&ctl->bar, (uint32_t)(NST - 1) & 1u);
+    fence_after_sync();
+    {
+        const int w = t >> 5, lane = t & 31, q = w & 3, half = w >> 2;
+        const int gqe = bid * 128 + q * 32 + lane;
+        const bool ok = gqe < total_q;
+        const int be = gqe / (HO * HO), reme = gqe % (HO * HO), ae = reme / HO, ce = reme % HO;
+        // columns [half*N/2, (half+1)*N/2): CIN/2 channels x 4 parities, 4 channels (16 columns) per TMEM load
+#pragma unroll 1
+        for (int g = 0; g < N / 32; ++g) {
+            float r[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (N / 2) + g * 16), r);
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ci = half * (CIN / 2) + g * 4 + i;
+                    const size_t base = (((size_t)be * CIN + ci) * HIN + 2 * ae) * HIN + 2 * ce;
+                    float2 top = make_float2(r[4 * i + 0], r[4 * i + 1]), bot = make_float2(r[4 * i + 2], r[4 * i + 3]);
+                    const float2 at = *reinterpret_cast<const float2*>(act_in + base);
+                    const float2 ab = *reinterpret_cast<const float2*>(act_in + base + HIN);
+                    top.x = leaky_grad(at.x, top.x); top.y = leaky_grad(at.y, top.y);
+                    bot.x = leaky_grad(ab.x, bot.x); bot.y = leaky_grad(ab.y, bot.y);
+                    *reinterpret_cast<float2*>(din + base) = top;
+                    *reinterpret_cast<float2*>(din + base + HIN) = bot;
+                }
+            }
+        }
+    }
+    tc_teardown<TMEM_COLS>(tmem);
+}
+
+// =============================================================================================================
+// weight + bias gradient.  Rows r = tap*CIN + ci (r = 9*CIN: the row of ones -> bias gradient), padded to RP.
+//   CTA = a contiguous range of pixel tiles (PXT pixels = PXT/8 MMA k-steps each); accumulators for all rows stay in
+//   TMEM (NBLK blocks of 128 rows x COUT columns; the last block overlaps its predecessor so that every block is a
+//   full M = 128) until the range is done, then one slice [RP][COUT] of partial sums goes to global memory.
+//   Thread (pixel p = t % PXT, group w = t / PXT): 4 channels x 9 taps.  Both operands are K-major with K = pixels:
+//   [chunk = pixel/4][row][4 pixels], 4-byte stores; the row count is padded to 1 (mod 8) so that the 32 lanes of a
+//   warp (consecutive pixels, one row) hit 32 different banks.
+// =============================================================================================================
+template <int CIN>
+struct WgradCfg {
+    static constexpr int PXT = 256 / (CIN / 4);              // CIN=32: 32 pixels, CIN=16: 64 pixels
+    static constexpr int ROWS = 9 * CIN + 1;                 // + ones row
+    static constexpr int NCH = (ROWS + 3) / 4;               // 16-byte chunks along the rows
+    static constexpr int RP = NCH * 4;
+    static constexpr int NBLK = (RP + 127) / 128;
+    static constexpr int RPAD = (RP + 7) / 8 * 8 + 1;        // smem row pitch (in 16-byte chunks), == 1 (mod 8)
+    __host__ __device__ static constexpr int row0(int blk) { return blk + 1 < NBLK ? blk * 128 : RP - 128; }
+};
+template <int CIN, int COUT>
+constexpr size_t conv_tc_wgrad_smem() {
+    using Cfg = WgradCfg<CIN>;
+    return (size_t)(2 * (Cfg::PXT / 4) * Cfg::RPAD * 4 + 2 * (Cfg::PXT / 4) * (COUT + 1) * 4) * sizeof(float);
+}
+
+template <int CIN, int COUT, int HIN>
+__device__ __forceinline__ void conv_tc_wgrad_body(const int bid, const int nslices, const float* __restrict__ in,
+                                                   const float* __restrict__ dpre, float* __restrict__ partial, int total_px,
+                                                   float* smem, TcCtl* ctl) {
+    using Cfg = WgradCfg<CIN>;
+    constexpr int HO = HIN / 2, PXT = Cfg::PXT, NBLK = Cfg::NBLK, RP = Cfg::RP, RPAD = Cfg::RPAD, CPAD = COUT + 1;
+    constexpr int A_HALF = (PXT / 4) * RPAD * 4, B_HALF = (PXT / 4) * CPAD * 4;  // floats
+    constexpr int TMEM_COLS = NBLK * COUT <= 32 ? 32 : NBLK * COUT <= 64 ? 64 : 128;
+    static_assert(COUT == 32, "epilogue assumes 32 output channels");
+    float* sA = smem;               // [hi|lo][PXT/4][RPAD rows][4 pixels]
+    float* sB = smem + 2 * A_HALF;  // [hi|lo][PXT/4][CPAD channels][4 pixels]
+    const int t = threadIdx.x, p = t % PXT, w = t / PXT;  // w = group of 4 input channels
+    const uint32_t tmem = tc_setup<TMEM_COLS>(ctl);
+
+    // the rows 9*CIN .. RP-1: ones (bias gradient) + zero padding, written once
+    for (int i = t; i < PXT * 4; i += 256) {
+        const int pp = i % PXT, rr = 9 * CIN + i / PXT, off = ((pp >> 2) * RPAD + rr) * 4 + (pp & 3);
+        sA[off] = rr == 9 * CIN ? 1.f : 0.f;
+        sA[A_HALF + off] = 0.f;
+    }
+    const int ntiles = (total_px + PXT - 1) / PXT;
+    const int t0 = (int)((long long)ntiles * bid / nslices), t1 = (int)((long long)ntiles * (bid + 1) / nslices);
+
+    float v[9][4];
+    float dv[(COUT / 4) * PXT / 256][4];
+    auto gather = [&](int tile) {
+        const int gp = tile * PXT + p;
+        const bool valid = gp < total_px;
+        const int b = gp / (HO * HO), rem = gp % (HO * HO), oh = rem / HO, ow = rem % HO;
+        const int ih0 = 2 * oh - 1, iw0 = 2 * ow - 1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float* q = in + ((size_t)b * CIN + 4 * w + e) * HIN * HIN;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int ih = ih0 + kh, iw = iw0 + kw;
+                    v[kh * 3 + kw][e] = (valid && ih >= 0 && iw >= 0) ? __ldg(q + ih * HIN + iw) : 0.f;
+                }
+        }
+        // dOut chunks: (COUT/4) * PXT chunks per tile, one or two per thread
+#pragma unroll
+        for (int u = 0; u < (COUT / 4) * PXT / 256; ++u) {
+            const int idx = t + u * 256, pp = idx % PXT, g = idx / PXT;
+            const int gpp = tile * PXT + pp;
+            const int bb = gpp / (HO * HO), rr = gpp % (HO * HO);
+            const float* d = dpre + ((size_t)bb * COUT + 4 * g) * HO * HO + rr;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dv[u][e] = gpp < total_px ? __ldg(d + (size_t)e * HO * HO) : 0.f;
+        }
+    };
+    constexpr uint32_t idesc = make_idesc(128, COUT, 0, 0);
+    uint32_t phase = 0;
+    if (t0 < t1) gather(t0);
+#pragma unroll 1
+    for (int tile = t0; tile < t1; ++tile) {
+        if (tile > t0) {
+            mbar_wait(&ctl->bar, phase);
+            phase ^= 1u;
+        }
+        {
+            float* dst = sA + ((p >> 2) * RPAD + 4 * w) * 4 + (p & 3);
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float hi = tf32_rna(v[j][e]);
+                    dst[(j * CIN + e) * 4] = hi;
+                    dst[A_HALF + (j * CIN + e) * 4] = tf32_rna(v[j][e] - hi);
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < (COUT / 4) * PXT / 256; ++u) {
+            const int idx = t + u * 256, pp = idx % PXT, g = idx / PXT;
+            float* dst = sB + ((pp >> 2) * CPAD + 4 * g) * 4 + (pp & 3);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float hi = tf32_rna(dv[u][e]);
+                dst[e * 4] = hi;
+                dst[B_HALF + e * 4] = tf32_rna(dv[u][e] - hi);
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (t == 0) {
+            fence_after_sync();
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) {
+#pragma unroll
+                for (int ks = 0; ks < PXT / 8; ++ks) {
+                    const uint32_t ao = a0 + (uint32_t)(2 * ks * RPAD + Cfg::row0(blk)) * 16u;
+                    const uint32_t bo = b0 + (uint32_t)(2 * ks * CPAD) * 16u;
+                    mma_3x(tmem + (uint32_t)(blk * COUT), make_desc(ao, RPAD * 16u, 128u), make_desc(ao + A_HALF * 4u, RPAD * 16u, 128u),
+                           make_desc(bo, CPAD * 16u, 128u), make_desc(bo + B_HALF * 4u, CPAD * 16u, 128u), idesc,
+                           (tile > t0 || ks > 0) ? 1u : 0u);
+                }
+            }
+            mma_commit(&ctl->bar);
+        }
+        if (tile + 1 < t1) gather(tile + 1);
+    }
+    float* slice = partial + (size_t)bid * RP * COUT;
+    if (t0 < t1) {
+        mbar_wait(&ctl->bar, phase);
+        fence_after_sync();
+        const int wp = t >> 5, lane = t & 31, q = wp & 3, half = wp >> 2;
+#pragma unroll
+        for (int blk = 0; blk < NBLK; ++blk) {
+            float r[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * COUT + half * 16), r);
+            const int row = Cfg::row0(blk) + q * 32 + lane;
+            if (blk == 0 || row >= blk * 128) {  // the overlapping part of the last block was already written
+                float4* o = reinterpret_cast<float4*>(slice + (size_t)row * COUT + half * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            }
+        }
+    } else {
+        for (int i = t; i < RP * COUT; i += 256) slice[i] = 0.f;
+    }
+    tc_teardown<TMEM_COLS>(tmem);
+}
+
+// one launch per layer: the first n_w CTAs compute weight-gradient slices, the rest the data gradient
+template <int CIN, int COUT, int HIN>
+constexpr size_t conv_tc_bwd_smem() {
+    return conv_tc_wgrad_smem<CIN, COUT>() > conv_tc_dgrad_smem<CIN, COUT>() ? conv_tc_wgrad_smem<CIN, COUT>()
+                                                                              : conv_tc_dgrad_smem<CIN, COUT>();
+}
+template <int CIN, int COUT, int HIN>
+__global__ void __launch_bounds__(256, 2)
+conv_tc_bwd(const float* __restrict__ in, const float* __restrict__ dpre, const float* __restrict__ wprep_dgrad,
+            const float* __restrict__ act_in, float* __restrict__ partial, float* __restrict__ din, int n_w, int total_px) {
+    extern __shared__ __align__(128) float smem_tc[];
+    __shared__ TcCtl ctl;
+    if ((int)blockIdx.x < n_w)
+        conv_tc_wgrad_body<CIN, COUT, HIN>(blockIdx.x, n_w, in, dpre, partial, total_px, smem_tc, &ctl);
+    else
+        conv_tc_dgrad_body<CIN, COUT, HIN>(blockIdx.x - n_w, dpre, wprep_dgrad, act_in, din, total_px, smem_tc, &ctl);
+}
+
+// sum of the weight-gradient slices of all five layers in index order (deterministic), one launch.
+//   tensor-core layers: slices [nslices][RP][32] (row = tap*cin + ci, last live row = bias) -> the reference's
+//   [co][ci][3][3] layout;  conv1 (cin == 0 here): slices [nslices][nw + nb] already in the reference layout.
+struct ReduceJob {
+    const float* partial;
+    float* dw;
+    float* db;
+    int nslices, n, stride, cin, nw, block0;  // n live outputs per slice, stride floats between slices
+};
+struct ReduceJobs {
+    ReduceJob j[5];
+};
+__global__ void __launch_bounds__(1024)
+wgrad_reduce_kernel(const ReduceJobs jobs) {
+    __shared__ float s_part[32][33];
+    int ji = 0;
+#pragma unroll
+    for (int k = 1; k < 5; ++k)
+        if ((int)blockIdx.x >= jobs.j[k].block0) ji = k;
+    const ReduceJob jb = jobs.j[ji];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = ((int)blockIdx.x - jb.block0) * 32 + lane;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (i < jb.n) {
+        int s = wid;
+        for (; s + 96 < jb.nslices; s += 128) {
+            a0 += __ldg(jb.partial + (size_t)s * jb.stride + i);
+            a1 += __ldg(jb.partial + (size_t)(s + 32) * jb.stride + i);
+            a2 += __ldg(jb.partial + (size_t)(s + 64) * jb.stride + i);
+            a3 += __ldg(jb.partial + (size_t)(s + 96) * jb.stride + i);
+        }
+        for (; s < jb.nslices; s += 32) a0 += __ldg(jb.partial + (size_t)s * jb.stride + i);
+    }
+    s_part[wid][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (wid == 0 && i < jb.n) {
+        float r = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r += s_part[k][lane];
+        if (jb.cin == 0) {
+            if (i < jb.nw) jb.dw[i] = r; else jb.db[i - jb.nw] = r;
+        } else {
+            const int row = i >> 5, co = i & 31;
+            if (row == 9 * jb.cin) jb.db[co] = r;
+            else jb.dw[((size_t)co * jb.cin + row % jb.cin) * 9 + row / jb.cin] = r;
+        }
+    }
+}
+
+}  // namespace tc
+}  // namespace dd

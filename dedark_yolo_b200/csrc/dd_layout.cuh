@@ -25,17 +25,36 @@ inline size_t pred_act_offset(int l, int B) {  // l in 0..5 (5 = fc1 output h)
     return off;
 }
 inline size_t predictor_acts_elems(int B) { return pred_act_offset(5, B) + (size_t)kFc1Out * B; }
-inline size_t predictor_acts_bytes(int B) { return predictor_acts_elems(B) * sizeof(float); }
 
-// backward scratch: gradients w.r.t. the pre-activations of every layer (same layout as acts) followed by
-// the split-K partial buffer of the weight-gradient kernels.
-constexpr int kWgradMaxSplit = 32;
-// per image: the slice buffers of all five layers' weight-gradient kernels (tiles x (weights + biases)); they are
-// all kept until the single deferred reduction at the end of the backward
-constexpr size_t kWgradPartialElemsPerImage =
-    (size_t)64 * (432 + 16) + 32 * (4608 + 32) + 8 * (9216 + 32) + 4 * (9216 + 32) + 1 * (9216 + 32);
+// prepared weights of conv2..conv5 (dd_conv_tc.cuh: TF32 hi/lo halves in the shared-memory operand layouts of the
+// forward and data-gradient GEMMs) are kept behind the activations: written by dd_predictor_fwd, read by
+// dd_predictor_bwd of the same step.
+__host__ __device__ constexpr size_t pred_prep_fwd_elems(int l) { return (size_t)18 * pred_cin(l) * pred_cout(l); }
+__host__ __device__ constexpr size_t pred_prep_dgrad_elems(int l) { return (size_t)32 * pred_cin(l) * pred_cout(l); }
+inline size_t pred_prep_offset(int l) {  // l in 1..5 (5 = end); [fwd_l | dgrad_l] per layer
+    size_t off = 0;
+    for (int i = 1; i < l; ++i) off += pred_prep_fwd_elems(i) + pred_prep_dgrad_elems(i);
+    return off;
+}
+inline size_t predictor_acts_ws_elems(int B) { return predictor_acts_elems(B) + pred_prep_offset(5); }
+inline size_t predictor_acts_bytes(int B) { return predictor_acts_ws_elems(B) * sizeof(float); }
+
+// backward scratch: gradients w.r.t. the pre-activations of every layer (same layout as acts) followed by the slice
+// buffers of the weight-gradient kernels (all kept until the single deferred reduction at the end of the backward).
+//   conv1 (CUDA cores): 64 tiles per image x (432 + 16);  conv2..conv5 (tensor cores): slices x RP x 32 with
+//   RP = rows (9*Cin + 1 ones row for the bias) rounded up to 4.
+constexpr int kWgradC1Slices = 64;
+__host__ __device__ constexpr int pred_wgrad_rp(int l) { return (9 * pred_cin(l) + 1 + 3) / 4 * 4; }
+__host__ __device__ constexpr int pred_wgrad_slices_per_image(int l) { return l == 1 ? 16 : l == 2 ? 8 : l == 3 ? 4 : 2; }
+inline size_t pred_wgrad_partial_offset(int l, int B) {  // l in 0..5 (5 = end)
+    size_t off = 0;
+    for (int i = 0; i < l; ++i)
+        off += i == 0 ? (size_t)B * kWgradC1Slices * (432 + 16)
+                      : (size_t)B * pred_wgrad_slices_per_image(i) * pred_wgrad_rp(i) * 32;
+    return off;
+}
 inline size_t predictor_bwd_ws_bytes(int B) {
-    return (predictor_acts_elems(B) + kWgradPartialElemsPerImage * B) * sizeof(float);
+    return (predictor_acts_elems(B) + pred_wgrad_partial_offset(5, B)) * sizeof(float);
 }
 
 // ---- fused filter chain --------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 // dd_predictor.cu -- a4 + a5: bilinear resize to 256x256 and the parameter-predictor CNN, forward and
-// backward, in fp32 on the CUDA cores (exact-parity path: the 1e-5 output gate does not survive
-// TF32/bf16 operand rounding in these GEMMs).
+// backward.  conv2..conv5 (the dense GEMMs) run on the tensor cores (dd_conv_tc.cuh: tcgen05 kind::tf32 with split
+// operands, "3xTF32", because the 1e-5 output gate does not survive plain TF32 operand rounding); conv1 (K = 27),
+// the resize and the two small FC layers stay on the CUDA cores.
 //
 // Reference: nn/modules/llie.py:43 (F.interpolate bilinear, align_corners=False),
 //            nn/modules/common.py:9-23 (ConvBlock: Conv2d k3 s2 p1 + LeakyReLU 0.1),
@@ -10,6 +11,7 @@
 // reductions are fixed-order (per-thread serial loops, block_sum, split partials summed in index
 // order): bit-reproducible run to run.
 #include "dd_common.cuh"
+#include "dd_conv_tc.cuh"
 #include "dd_conv_tiled.cuh"
 #include "dd_layout.cuh"
 
@@ -74,80 +76,6 @@ resize256_bwd_kernel(const float* __restrict__ dr, float* __restrict__ dx, int B
         acc = fmaf(wy, racc, acc);
     }
     dx[((size_t)plane * H + ys) * W + xs] += acc;
-}
-
-// -------------------------------------------------------------------------------------------------
-// conv 3x3, stride 2, pad 1, + bias + LeakyReLU(0.1): direct convolution, register-tiled
-//   thread = PX horizontally adjacent output pixels x CO_T output channels
-//   weights staged once per CTA in shared memory as [ci*9 + kh*3 + kw][co] (broadcast 128-bit reads)
-// -------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, int HIN, int PX, int CO_T>
-__global__ void __launch_bounds__(256)
-conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                float* __restrict__ out, int B) {
-    constexpr int HO = HIN / 2;
-    constexpr int PXG = HO * HO / PX;   // pixel groups per image
-    constexpr int COG = COUT / CO_T;    // channel groups
-    __shared__ __align__(16) float sw[CIN * 9 * COUT];
-    // w is [co][ci][kh][kw]; co runs fastest over the lanes so the shared-memory writes are conflict-free (the
-    // strided global reads come out of L2)
-    for (int i = threadIdx.x; i < CIN * 9 * COUT; i += blockDim.x) {
-        const int co = i % COUT, rem = i / COUT;
-        sw[i] = __ldg(w + co * (CIN * 9) + rem);
-    }
-    __syncthreads();
-    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= (long long)B * PXG * COG) return;
-    const int pg = (int)(item % PXG);
-    const int cog = (int)((item / PXG) % COG);
-    const int b = (int)(item / ((long long)PXG * COG));
-    const int oh = pg / (HO / PX), ow0 = (pg % (HO / PX)) * PX;
-
-    float acc[PX][CO_T];
-#pragma unroll
-    for (int p = 0; p < PX; ++p)
-#pragma unroll
-        for (int c = 0; c < CO_T; ++c) acc[p][c] = 0.f;
-
-    const float* inb = in + (size_t)b * CIN * HIN * HIN;
-    for (int ci = 0; ci < CIN; ++ci) {
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int ih = 2 * oh + kh - 1;
-            if (ih < 0 || ih >= HIN) continue;
-            const float* row = inb + ((size_t)ci * HIN + ih) * HIN;
-            float v[2 * PX + 1];
-#pragma unroll
-            for (int t = 0; t < 2 * PX + 1; ++t) {
-                const int iw = 2 * ow0 - 1 + t;
-                v[t] = (iw >= 0) ? __ldg(row + iw) : 0.f;   // iw <= HIN-1 always
-            }
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const float* wp = sw + (ci * 9 + kh * 3 + kw) * COUT + cog * CO_T;
-#pragma unroll
-                for (int c4 = 0; c4 < CO_T; c4 += 4) {
-                    const float4 wv = *reinterpret_cast<const float4*>(wp + c4);
-#pragma unroll
-                    for (int p = 0; p < PX; ++p) {
-                        const float a = v[2 * p + kw];
-                        acc[p][c4 + 0] = fmaf(a, wv.x, acc[p][c4 + 0]);
-                        acc[p][c4 + 1] = fmaf(a, wv.y, acc[p][c4 + 1]);
-                        acc[p][c4 + 2] = fmaf(a, wv.z, acc[p][c4 + 2]);
-                        acc[p][c4 + 3] = fmaf(a, wv.w, acc[p][c4 + 3]);
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < CO_T; ++c) {
-        const int co = cog * CO_T + c;
-        const float bv = __ldg(bias + co);
-        float* o = out + (((size_t)b * COUT + co) * HO + oh) * HO + ow0;
-#pragma unroll
-        for (int p = 0; p < PX; ++p) o[p] = leaky(acc[p][c] + bv);
-    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -216,100 +144,6 @@ conv_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, c
         }
         *reinterpret_cast<float2*>(din + base) = top;
         *reinterpret_cast<float2*>(din + base + HIN) = bot;
-    }
-}
-
-// -------------------------------------------------------------------------------------------------
-// weight (+bias) gradient.  CTA = (tile of 4 output channels, one input channel, one slice of the
-// (b, oh) rows).  Each thread keeps 4x9 accumulators; block_sum -> partial[slice][...]; a second kernel
-// adds the slices in index order.
-// -------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, int HIN>
-__global__ void __launch_bounds__(256)
-conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dpre, float* __restrict__ partial,
-                  int B, int split) {
-    constexpr int HO = HIN / 2;
-    constexpr int NW = COUT * CIN * 9;
-    __shared__ float s_red[32];
-    const int cot = blockIdx.x / CIN, ci = blockIdx.x % CIN;  // cot: tile of 4 output channels
-    const int slice = blockIdx.y;
-    const int rows = B * HO;
-    const int per = (rows + split - 1) / split;
-    const int r0 = slice * per, r1 = min(rows, r0 + per);
-
-    float acc[4][9];
-    float accb[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        accb[t] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) acc[t][k] = 0.f;
-    }
-    for (int idx = threadIdx.x; idx < (r1 - r0) * HO; idx += blockDim.x) {
-        const int row = r0 + idx / HO, ow = idx % HO;
-        const int b = row / HO, oh = row % HO;
-        float v[9];
-        const float* ip = in + ((size_t)b * CIN + ci) * HIN * HIN;
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int ih = 2 * oh + kh - 1;
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int iw = 2 * ow + kw - 1;
-                v[kh * 3 + kw] = (ih >= 0 && ih < HIN && iw >= 0) ? __ldg(ip + (size_t)ih * HIN + iw) : 0.f;
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float d = __ldg(dpre + (((size_t)b * COUT + cot * 4 + t) * HO + oh) * HO + ow);
-            accb[t] += d;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) acc[t][k] = fmaf(d, v[k], acc[t][k]);
-        }
-    }
-    float* out = partial + (size_t)slice * (NW + COUT);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int co = cot * 4 + t;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const float s = block_sum<float>(acc[t][k], s_red);
-            if (threadIdx.x == 0) out[(co * CIN + ci) * 9 + k] = s;
-        }
-        if (ci == 0) {
-            const float s = block_sum<float>(accb[t], s_red);
-            if (threadIdx.x == 0) out[NW + co] = s;
-        }
-    }
-}
-
-// sum of the slices of a partial buffer [split][nw + nb]: block = 32 consecutive outputs x 32 warps; warp w adds the
-// slices s = w, w + 32, ... (4 loads in flight), then the 32 per-warp sums are added in index order: deterministic.
-__global__ void __launch_bounds__(1024)
-wgrad_reduce_kernel(const float* __restrict__ partial, int split, int nw, int nb, float* __restrict__ dw,
-                    float* __restrict__ db) {
-    __shared__ float s_part[32][33];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + lane;
-    const size_t stride = (size_t)(nw + nb);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (i < nw + nb) {
-        int s = wid;
-        for (; s + 96 < split; s += 128) {
-            a0 += __ldg(partial + (size_t)s * stride + i);
-            a1 += __ldg(partial + (size_t)(s + 32) * stride + i);
-            a2 += __ldg(partial + (size_t)(s + 64) * stride + i);
-            a3 += __ldg(partial + (size_t)(s + 96) * stride + i);
-        }
-        for (; s < split; s += 32) a0 += __ldg(partial + (size_t)s * stride + i);
-    }
-    s_part[wid][lane] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
-    if (wid == 0 && i < nw + nb) {
-        float r = 0.f;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) r += s_part[k][lane];
-        if (i < nw) dw[i] = r; else db[i - nw] = r;
     }
 }
 
@@ -404,14 +238,6 @@ fc1_dgrad_kernel(const float* __restrict__ dhpre, const float* __restrict__ w1, 
 // -------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // -------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, int HIN, int PX, int CO_T>
-static void launch_conv_fwd(const float* in, const float* w, const float* b, float* out, int B, cudaStream_t st) {
-    constexpr int HO = HIN / 2;
-    const long long items = (long long)B * (HO * HO / PX) * (COUT / CO_T);
-    conv_fwd_kernel<CIN, COUT, HIN, PX, CO_T><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(in, w, b, out, B);
-    count_launch();
-}
-
 template <int CIN, int COUT, int HIN, int CI_T>
 static void launch_conv_dgrad(const float* dpre, const float* w, const float* act_in, float* din, int B,
                               cudaStream_t st) {
@@ -421,21 +247,7 @@ static void launch_conv_dgrad(const float* dpre, const float* w, const float* ac
     count_launch();
 }
 
-template <int CIN, int COUT, int HIN>
-static void launch_conv_wgrad(const float* in, const float* dpre, float* partial, float* dw, float* db, int B,
-                              cudaStream_t st) {
-    constexpr int HO = HIN / 2;
-    constexpr int NW = COUT * CIN * 9;
-    // slices of the (b, oh) rows: aim at ~4096 reduction elements per CTA
-    int split = (int)(((long long)B * HO * HO + 4095) / 4096);
-    split = split < 1 ? 1 : (split > kWgradMaxSplit ? kWgradMaxSplit : split);
-    dim3 grid((COUT / 4) * CIN, split);
-    conv_wgrad_kernel<CIN, COUT, HIN><<<grid, 256, 0, st>>>(in, dpre, partial, B, split);
-    wgrad_reduce_kernel<<<(NW + COUT + 31) / 32, 1024, 0, st>>>(partial, split, NW, COUT, dw, db);
-    count_launch(2);
-}
-
-// ---- tiled kernels (dd_conv_tiled.cuh) -----------------------------------------------------------
+// ---- conv1: shared-memory-tiled CUDA-core kernel (dd_conv_tiled.cuh) ------------------------------
 template <int CIN, int COUT, int HIN, int TH, int TW, int CICH, int PY>
 static void launch_fwd_tiled(const float* in, const float* w, const float* b, float* out, int B, cudaStream_t st) {
     constexpr int HO = HIN / 2;
@@ -446,21 +258,37 @@ static void launch_fwd_tiled(const float* in, const float* w, const float* b, fl
     count_launch();
 }
 
-// weight gradient (slices -> `partial`) and data gradient of one layer in one launch
-template <int CIN, int COUT, int HIN, int WTH, int WTW, int CO_T, int TQH, int TQW, int COCH, int QY>
-static int launch_bwd_layer(const float* in, const float* dpre, const float* w, const float* act_in, float* partial,
-                            float* din, int B, cudaStream_t st) {
+// ---- conv2..conv5: tensor-core kernels (dd_conv_tc.cuh) --------------------------------------------
+template <int CIN, int COUT, int HIN>
+static int launch_tc_fwd(const float* in, const float* wprep, const float* bias, float* out, int B, cudaStream_t st) {
     constexpr int HO = HIN / 2;
-    constexpr size_t sm_w = conv_wgrad_smem<CIN, COUT, WTH, WTW>(), sm_d = conv_dgrad_smem<CIN, COUT, TQH, TQW, COCH>();
-    constexpr size_t smem = sm_w > sm_d ? sm_w : sm_d;
-    auto kern = conv_bwd_layer<CIN, COUT, HIN, WTH, WTW, CO_T, TQH, TQW, COCH, QY>;
+    constexpr size_t smem = tc::conv_tc_fwd_smem<CIN, COUT>();
+    auto kern = tc::conv_tc_fwd<CIN, COUT, HIN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(conv_bwd_layer): %s", cudaGetErrorString(e));
+        set_error("cudaFuncSetAttribute(conv_tc_fwd): %s", cudaGetErrorString(e));
         return DD_ERR_CUDA;
     }
-    const int n_w = B * (HO / WTH) * (HO / WTW), n_d = B * (HO / TQH) * (HO / TQW);
-    kern<<<n_w + n_d, 256, smem, st>>>(in, dpre, w, act_in, partial, din, n_w);
+    const int total = B * HO * HO;
+    kern<<<(total + 127) / 128, 256, smem, st>>>(in, wprep, bias, out, total);
+    count_launch();
+    return DD_OK;
+}
+
+// weight gradient (slices -> `partial`) and data gradient of one layer in one launch
+template <int CIN, int COUT, int HIN>
+static int launch_tc_bwd(const float* in, const float* dpre, const float* wprep_dgrad, const float* act_in, float* partial,
+                         float* din, int n_slices, int B, cudaStream_t st) {
+    constexpr int HO = HIN / 2;
+    constexpr size_t smem = tc::conv_tc_bwd_smem<CIN, COUT, HIN>();
+    auto kern = tc::conv_tc_bwd<CIN, COUT, HIN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(conv_tc_bwd): %s", cudaGetErrorString(e));
+        return DD_ERR_CUDA;
+    }
+    const int total = B * HO * HO;
+    kern<<<n_slices + (total + 127) / 128, 256, smem, st>>>(in, dpre, wprep_dgrad, act_in, partial, din, n_slices, total);
     count_launch();
     return DD_OK;
 }
@@ -502,10 +330,19 @@ extern "C" int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, f
     float* a[6];
     for (int l = 0; l < 6; ++l) a[l] = acts + pred_act_offset(l, B);
     launch_fwd_tiled<3, 16, 256, 16, 32, 3, 4>(r, w->conv_w[0], w->conv_b[0], a[0], B, st);
-    launch_fwd_tiled<16, 32, 128, 8, 32, 8, 4>(a[0], w->conv_w[1], w->conv_b[1], a[1], B, st);
-    launch_fwd_tiled<32, 32, 64, 4, 32, 8, 2>(a[1], w->conv_w[2], w->conv_b[2], a[2], B, st);
-    launch_fwd_tiled<32, 32, 32, 4, 16, 8, 1>(a[2], w->conv_w[3], w->conv_b[3], a[3], B, st);
-    launch_fwd_tiled<32, 32, 16, 8, 8, 8, 1>(a[3], w->conv_w[4], w->conv_b[4], a[4], B, st);
+    float* prep = acts + predictor_acts_elems(B);
+    {
+        tc::PrepJobs jobs;
+        for (int l = 1; l < 5; ++l)
+            jobs.j[l - 1] = tc::PrepJob{w->conv_w[l], prep + pred_prep_offset(l), prep + pred_prep_offset(l) + pred_prep_fwd_elems(l),
+                                        pred_cin(l), pred_cout(l)};
+        tc::prep_weights_kernel<<<dim3(32, 4), 256, 0, st>>>(jobs);
+        count_launch();
+    }
+    if (int e = launch_tc_fwd<16, 32, 128>(a[0], prep + pred_prep_offset(1), w->conv_b[1], a[1], B, st)) return e;
+    if (int e = launch_tc_fwd<32, 32, 64>(a[1], prep + pred_prep_offset(2), w->conv_b[2], a[2], B, st)) return e;
+    if (int e = launch_tc_fwd<32, 32, 32>(a[2], prep + pred_prep_offset(3), w->conv_b[3], a[3], B, st)) return e;
+    if (int e = launch_tc_fwd<32, 32, 16>(a[3], prep + pred_prep_offset(4), w->conv_b[4], a[4], B, st)) return e;
     fc1_fwd_kernel<<<(B * kFc1Out * 32 + 255) / 256, 256, 0, st>>>(a[4], w->fc1_w, w->fc1_b, a[5], B);
     fc2_fwd_kernel<<<(B * kFeat + 255) / 256, 256, 0, st>>>(a[5], w->fc2_w, w->fc2_b, feat, B);
     count_launch(2);
@@ -533,31 +370,31 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     fc1_wgrad_kernel<<<(kFc1Out * kFc1In + 255) / 256, 256, 0, st>>>(d[5], a[4], g->fc1_w, g->fc1_b, B);
     fc1_dgrad_kernel<<<(B * kFc1In + 255) / 256, 256, 0, st>>>(d[5], w->fc1_w, a[4], d[4], B);
     count_launch(3);
-    // conv5 .. conv1: weight gradient from (input act, dpre), then data gradient into the previous layer
-    // per-layer slice buffers (all kept until the single deferred reduction at the end)
-    constexpr int kSlices[5] = {64, 32, 8, 4, 1};                       // weight-gradient tiles per image, layers 1..5
-    constexpr int kNw[5] = {432, 4608, 9216, 9216, 9216}, kNb[5] = {16, 32, 32, 32, 32};
+    // conv5 .. conv2: weight-gradient slices and the data gradient of a layer in one tensor-core launch; conv1: weight
+    // gradient on the CUDA cores; one deferred reduction of all slice buffers at the end
+    const float* prep = acts + predictor_acts_elems(B);
     float* pl[5];
-    {
-        size_t off = 0;
-        for (int l = 0; l < 5; ++l) {
-            pl[l] = partial + off;
-            off += (size_t)B * kSlices[l] * (kNw[l] + kNb[l]);
-        }
+    int nsl[5];
+    for (int l = 0; l < 5; ++l) {
+        pl[l] = partial + pred_wgrad_partial_offset(l, B);
+        nsl[l] = B * (l == 0 ? kWgradC1Slices : pred_wgrad_slices_per_image(l));
     }
-    if (int e = launch_bwd_layer<32, 32, 16, 8, 8, 4, 8, 8, 8, 1>(a[3], d[4], w->conv_w[4], a[3], pl[4], d[3], B, st)) return e;
-    if (int e = launch_bwd_layer<32, 32, 32, 4, 16, 4, 4, 16, 8, 1>(a[2], d[3], w->conv_w[3], a[2], pl[3], d[2], B, st)) return e;
-    if (int e = launch_bwd_layer<32, 32, 64, 4, 32, 4, 4, 32, 8, 2>(a[1], d[2], w->conv_w[2], a[1], pl[2], d[1], B, st)) return e;
-    if (int e = launch_bwd_layer<16, 32, 128, 4, 32, 2, 8, 32, 8, 2>(a[0], d[1], w->conv_w[1], a[0], pl[1], d[0], B, st)) return e;
-    conv_wgrad_tiled_c3<16, 256, 8, 32><<<B * kSlices[0], 32 * 8, 0, st>>>(r, d[0], pl[0]);  // first layer (CIN = 3)
+    auto dg = [&](int l) { return prep + pred_prep_offset(l) + pred_prep_fwd_elems(l); };
+    if (int e = launch_tc_bwd<32, 32, 16>(a[3], d[4], dg(4), a[3], pl[4], d[3], nsl[4], B, st)) return e;
+    if (int e = launch_tc_bwd<32, 32, 32>(a[2], d[3], dg(3), a[2], pl[3], d[2], nsl[3], B, st)) return e;
+    if (int e = launch_tc_bwd<32, 32, 64>(a[1], d[2], dg(2), a[1], pl[2], d[1], nsl[2], B, st)) return e;
+    if (int e = launch_tc_bwd<16, 32, 128>(a[0], d[1], dg(1), a[0], pl[1], d[0], nsl[1], B, st)) return e;
+    conv_wgrad_tiled_c3<16, 256, 8, 32><<<nsl[0], 32 * 8, 0, st>>>(r, d[0], pl[0]);  // first layer (CIN = 3)
     {
-        ReduceJobs jobs;
+        tc::ReduceJobs jobs;
         int block0 = 0;
         for (int l = 0; l < 5; ++l) {
-            jobs.j[l] = ReduceJob{pl[l], g->conv_w[l], g->conv_b[l], B * kSlices[l], kNw[l], kNb[l], block0};
-            block0 += (kNw[l] + kNb[l] + 31) / 32;
+            const int n = l == 0 ? 432 + 16 : (9 * pred_cin(l) + 1) * 32;
+            jobs.j[l] = tc::ReduceJob{pl[l], g->conv_w[l], g->conv_b[l], nsl[l], n, l == 0 ? n : pred_wgrad_rp(l) * 32,
+                                      l == 0 ? 0 : pred_cin(l), 432, block0};
+            block0 += (n + 31) / 32;
         }
-        wgrad_reduce_all_kernel<<<block0, 1024, 0, st>>>(jobs);
+        tc::wgrad_reduce_kernel<<<block0, 1024, 0, st>>>(jobs);
     }
     count_launch(2);
     if (dr) launch_conv_dgrad<3, 16, 256, 3>(d[0], w->conv_w[0], nullptr, dr, B, st);
