@@ -24,6 +24,26 @@
 namespace dd {
 namespace tc {
 
+// optional in-kernel time stamps (profiles/microbench/tc_probe.cu defines DD_TC_TIMING); no code otherwise
+#ifdef DD_TC_TIMING
+__device__ long long g_tc_stamp[64];
+#define DD_TC_STAMP(i)                                                         \
+    do {                                                                       \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_tc_stamp[(i)] = clock64();  \
+    } while (0)
+#define DD_TC_STAMP_T(i, thr)                                                     \
+    do {                                                                         \
+        if (blockIdx.x == 0 && threadIdx.x == (thr)) g_tc_stamp[(i)] = clock64(); \
+    } while (0)
+#else
+#define DD_TC_STAMP(i) \
+    do {               \
+    } while (0)
+#define DD_TC_STAMP_T(i, thr) \
+    do {                      \
+    } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- mbarrier ----------------------------------------------------------------------------------------------
@@ -42,10 +62,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
 // bounded spin: a lost arrival traps (the launch fails with an error) instead of hanging the device
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
         if (spin > (1u << 24)) __trap();
+}
+
+// ---- 16-byte asynchronous global -> shared copies (LDGSTS) ----------------------------------------------------
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// one lane of a converged warp (the compiler recognises elect.sync and issues the tcgen05 instructions of the guarded
+// block once, without the per-active-thread loop it emits for an ordinary `lane == 0` test)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- tensor memory -----------------------------------------------------------------------------------------
@@ -74,6 +112,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// registers -> 16 (4) consecutive fp32 columns of this warp's 32 TMEM lanes (thread i writes lane base + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors -------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64)).
@@ -100,6 +155,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with the A operand in tensor memory (lane = row, one fp32 column per k): no shared-memory traffic for A
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // all MMAs issued so far by this thread -> one arrival on `bar` when they have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -113,11 +177,9 @@ __device__ __forceinline__ void mma_3x(uint32_t d, uint64_t a_hi, uint64_t a_lo,
 }
 
 // ---- operand split -----------------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// round to nearest (ties away from zero) to TF32's 10 explicit mantissa bits == cvt.rna.tf32.f32, done as two integer
+// ops on the ALU pipe (the conversion instruction is rate-limited: it cost ~1000 cycles per 128x72 stage)
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split4(const float v0, const float v1, const float v2, const float v3, float4& hi, float4& lo) {
     hi.x = tf32_rna(v0); hi.y = tf32_rna(v1); hi.z = tf32_rna(v2); hi.w = tf32_rna(v3);
     lo.x = tf32_rna(v0 - hi.x); lo.y = tf32_rna(v1 - hi.y); lo.z = tf32_rna(v2 - hi.z); lo.w = tf32_rna(v3 - hi.w);
@@ -125,7 +187,7 @@ __device__ __forceinline__ void split4(const float v0, const float v1, const flo
 
 // ---- prepared weights (one launch per forward; the weights change every optimizer step) ----------------------
 // per layer l = 1..4 (conv2..conv5), floats:
-//   fwd  : [stage c = ci/8][hi|lo][slot s = 2*tap + (ci%8)/4][co][e = ci%4]                = 2 * 9*CIN*COUT
+//   fwd  : [stage c = ci/8][slot s = 9*((ci%8)/4) + tap][row = co (hi) | COUT + co (lo)][e = ci%4] = 2 * 9*CIN*COUT
 //   dgrad: [stage c = co/8][hi|lo][slot s = co%8][n = ci*4 + py*2 + px][e = da*2 + dc]     = 2 * 16*CIN*COUT
 __host__ __device__ constexpr int prep_fwd_elems(int cin, int cout) { return 2 * 9 * cin * cout; }
 __host__ __device__ constexpr int prep_dgrad_elems(int cin, int cout) { return 2 * 16 * cin * cout; }
@@ -150,10 +212,10 @@ prep_weights_kernel(PrepJobs jobs) {
         float *hi, *lo;
         if (i < nf) {
             const int e = i & 3, co = (i >> 2) % cout, s = (i / (4 * cout)) % 18, c = i / (4 * cout * 18);
-            const int tap = s >> 1, ci = 8 * c + 4 * (s & 1) + e;
+            const int tap = s % 9, ci = 8 * c + 4 * (s / 9) + e;
             v = __ldg(jb.w + ((size_t)co * cin + ci) * 9 + tap);
-            hi = jb.fwd + (size_t)c * (2 * 18 * cout * 4) + (size_t)(s * cout + co) * 4 + e;
-            lo = hi + 18 * cout * 4;
+            hi = jb.fwd + (size_t)c * (18 * 2 * cout * 4) + (size_t)(s * 2 * cout + co) * 4 + e;
+            lo = hi + cout * 4;
         } else {
             const int k = i - nf, N = 4 * cin;
             const int e = k & 3, n = (k >> 2) % N, s = (k / (4 * N)) % 8, c = k / (4 * N * 8);
@@ -196,97 +258,186 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
 
 // =============================================================================================================
 // forward:  out = leaky(conv(in, W) + bias)
-//   CTA = 128 output pixels x all COUT channels, 256 threads; the K = 9*CIN reduction runs in stages of 8 input
-//   channels (72 k = 9 MMA k-steps, one per tap): thread (pixel m = t%128, half h = t/128) gathers the 3x3 windows of
-//   4 channels (36 loads in flight, issued one stage ahead), splits them and stores 9 + 9 16-byte chunks.
+//   Persistent, warp-specialised CTA (one per SM): warps 0..7 produce, warp 8 issues the MMAs.
+//   * the prepared weights (B operand) of ALL K stages are brought into shared memory once per CTA (cp.async);
+//   * the im2col A operand never touches shared memory: a tile = 128 output pixels = the 128 TMEM lanes; producer
+//     thread (pixel m = t%128, half h = t/128) gathers the 3x3 windows of 4 channels (one stage = 8 channels = 72 k),
+//     splits them and writes its 36 hi + 36 lo values straight into its TMEM lane (tcgen05.st), into one of two A
+//     buffers; the MMAs take A from tensor memory (with N = 32..64 an A operand in shared memory costs more
+//     shared-memory bandwidth than the MMA costs tensor-pipe time: measured 94 cycles per MMA).  full[]/empty[]
+//     mbarriers hand the buffers to the MMA warp and back (tcgen05.commit);
+//   * per k-step two MMAs:  a_hi x [b_hi | b_lo] (N = 64)  and  a_lo x b_hi (N = 32, accumulating onto columns 0..31);
+//     the epilogue adds the two column blocks, bias, LeakyReLU.
+//   TMEM columns: [0,64) accumulator, then two A buffers of [72 hi | 72 lo].
 // =============================================================================================================
 template <int CIN, int COUT>
-constexpr size_t conv_tc_fwd_smem() { return (size_t)(2 * 18 * 128 * 4 + 2 * 18 * COUT * 4) * sizeof(float); }
+constexpr size_t conv_tc_fwd_smem() { return (size_t)((CIN / 8) * 18 * 2 * COUT * 4) * sizeof(float); }
+
+struct FwdCtl {
+    uint64_t full[2], empty[2], done;
+    uint32_t tmem_base;
+};
 
 template <int CIN, int COUT, int HIN>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(288, 1)
 conv_tc_fwd(const float* __restrict__ in, const float* __restrict__ wprep, const float* __restrict__ bias,
             float* __restrict__ out, int total_px) {
     constexpr int HO = HIN / 2, NST = CIN / 8;
-    constexpr int A_HALF = 18 * 128 * 4, B_HALF = 18 * COUT * 4;  // floats
-    constexpr int TMEM_COLS = 32;
+    constexpr int B_STAGE = 18 * 2 * COUT * 4;      // floats: [18 slots][hi rows | lo rows][4]
+    constexpr uint32_t TMEM_COLS = 512, A_COL0 = 64, A_BUF = 144, A_LO = 72;
     static_assert(COUT == 32, "epilogue assumes 32 output channels");
     extern __shared__ __align__(128) float smem_tc[];
-    __shared__ TcCtl ctl;
-    float* sA = smem_tc;               // [hi|lo][18 slots][128 px][4]
-    float* sB = smem_tc + 2 * A_HALF;  // [hi|lo][18 slots][COUT][4]
-    const int t = threadIdx.x, m = t & 127, h = t >> 7;
-    const uint32_t tmem = tc_setup<TMEM_COLS>(&ctl);
+    __shared__ FwdCtl ctl;
+    float* sB = smem_tc;  // [NST][18 slots][2*COUT rows][4]
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int ntiles = (total_px + 127) / 128;
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    const int gp = blockIdx.x * 128 + m;
-    const bool valid = gp < total_px;
-    const int b = gp / (HO * HO), rem = gp % (HO * HO), oh = rem / HO, ow = rem % HO;
-    const float* in_img = in + (size_t)b * CIN * HIN * HIN;
-    const int ih0 = 2 * oh - 1, iw0 = 2 * ow - 1;
+    DD_TC_STAMP(0);
+    if (warp == 8) tmem_alloc(&ctl.tmem_base, TMEM_COLS);
+    if (t == 0) {
+        mbar_init(&ctl.full[0], 256); mbar_init(&ctl.full[1], 256);
+        mbar_init(&ctl.empty[0], 1); mbar_init(&ctl.empty[1], 1);
+        mbar_init(&ctl.done, 1);
+        fence_mbar_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = ctl.tmem_base;
+    DD_TC_STAMP(1);
 
-    float v[9][4];
-    auto gather = [&](int c) {
+    if (warp < 8) {
+        // ================================ producers + epilogue ================================
+        const int m = t & 127, h = t >> 7, q = warp & 3;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        for (int i = t; i < NST * B_STAGE / 4; i += 256) cp_async16(sB + 4 * i, wprep + 4 * i);
+        cp_async_commit();
+
+        // im2col gather of one stage (4 channels x 3x3 window) into registers: per window row one aligned 64-bit load
+        // (columns 2*ow, 2*ow+1); the left neighbour (column 2*ow-1) comes from the previous lane's load
+        struct Raw {
+            float2 x[12];  // [e*3 + kh]: columns 2*ow, 2*ow+1
+            float own[12]; // column 2*ow-1, loaded by lane 0 only
+        };
+        auto gather = [&](Raw& v, int tile, int c) {
+            const int gp = tile * 128 + m;
+            const bool valid = gp < total_px;
+            const int b = gp / (HO * HO), rem = gp % (HO * HO), oh = rem / HO, ow = rem % HO;
+            const float* img = in + ((size_t)b * CIN + 8 * c + 4 * h) * HIN * HIN + 2 * ow;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float* p = in_img + (size_t)(8 * c + 4 * h + e) * HIN * HIN;
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int ih = 2 * oh - 1 + kh;
+                    const bool ok = valid && ih >= 0;
+                    const float* rp = img + (size_t)e * HIN * HIN + ih * HIN;
+                    v.x[e * 3 + kh] = ok ? __ldg(reinterpret_cast<const float2*>(rp)) : make_float2(0.f, 0.f);
+                    v.own[e * 3 + kh] = (ok && lane == 0 && ow > 0) ? __ldg(rp - 1) : 0.f;
+                }
+        };
+        // stage (it, c) + 2 in this CTA's sequence of stages, if there is one
+        auto gather_ahead = [&](Raw& v, int it, int c) {
+            c += 2;
+            if (c >= NST) { c -= NST; ++it; }
+            if (it < my_tiles) gather(v, blockIdx.x + it * gridDim.x, c);
+        };
+        int g = 0;  // running stage counter (A buffer = g & 1); NST is even, so g & 1 == c & 1
+        auto stage = [&](Raw& v, int it, int c) {
+            const int s = g & 1;
+            if (g >= 2) mbar_wait(&ctl.empty[s], (uint32_t)((g >> 1) - 1) & 1u);  // stage g-2's MMAs have read buffer s
+            fence_after_sync();
+            DD_TC_STAMP(2 + 4 * (g & 7));
+            const bool first_col = (m % HO) == 0;  // ow == 0: HO divides 128, so the column does not depend on the tile
+            // k order within the stage: (half h, tap j, channel e) -> TMEM column h*36 + j*4 + e
+            float hi[36], lo[36];
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int ih = ih0 + kh, iw = iw0 + kw;
-                    v[kh * 3 + kw][e] = (valid && ih >= 0 && iw >= 0) ? __ldg(p + ih * HIN + iw) : 0.f;
+                for (int e = 0; e < 4; ++e) {
+                    const float nb = __shfl_up_sync(0xffffffffu, v.x[e * 3 + kh].y, 1);
+                    const float left = first_col ? 0.f : (lane == 0 ? v.own[e * 3 + kh] : nb);
+                    const float val[3] = {left, v.x[e * 3 + kh].x, v.x[e * 3 + kh].y};
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int k = (kh * 3 + kw) * 4 + e;
+                        hi[k] = tf32_rna(val[kw]);
+                        lo[k] = tf32_rna(val[kw] - hi[k]);
+                    }
                 }
+            const uint32_t a_col = tmem + lane_base + A_COL0 + (uint32_t)s * A_BUF + (uint32_t)h * 36u;
+            tmem_st16(a_col, hi); tmem_st16(a_col + 16, hi + 16); tmem_st4(a_col + 32, hi + 32);
+            tmem_st16(a_col + A_LO, lo); tmem_st16(a_col + A_LO + 16, lo + 16); tmem_st4(a_col + A_LO + 32, lo + 32);
+            tmem_st_wait();
+            fence_before_sync();
+            mbar_arrive(&ctl.full[s]);
+            DD_TC_STAMP(3 + 4 * (g & 7));
+            gather_ahead(v, it, c);
+            DD_TC_STAMP(4 + 4 * (g & 7));
+            ++g;
+        };
+        static_assert(NST % 2 == 0, "two register stages alternate");
+        Raw v0, v1;
+        if (my_tiles > 0) {
+            gather(v0, blockIdx.x, 0);
+            gather(v1, blockIdx.x, 1);
         }
-    };
-    gather(0);
-    constexpr uint32_t idesc = make_idesc(128, COUT, 0, 0);
+        cp_async_wait_all();
+        fence_proxy_async();  // the weights in shared memory are read by the tensor core (async proxy)
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
 #pragma unroll 1
-    for (int c = 0; c < NST; ++c) {
-        if (c > 0) mbar_wait(&ctl.bar, (uint32_t)(c - 1) & 1u);  // the MMAs of the previous stage have read the buffers
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            float4 hi, lo;
-            split4(v[j][0], v[j][1], v[j][2], v[j][3], hi, lo);
-            const int off = ((2 * j + h) * 128 + m) * 4;
-            *reinterpret_cast<float4*>(sA + off) = hi;
-            *reinterpret_cast<float4*>(sA + A_HALF + off) = lo;
-        }
-        {
-            const float4* src = reinterpret_cast<const float4*>(wprep + (size_t)c * 2 * B_HALF);
-            float4* dst = reinterpret_cast<float4*>(sB);
-            for (int i = t; i < 2 * B_HALF / 4; i += 256) dst[i] = __ldg(src + i);
-        }
-        fence_proxy_async();
-        __syncthreads();
-        if (t == 0) {
-            fence_after_sync();
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-#pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                const uint32_t ao = a0 + (uint32_t)(2 * j) * 2048u, bo = b0 + (uint32_t)(2 * j) * (COUT * 16u);
-                mma_3x(tmem, make_desc(ao, 2048u, 128u), make_desc(ao + A_HALF * 4u, 2048u, 128u),
-                       make_desc(bo, COUT * 16u, 128u), make_desc(bo + B_HALF * 4u, COUT * 16u, 128u), idesc,
-                       (c > 0 || j > 0) ? 1u : 0u);
+            for (int c = 0; c < NST; c += 2) {
+                stage(v0, it, c);
+                stage(v1, it, c + 1);
             }
-            mma_commit(&ctl.bar);
-        }
-        if (c + 1 < NST) gather(c + 1);  // overlaps the MMAs
-    }
-    mbar_wait(&ctl.bar, (uint32_t)(NST - 1) & 1u);
-    fence_after_sync();
-    {
-        const int w = t >> 5, lane = t & 31, q = w & 3, half = w >> 2;
-        float r[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 16), r);
-        const int gpe = blockIdx.x * 128 + q * 32 + lane;
-        if (gpe < total_px) {
-            const int be = gpe / (HO * HO), reme = gpe % (HO * HO);
-            float* o = out + ((size_t)be * COUT + half * 16) * (HO * HO) + reme;
+            // epilogue of this tile (the next tile's gathers are already in flight)
+            mbar_wait(&ctl.done, (uint32_t)it & 1u);
+            fence_after_sync();
+            DD_TC_STAMP(40);
+            const int half = warp >> 2;
+            float r0[16], r1[16];
+            tmem_ld16(tmem + lane_base + (uint32_t)(half * 16), r0);
+            tmem_ld16(tmem + lane_base + (uint32_t)(COUT + half * 16), r1);
+            fence_before_sync();  // orders the TMEM reads before the next full[] arrival (the next tile overwrites them)
+            const int gpe = tile * 128 + q * 32 + lane;
+            if (gpe < total_px) {
+                const int be = gpe / (HO * HO), reme = gpe % (HO * HO);
+                float* o = out + ((size_t)be * COUT + half * 16) * (HO * HO) + reme;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[(size_t)i * (HO * HO)] = leaky(r[i] + __ldg(bias + half * 16 + i));
+                for (int i = 0; i < 16; ++i) o[(size_t)i * (HO * HO)] = leaky((r0[i] + r1[i]) + __ldg(bias + half * 16 + i));
+            }
+            DD_TC_STAMP(41);
+        }
+    } else {
+        // ================================ MMA issuer (warp 8) ================================
+        constexpr uint32_t idesc64 = make_idesc(128, 2 * COUT, 0, 0), idesc32 = make_idesc(128, COUT, 0, 0);
+        const uint32_t b_base = smem_u32(sB);
+        const int nstages = my_tiles * NST;
+        for (int g = 0; g < nstages; ++g) {
+            const int s = g & 1, c = g % NST;
+            mbar_wait(&ctl.full[s], (uint32_t)(g >> 1) & 1u);
+            fence_after_sync();
+            DD_TC_STAMP_T(44 + 2 * (g & 7), 256);
+            if (elect_one()) {
+                const uint32_t a0 = tmem + A_COL0 + (uint32_t)s * A_BUF, b0 = b_base + (uint32_t)c * (B_STAGE * 4u);
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    const uint64_t bd = make_desc(b0 + (uint32_t)(2 * j) * (2 * COUT * 16u), 2 * COUT * 16u, 128u);
+                    mma_tf32_ts(tmem, a0 + 8u * j, bd, idesc64, (c > 0 || j > 0) ? 1u : 0u);   // hi x [hi | lo]
+                    mma_tf32_ts(tmem, a0 + A_LO + 8u * j, bd, idesc32, 1u);                     // lo x hi
+                }
+                mma_commit(&ctl.empty[s]);
+                if (c == NST - 1) mma_commit(&ctl.done);
+            }
+            DD_TC_STAMP_T(45 + 2 * (g & 7), 256);
+            __syncwarp();
         }
     }
-    tc_teardown<TMEM_COLS>(tmem);
+    DD_TC_STAMP(42);
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // =============================================================================================================

@@ -259,6 +259,15 @@ static void launch_fwd_tiled(const float* in, const float* w, const float* b, fl
 }
 
 // ---- conv2..conv5: tensor-core kernels (dd_conv_tc.cuh) --------------------------------------------
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
 template <int CIN, int COUT, int HIN>
 static int launch_tc_fwd(const float* in, const float* wprep, const float* bias, float* out, int B, cudaStream_t st) {
     constexpr int HO = HIN / 2;
@@ -269,8 +278,8 @@ static int launch_tc_fwd(const float* in, const float* wprep, const float* bias,
         set_error("cudaFuncSetAttribute(conv_tc_fwd): %s", cudaGetErrorString(e));
         return DD_ERR_CUDA;
     }
-    const int total = B * HO * HO;
-    kern<<<(total + 127) / 128, 256, smem, st>>>(in, wprep, bias, out, total);
+    const int total = B * HO * HO, ntiles = (total + 127) / 128;
+    kern<<<ntiles < sm_count() ? ntiles : sm_count(), 288, smem, st>>>(in, wprep, bias, out, total);  // persistent: <= 1 CTA per SM
     count_launch();
     return DD_OK;
 }

@@ -3,6 +3,7 @@
     python profiles/summarize_launches.py gpurun_out/launches.csv [skip_steps]
 """
 import csv
+import re
 import sys
 from collections import OrderedDict
 
@@ -10,7 +11,7 @@ rows = list(csv.reader(open(sys.argv[1])))
 h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 hdr = rows[h]
 kn, mv, gs, bs = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
-launches = [(r[kn], float(r[mv].replace(",", "")) / 1000.0, r[gs], r[bs]) for r in rows[h + 1:] if len(r) > mv and r[kn].startswith(("dd::", "void dd::"))]
+launches = [(r[kn], float(r[mv].replace(",", "")) / 1000.0, r[gs], r[bs]) for r in rows[h + 1:] if len(r) > mv and re.match(r"(void )?(dd|tc)::", r[kn])]
 # a step starts at every synth kernel
 starts = [i for i, l in enumerate(launches) if "synth_" in l[0] and "finalize" not in l[0]]
 steps = [launches[a:b] for a, b in zip(starts, starts[1:] + [len(launches)])]
