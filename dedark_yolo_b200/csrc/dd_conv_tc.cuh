@@ -5,8 +5,9 @@
 //
 // Precision.  The 1e-5 output gate of the module does not survive TF32 operand rounding, so every operand is split
 // on the fly into  x = hi + lo  (hi = rna_tf32(x), lo = rna_tf32(x - hi); both exactly representable in TF32) and
-// every product is issued as three MMAs  lo*hi + hi*lo + hi*hi  with fp32 accumulation in TMEM ("3xTF32"): the
-// dropped lo*lo term and the rounding of lo are each <= 2^-22 relative.
+// every product is issued as  hi*hi + hi*lo + lo*hi  with fp32 accumulation in TMEM ("3xTF32"; the first two share one
+// MMA whose B operand is the stacked [hi | lo], the epilogue adds the two accumulator column blocks): the dropped
+// lo*lo term and the rounding of lo are each <= 2^-22 relative.
 //
 // Three GEMMs per layer (3x3 / stride 2 / pad 1 conv, Cin -> Cout, input HIN x HIN, output HO = HIN/2):
 //   forward  D[pixel][co]        = sum_{tap,ci}  im2col[pixel][tap,ci] * W[co][ci][tap]            (M=128, N=Cout)
@@ -168,27 +169,14 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 3xTF32: lo*hi + hi*lo + hi*hi (small terms first)
-__device__ __forceinline__ void mma_3x(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
-                                       uint32_t accumulate) {
-    mma_tf32(d, a_lo, b_hi, idesc, accumulate);
-    mma_tf32(d, a_hi, b_lo, idesc, 1u);
-    mma_tf32(d, a_hi, b_hi, idesc, 1u);
-}
-
 // ---- operand split -----------------------------------------------------------------------------------------
 // round to nearest (ties away from zero) to TF32's 10 explicit mantissa bits == cvt.rna.tf32.f32, done as two integer
 // ops on the ALU pipe (the conversion instruction is rate-limited: it cost ~1000 cycles per 128x72 stage)
 __device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-__device__ __forceinline__ void split4(const float v0, const float v1, const float v2, const float v3, float4& hi, float4& lo) {
-    hi.x = tf32_rna(v0); hi.y = tf32_rna(v1); hi.z = tf32_rna(v2); hi.w = tf32_rna(v3);
-    lo.x = tf32_rna(v0 - hi.x); lo.y = tf32_rna(v1 - hi.y); lo.z = tf32_rna(v2 - hi.z); lo.w = tf32_rna(v3 - hi.w);
-}
-
 // ---- prepared weights (one launch per forward; the weights change every optimizer step) ----------------------
 // per layer l = 1..4 (conv2..conv5), floats:
 //   fwd  : [stage c = ci/8][slot s = 9*((ci%8)/4) + tap][row = co (hi) | COUT + co (lo)][e = ci%4] = 2 * 9*CIN*COUT
-//   dgrad: [stage c = co/8][hi|lo][slot s = co%8][n = ci*4 + py*2 + px][e = da*2 + dc]     = 2 * 16*CIN*COUT
+//   dgrad: [stage c = co/8][slot s = co%8][row = n (hi) | 4*CIN + n (lo); n = ci*4 + py*2 + px][e = da*2 + dc] = 2 * 16*CIN*COUT
 __host__ __device__ constexpr int prep_fwd_elems(int cin, int cout) { return 2 * 9 * cin * cout; }
 __host__ __device__ constexpr int prep_dgrad_elems(int cin, int cout) { return 2 * 16 * cin * cout; }
 
@@ -222,38 +210,13 @@ prep_weights_kernel(PrepJobs jobs) {
             const int co = 8 * c + s, ci = n >> 2, py = (n >> 1) & 1, px = n & 1, da = e >> 1, dc = e & 1;
             const int kh = py - 2 * da + 1, kw = px - 2 * dc + 1;
             v = (kh >= 0 && kw >= 0) ? __ldg(jb.w + ((size_t)co * cin + ci) * 9 + kh * 3 + kw) : 0.f;  // kh, kw <= 2 always
-            hi = jb.dgrad + (size_t)c * (2 * 8 * N * 4) + (size_t)(s * N + n) * 4 + e;
-            lo = hi + 8 * N * 4;
+            hi = jb.dgrad + (size_t)c * (8 * 2 * N * 4) + (size_t)(s * 2 * N + n) * 4 + e;
+            lo = hi + N * 4;
         }
         const float h = tf32_rna(v);
         *hi = h;
         *lo = tf32_rna(v - h);
     }
-}
-
-// ---- shared bookkeeping of the three kernels -----------------------------------------------------------------
-struct TcCtl {
-    uint64_t bar;        // MMA-completion barrier (one arrival per commit)
-    uint32_t tmem_base;  // written by tcgen05.alloc
-};
-
-template <int TMEM_COLS>
-__device__ __forceinline__ uint32_t tc_setup(TcCtl* ctl) {
-    if (threadIdx.x < 32) tmem_alloc(&ctl->tmem_base, TMEM_COLS);
-    if (threadIdx.x == 32) {
-        mbar_init(&ctl->bar, 1);
-        fence_mbar_init();
-    }
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    return ctl->tmem_base;
-}
-template <int TMEM_COLS>
-__device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
-    fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // =============================================================================================================
@@ -441,122 +404,170 @@ conv_tc_fwd(const float* __restrict__ in, const float* __restrict__ wprep, const
 }
 
 // =============================================================================================================
-// data gradient:  din = leaky'(act_in) * conv_transpose(dpre, W)      (gradient w.r.t. the previous PRE-activation)
-//   CTA = 128 quads x all 4*CIN (channel, parity) columns; K = 4*COUT runs in stages of 8 output channels
-//   (32 k = 4 MMA k-steps): thread (quad m, half h) loads the 2x2 neighbourhoods of 4 channels.
+// backward of one layer in ONE launch of persistent, warp-specialised CTAs (one per SM, 288 threads: warps 0..7
+// produce operands and run the epilogue, warp 8 issues the MMAs): the first n_w CTAs accumulate weight-gradient
+// slices, the others compute the data gradient (the two are independent given dpre).
 // =============================================================================================================
+struct BwdCtl {
+    uint64_t full[2], empty[2], done;
+    uint32_t tmem_base;
+};
+constexpr uint32_t kBwdTmemCols = 512;
+
+// -------------------------------------------------------------------------------------------------------------
+// data gradient:  din = leaky'(act_in) * conv_transpose(dpre, W)      (gradient w.r.t. the previous PRE-activation)
+//   tile = 128 quads = the 128 TMEM lanes, N = 4*CIN (channel, parity) columns; K = 4*COUT runs in stages of 8 output
+//   channels (32 k = 4 MMA k-steps).  Producer thread (quad m, half h) loads the 2x2 neighbourhoods of 4 channels,
+//   splits them and writes 16 hi + 16 lo values into its TMEM lane (A operand in tensor memory); the prepared
+//   weights of all stages stay in shared memory.  Per k-step:  a_hi x [w_hi | w_lo] (N = 8*CIN)  and  a_lo x w_hi.
+//   TMEM columns: [0, 8*CIN) accumulator, then two A buffers of [32 hi | 32 lo].
+// -------------------------------------------------------------------------------------------------------------
 template <int CIN, int COUT>
-constexpr size_t conv_tc_dgrad_smem() { return (size_t)(2 * 8 * 128 * 4 + 2 * 8 * 4 * CIN * 4) * sizeof(float); }
+constexpr size_t conv_tc_dgrad_smem() { return (size_t)((COUT / 8) * 8 * 2 * 4 * CIN * 4) * sizeof(float); }
 
 template <int CIN, int COUT, int HIN>
-__device__ __forceinline__ void conv_tc_dgrad_body(const int bid, const float* __restrict__ dpre, const float* __restrict__ wprep,
-                                                   const float* __restrict__ act_in, float* __restrict__ din, int total_q,
-                                                   float* smem, TcCtl* ctl) {
+__device__ __forceinline__ void conv_tc_dgrad_body(const int cta, const int nctas, const float* __restrict__ dpre,
+                                                   const float* __restrict__ wprep, const float* __restrict__ act_in,
+                                                   float* __restrict__ din, int total_q, float* smem, BwdCtl* ctl) {
     constexpr int HO = HIN / 2, NST = COUT / 8, N = 4 * CIN;
-    constexpr int A_HALF = 8 * 128 * 4, B_HALF = 8 * N * 4;  // floats
-    constexpr int TMEM_COLS = N < 32 ? 32 : N;
-    float* sA = smem;               // [hi|lo][8 slots][128 quads][4]
-    float* sB = smem + 2 * A_HALF;  // [hi|lo][8 slots][N][4]
-    const int t = threadIdx.x, m = t & 127, h = t >> 7;
-    const uint32_t tmem = tc_setup<TMEM_COLS>(ctl);
+    constexpr int B_STAGE = 8 * 2 * N * 4;  // floats: [8 slots][hi rows | lo rows][4]
+    constexpr uint32_t A_COL0 = 2 * N, A_BUF = 64, A_LO = 32;
+    static_assert(NST % 2 == 0 && A_COL0 + 2 * A_BUF <= kBwdTmemCols, "layout");
+    float* sB = smem;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t tmem = ctl->tmem_base;
+    const int ntiles = (total_q + 127) / 128;
+    const int my_tiles = (cta < ntiles) ? (ntiles - 1 - cta) / nctas + 1 : 0;
 
-    const int gq = bid * 128 + m;
-    const bool valid = gq < total_q;
-    const int b = gq / (HO * HO), rem = gq % (HO * HO), a = rem / HO, cq = rem % HO;
-    const bool a1 = valid && (a + 1 < HO), c1 = cq + 1 < HO;
-    const float* dimg = dpre + (size_t)b * COUT * HO * HO + rem;
+    if (warp < 8) {
+        const int m = t & 127, h = t >> 7, q = warp & 3, half = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        for (int i = t; i < NST * B_STAGE / 4; i += 256) cp_async16(sB + 4 * i, wprep + 4 * i);
+        cp_async_commit();
 
-    float v[4][4];
-    auto gather = [&](int c) {
+        struct Raw { float v[16]; };  // [channel e][nb = da*2 + dc]
+        auto gather = [&](Raw& r, int tile, int c) {
+            const int gq = tile * 128 + m;
+            const bool valid = gq < total_q;
+            const int b = gq / (HO * HO), rem = gq % (HO * HO), a = rem / HO, cq = rem % HO;
+            const bool a1 = valid && (a + 1 < HO), c1 = cq + 1 < HO;
+            const float* p0 = dpre + ((size_t)b * COUT + 8 * c + 4 * h) * HO * HO + rem;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float* p = dimg + (size_t)(8 * c + 4 * h + e) * HO * HO;
-            v[e][0] = valid ? __ldg(p) : 0.f;
-            v[e][1] = (valid && c1) ? __ldg(p + 1) : 0.f;
-            v[e][2] = a1 ? __ldg(p + HO) : 0.f;
-            v[e][3] = (a1 && c1) ? __ldg(p + HO + 1) : 0.f;
-        }
-    };
-    gather(0);
-    constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
-#pragma unroll 1
-    for (int c = 0; c < NST; ++c) {
-        if (c > 0) mbar_wait(&ctl->bar, (uint32_t)(c - 1) & 1u);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float4 hi, lo;
-            split4(v[e][0], v[e][1], v[e][2], v[e][3], hi, lo);
-            const int off = ((4 * h + e) * 128 + m) * 4;
-            *reinterpret_cast<float4*>(sA + off) = hi;
-            *reinterpret_cast<float4*>(sA + A_HALF + off) = lo;
-        }
-        {
-            const float4* src = reinterpret_cast<const float4*>(wprep + (size_t)c * 2 * B_HALF);
-            float4* dst = reinterpret_cast<float4*>(sB);
-            for (int i = t; i < 2 * B_HALF / 4; i += 256) dst[i] = __ldg(src + i);
-        }
-        fence_proxy_async();
-        __syncthreads();
-        if (t == 0) {
-            fence_after_sync();
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t ao = a0 + (uint32_t)(2 * j) * 2048u, bo = b0 + (uint32_t)(2 * j) * (N * 16u);
-                mma_3x(tmem, make_desc(ao, 2048u, 128u), make_desc(ao + A_HALF * 4u, 2048u, 128u),
-                       make_desc(bo, N * 16u, 128u), make_desc(bo + B_HALF * 4u, N * 16u, 128u), idesc,
-                       (c > 0 || j > 0) ? 1u : 0u);
+            for (int e = 0; e < 4; ++e) {
+                const float* p = p0 + (size_t)e * HO * HO;
+                r.v[4 * e + 0] = valid ? __ldg(p) : 0.f;
+                r.v[4 * e + 1] = (valid && c1) ? __ldg(p + 1) : 0.f;
+                r.v[4 * e + 2] = a1 ? __ldg(p + HO) : 0.f;
+                r.v[4 * e + 3] = (a1 && c1) ? __ldg(p + HO + 1) : 0.f;
             }
-            mma_commit(&ctl->bar);
-        }
-        if (c + 1 < NST) gather(c + 1);
-    }
-    mbar_wait(&ctl->bar, (uint32_t)(NST - 1) & 1u);
-    fence_after_sync();
-    {
-        const int w = t >> 5, lane = t & 31, q = w & 3, half = w >> 2;
-        const int gqe = bid * 128 + q * 32 + lane;
-        const bool ok = gqe < total_q;
-        const int be = gqe / (HO * HO), reme = gqe % (HO * HO), ae = reme / HO, ce = reme % HO;
-        // columns [half*N/2, (half+1)*N/2): CIN/2 channels x 4 parities, 4 channels (16 columns) per TMEM load
-#pragma unroll 1
-        for (int g = 0; g < N / 32; ++g) {
-            float r[16];
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (N / 2) + g * 16), r);
-            if (ok) {
+        };
+        auto gather_ahead = [&](Raw& r, int it, int c) {
+            c += 2;
+            if (c >= NST) { c -= NST; ++it; }
+            if (it < my_tiles) gather(r, cta + it * nctas, c);
+        };
+        int g = 0;
+        auto stage = [&](Raw& r, int it, int c) {
+            const int s = g & 1;
+            if (g >= 2) mbar_wait(&ctl->empty[s], (uint32_t)((g >> 1) - 1) & 1u);
+            fence_after_sync();
+            float hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int ci = half * (CIN / 2) + g * 4 + i;
-                    const size_t base = (((size_t)be * CIN + ci) * HIN + 2 * ae) * HIN + 2 * ce;
-                    float2 top = make_float2(r[4 * i + 0], r[4 * i + 1]), bot = make_float2(r[4 * i + 2], r[4 * i + 3]);
-                    const float2 at = *reinterpret_cast<const float2*>(act_in + base);
-                    const float2 ab = *reinterpret_cast<const float2*>(act_in + base + HIN);
-                    top.x = leaky_grad(at.x, top.x); top.y = leaky_grad(at.y, top.y);
-                    bot.x = leaky_grad(ab.x, bot.x); bot.y = leaky_grad(ab.y, bot.y);
-                    *reinterpret_cast<float2*>(din + base) = top;
-                    *reinterpret_cast<float2*>(din + base + HIN) = bot;
+            for (int k = 0; k < 16; ++k) {
+                hi[k] = tf32_rna(r.v[k]);
+                lo[k] = tf32_rna(r.v[k] - hi[k]);
+            }
+            const uint32_t a_col = tmem + lane_base + A_COL0 + (uint32_t)s * A_BUF + (uint32_t)h * 16u;
+            tmem_st16(a_col, hi);
+            tmem_st16(a_col + A_LO, lo);
+            tmem_st_wait();
+            fence_before_sync();
+            mbar_arrive(&ctl->full[s]);
+            gather_ahead(r, it, c);
+            ++g;
+        };
+        Raw r0, r1;
+        if (my_tiles > 0) {
+            gather(r0, cta, 0);
+            gather(r1, cta, 1);
+        }
+        cp_async_wait_all();
+        fence_proxy_async();
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = cta + it * nctas;
+#pragma unroll 1
+            for (int c = 0; c < NST; c += 2) {
+                stage(r0, it, c);
+                stage(r1, it, c + 1);
+            }
+            mbar_wait(&ctl->done, (uint32_t)it & 1u);
+            fence_after_sync();
+            const int gqe = tile * 128 + q * 32 + lane;
+            const bool ok = gqe < total_q;
+            const int be = gqe / (HO * HO), reme = gqe % (HO * HO), ae = reme / HO, ce = reme % HO;
+            // columns [half*N/2, (half+1)*N/2) (+ N for the hi x lo block): CIN/2 channels x 4 parities, 4 channels per load
+#pragma unroll 1
+            for (int gg = 0; gg < N / 32; ++gg) {
+                float ra[16], rb[16];
+                tmem_ld16(tmem + lane_base + (uint32_t)(half * (N / 2) + gg * 16), ra);
+                tmem_ld16(tmem + lane_base + (uint32_t)(N + half * (N / 2) + gg * 16), rb);
+                if (ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int ci = half * (CIN / 2) + gg * 4 + i;
+                        const size_t base = (((size_t)be * CIN + ci) * HIN + 2 * ae) * HIN + 2 * ce;
+                        float2 top = make_float2(ra[4 * i + 0] + rb[4 * i + 0], ra[4 * i + 1] + rb[4 * i + 1]);
+                        float2 bot = make_float2(ra[4 * i + 2] + rb[4 * i + 2], ra[4 * i + 3] + rb[4 * i + 3]);
+                        const float2 at = *reinterpret_cast<const float2*>(act_in + base);
+                        const float2 ab = *reinterpret_cast<const float2*>(act_in + base + HIN);
+                        top.x = leaky_grad(at.x, top.x); top.y = leaky_grad(at.y, top.y);
+                        bot.x = leaky_grad(ab.x, bot.x); bot.y = leaky_grad(ab.y, bot.y);
+                        *reinterpret_cast<float2*>(din + base) = top;
+                        *reinterpret_cast<float2*>(din + base + HIN) = bot;
+                    }
                 }
             }
+            fence_before_sync();
+        }
+    } else {
+        constexpr uint32_t idesc_2n = make_idesc(128, 2 * N, 0, 0), idesc_n = make_idesc(128, N, 0, 0);
+        const uint32_t b_base = smem_u32(sB);
+        const int nstages = my_tiles * NST;
+        for (int g = 0; g < nstages; ++g) {
+            const int s = g & 1, c = g % NST;
+            mbar_wait(&ctl->full[s], (uint32_t)(g >> 1) & 1u);
+            fence_after_sync();
+            if (elect_one()) {
+                const uint32_t a0 = tmem + A_COL0 + (uint32_t)s * A_BUF, b0 = b_base + (uint32_t)c * (B_STAGE * 4u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t bd = make_desc(b0 + (uint32_t)(2 * j) * (2 * N * 16u), 2 * N * 16u, 128u);
+                    mma_tf32_ts(tmem, a0 + 8u * j, bd, idesc_2n, (c > 0 || j > 0) ? 1u : 0u);  // hi x [hi | lo]
+                    mma_tf32_ts(tmem, a0 + A_LO + 8u * j, bd, idesc_n, 1u);                    // lo x hi
+                }
+                mma_commit(&ctl->empty[s]);
+                if (c == NST - 1) mma_commit(&ctl->done);
+            }
+            __syncwarp();
         }
     }
-    tc_teardown<TMEM_COLS>(tmem);
 }
 
-// =============================================================================================================
+// -------------------------------------------------------------------------------------------------------------
 // weight + bias gradient.  Rows r = tap*CIN + ci (r = 9*CIN: the row of ones -> bias gradient), padded to RP.
 //   CTA = a contiguous range of pixel tiles (PXT pixels = PXT/8 MMA k-steps each); accumulators for all rows stay in
-//   TMEM (NBLK blocks of 128 rows x COUT columns; the last block overlaps its predecessor so that every block is a
-//   full M = 128) until the range is done, then one slice [RP][COUT] of partial sums goes to global memory.
-//   Thread (pixel p = t % PXT, group w = t / PXT): 4 channels x 9 taps.  Both operands are K-major with K = pixels:
-//   [chunk = pixel/4][row][4 pixels], 4-byte stores; the row count is padded to 1 (mod 8) so that the 32 lanes of a
-//   warp (consecutive pixels, one row) hit 32 different banks.
-// =============================================================================================================
+//   TMEM (NBLK blocks of 128 rows; the last block overlaps its predecessor so that every block is a full M = 128)
+//   until the range is done, then one slice [RP][COUT] of partial sums goes to global memory.
+//   Producer thread (pixel p = t % PXT, group w = t / PXT): 4 channels x 9 taps.  Both operands are K-major with
+//   K = pixels: [chunk = pixel/4][row][4 pixels], 4-byte stores; the row pitch is 1 (mod 8) chunks so that the 32
+//   lanes of a warp (consecutive pixels, one row) hit 32 different banks.  Two operand buffers alternate.
+//   Per (block, k-step):  a_hi x [d_hi | d_lo] (N = 64)  and  a_lo x d_hi (N = 32).  TMEM: block b at columns 64*b.
+// -------------------------------------------------------------------------------------------------------------
 template <int CIN>
 struct WgradCfg {
     static constexpr int PXT = 256 / (CIN / 4);              // CIN=32: 32 pixels, CIN=16: 64 pixels
     static constexpr int ROWS = 9 * CIN + 1;                 // + ones row
-    static constexpr int NCH = (ROWS + 3) / 4;               // 16-byte chunks along the rows
-    static constexpr int RP = NCH * 4;
+    static constexpr int RP = (ROWS + 3) / 4 * 4;
     static constexpr int NBLK = (RP + 127) / 128;
     static constexpr int RPAD = (RP + 7) / 8 * 8 + 1;        // smem row pitch (in 16-byte chunks), == 1 (mod 8)
     __host__ __device__ static constexpr int row0(int blk) { return blk + 1 < NBLK ? blk * 128 : RP - 128; }
@@ -564,150 +575,190 @@ struct WgradCfg {
 template <int CIN, int COUT>
 constexpr size_t conv_tc_wgrad_smem() {
     using Cfg = WgradCfg<CIN>;
-    return (size_t)(2 * (Cfg::PXT / 4) * Cfg::RPAD * 4 + 2 * (Cfg::PXT / 4) * (COUT + 1) * 4) * sizeof(float);
+    return (size_t)2 * (2 * (Cfg::PXT / 4) * Cfg::RPAD * 4 + (Cfg::PXT / 4) * (2 * COUT + 1) * 4) * sizeof(float);
 }
 
 template <int CIN, int COUT, int HIN>
-__device__ __forceinline__ void conv_tc_wgrad_body(const int bid, const int nslices, const float* __restrict__ in,
+__device__ __forceinline__ void conv_tc_wgrad_body(const int cta, const int nslices, const float* __restrict__ in,
                                                    const float* __restrict__ dpre, float* __restrict__ partial, int total_px,
-                                                   float* smem, TcCtl* ctl) {
+                                                   float* smem, BwdCtl* ctl) {
     using Cfg = WgradCfg<CIN>;
-    constexpr int HO = HIN / 2, PXT = Cfg::PXT, NBLK = Cfg::NBLK, RP = Cfg::RP, RPAD = Cfg::RPAD, CPAD = COUT + 1;
-    constexpr int A_HALF = (PXT / 4) * RPAD * 4, B_HALF = (PXT / 4) * CPAD * 4;  // floats
-    constexpr int TMEM_COLS = NBLK * COUT <= 32 ? 32 : NBLK * COUT <= 64 ? 64 : 128;
-    static_assert(COUT == 32, "epilogue assumes 32 output channels");
-    float* sA = smem;               // [hi|lo][PXT/4][RPAD rows][4 pixels]
-    float* sB = smem + 2 * A_HALF;  // [hi|lo][PXT/4][CPAD channels][4 pixels]
-    const int t = threadIdx.x, p = t % PXT, w = t / PXT;  // w = group of 4 input channels
-    const uint32_t tmem = tc_setup<TMEM_COLS>(ctl);
-
-    // the rows 9*CIN .. RP-1: ones (bias gradient) + zero padding, written once
-    for (int i = t; i < PXT * 4; i += 256) {
-        const int pp = i % PXT, rr = 9 * CIN + i / PXT, off = ((pp >> 2) * RPAD + rr) * 4 + (pp & 3);
-        sA[off] = rr == 9 * CIN ? 1.f : 0.f;
-        sA[A_HALF + off] = 0.f;
-    }
+    constexpr int HO = HIN / 2, PXT = Cfg::PXT, NBLK = Cfg::NBLK, RP = Cfg::RP, RPAD = Cfg::RPAD, CPAD = 2 * COUT + 1;
+    constexpr int A_HALF = (PXT / 4) * RPAD * 4, B_SZ = (PXT / 4) * CPAD * 4;  // floats
+    constexpr int BUF = 2 * A_HALF + B_SZ;
+    constexpr int NDV = (COUT / 4) * PXT / 256;
+    static_assert(COUT == 32 && NBLK * 64 <= (int)kBwdTmemCols, "layout");
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t tmem = ctl->tmem_base;
     const int ntiles = (total_px + PXT - 1) / PXT;
-    const int t0 = (int)((long long)ntiles * bid / nslices), t1 = (int)((long long)ntiles * (bid + 1) / nslices);
+    const int t0 = (int)((long long)ntiles * cta / nslices), t1 = (int)((long long)ntiles * (cta + 1) / nslices);
+    float* slice = partial + (size_t)cta * RP * COUT;
 
-    float v[9][4];
-    float dv[(COUT / 4) * PXT / 256][4];
-    auto gather = [&](int tile) {
-        const int gp = tile * PXT + p;
-        const bool valid = gp < total_px;
-        const int b = gp / (HO * HO), rem = gp % (HO * HO), oh = rem / HO, ow = rem % HO;
-        const int ih0 = 2 * oh - 1, iw0 = 2 * ow - 1;
+    if (warp < 8) {
+        const int p = t % PXT, w = t / PXT;  // w = group of 4 input channels
+        // rows 9*CIN .. RP-1 of both buffers: ones (bias gradient) + zero padding, written once
+        for (int i = t; i < 2 * PXT * 4; i += 256) {
+            const int bf = i / (PXT * 4), k = i % (PXT * 4), pp = k % PXT, rr = 9 * CIN + k / PXT;
+            const int off = bf * BUF + ((pp >> 2) * RPAD + rr) * 4 + (pp & 3);
+            smem[off] = rr == 9 * CIN ? 1.f : 0.f;
+            smem[off + A_HALF] = 0.f;
+        }
+        struct Raw {
+            float2 x[12];
+            float own[12];
+            float dv[NDV][4];
+        };
+        auto gather = [&](Raw& v, int tile) {
+            const int gp = tile * PXT + p;
+            const bool valid = gp < total_px;
+            const int b = gp / (HO * HO), rem = gp % (HO * HO), oh = rem / HO, ow = rem % HO;
+            const float* img = in + ((size_t)b * CIN + 4 * w) * HIN * HIN + 2 * ow;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float* q = in + ((size_t)b * CIN + 4 * w + e) * HIN * HIN;
+            for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int ih = ih0 + kh, iw = iw0 + kw;
-                    v[kh * 3 + kw][e] = (valid && ih >= 0 && iw >= 0) ? __ldg(q + ih * HIN + iw) : 0.f;
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int ih = 2 * oh - 1 + kh;
+                    const bool ok = valid && ih >= 0;
+                    const float* rp = img + (size_t)e * HIN * HIN + ih * HIN;
+                    v.x[e * 3 + kh] = ok ? __ldg(reinterpret_cast<const float2*>(rp)) : make_float2(0.f, 0.f);
+                    v.own[e * 3 + kh] = (ok && lane == 0 && ow > 0) ? __ldg(rp - 1) : 0.f;
                 }
-        }
-        // dOut chunks: (COUT/4) * PXT chunks per tile, one or two per thread
 #pragma unroll
-        for (int u = 0; u < (COUT / 4) * PXT / 256; ++u) {
-            const int idx = t + u * 256, pp = idx % PXT, g = idx / PXT;
-            const int gpp = tile * PXT + pp;
-            const int bb = gpp / (HO * HO), rr = gpp % (HO * HO);
-            const float* d = dpre + ((size_t)bb * COUT + 4 * g) * HO * HO + rr;
+            for (int u = 0; u < NDV; ++u) {
+                const int idx = t + u * 256, pp = idx % PXT, gch = idx / PXT;
+                const int gpp = tile * PXT + pp;
+                const int bb = gpp / (HO * HO), rr = gpp % (HO * HO);
+                const float* d = dpre + ((size_t)bb * COUT + 4 * gch) * HO * HO + rr;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) dv[u][e] = gpp < total_px ? __ldg(d + (size_t)e * HO * HO) : 0.f;
-        }
-    };
-    constexpr uint32_t idesc = make_idesc(128, COUT, 0, 0);
-    uint32_t phase = 0;
-    if (t0 < t1) gather(t0);
-#pragma unroll 1
-    for (int tile = t0; tile < t1; ++tile) {
-        if (tile > t0) {
-            mbar_wait(&ctl->bar, phase);
-            phase ^= 1u;
-        }
-        {
-            float* dst = sA + ((p >> 2) * RPAD + 4 * w) * 4 + (p & 3);
+                for (int e = 0; e < 4; ++e) v.dv[u][e] = gpp < total_px ? __ldg(d + (size_t)e * HO * HO) : 0.f;
+            }
+        };
+        int g = 0;
+        auto stage = [&](Raw& v, int tile) {
+            const int s = g & 1;
+            if (g >= 2) mbar_wait(&ctl->empty[s], (uint32_t)((g >> 1) - 1) & 1u);
+            float* sA = smem + s * BUF;
+            float* sB = sA + 2 * A_HALF;
+            const bool first_col = (p % HO) == 0;  // ow == 0 (HO divides PXT or PXT divides HO: the column is tile-independent)
+            {
+                float* dst = sA + ((p >> 2) * RPAD + 4 * w) * 4 + (p & 3);
 #pragma unroll
-            for (int j = 0; j < 9; ++j)
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float nb = __shfl_up_sync(0xffffffffu, v.x[e * 3 + kh].y, 1);
+                        const float left = first_col ? 0.f : (lane == 0 ? v.own[e * 3 + kh] : nb);
+                        const float val[3] = {left, v.x[e * 3 + kh].x, v.x[e * 3 + kh].y};
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const float hi = tf32_rna(val[kw]);
+                            dst[((kh * 3 + kw) * CIN + e) * 4] = hi;
+                            dst[A_HALF + ((kh * 3 + kw) * CIN + e) * 4] = tf32_rna(val[kw] - hi);
+                        }
+                    }
+            }
+#pragma unroll
+            for (int u = 0; u < NDV; ++u) {
+                const int idx = t + u * 256, pp = idx % PXT, gch = idx / PXT;
+                float* dst = sB + ((pp >> 2) * CPAD + 4 * gch) * 4 + (pp & 3);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float hi = tf32_rna(v[j][e]);
-                    dst[(j * CIN + e) * 4] = hi;
-                    dst[A_HALF + (j * CIN + e) * 4] = tf32_rna(v[j][e] - hi);
+                    const float hi = tf32_rna(v.dv[u][e]);
+                    dst[e * 4] = hi;
+                    dst[(COUT + e) * 4] = tf32_rna(v.dv[u][e] - hi);
                 }
-        }
-#pragma unroll
-        for (int u = 0; u < (COUT / 4) * PXT / 256; ++u) {
-            const int idx = t + u * 256, pp = idx % PXT, g = idx / PXT;
-            float* dst = sB + ((pp >> 2) * CPAD + 4 * g) * 4 + (pp & 3);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float hi = tf32_rna(dv[u][e]);
-                dst[e * 4] = hi;
-                dst[B_HALF + e * 4] = tf32_rna(dv[u][e] - hi);
             }
+            fence_proxy_async();
+            mbar_arrive(&ctl->full[s]);
+            if (tile + 2 < t1) gather(v, tile + 2);
+            ++g;
+        };
+        Raw v0, v1;
+        if (t0 < t1) gather(v0, t0);
+        if (t0 + 1 < t1) gather(v1, t0 + 1);
+#pragma unroll 1
+        for (int tile = t0; tile < t1; tile += 2) {
+            stage(v0, tile);
+            if (tile + 1 < t1) stage(v1, tile + 1);
         }
-        fence_proxy_async();
-        __syncthreads();
-        if (t == 0) {
+        if (t0 < t1) {
+            mbar_wait(&ctl->done, 0u);
             fence_after_sync();
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            const int q = warp & 3, half = warp >> 2;
 #pragma unroll
             for (int blk = 0; blk < NBLK; ++blk) {
+                float ra[16], rb[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 64 + half * 16), ra);
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 64 + COUT + half * 16), rb);
+                const int row = Cfg::row0(blk) + q * 32 + lane;
+                if (row >= blk * 128) {  // the overlapping part of the last block was already written
+                    float4* o = reinterpret_cast<float4*>(slice + (size_t)row * COUT + half * 16);
 #pragma unroll
-                for (int ks = 0; ks < PXT / 8; ++ks) {
-                    const uint32_t ao = a0 + (uint32_t)(2 * ks * RPAD + Cfg::row0(blk)) * 16u;
-                    const uint32_t bo = b0 + (uint32_t)(2 * ks * CPAD) * 16u;
-                    mma_3x(tmem + (uint32_t)(blk * COUT), make_desc(ao, RPAD * 16u, 128u), make_desc(ao + A_HALF * 4u, RPAD * 16u, 128u),
-                           make_desc(bo, CPAD * 16u, 128u), make_desc(bo + B_HALF * 4u, CPAD * 16u, 128u), idesc,
-                           (tile > t0 || ks > 0) ? 1u : 0u);
+                    for (int i = 0; i < 4; ++i)
+                        o[i] = make_float4(ra[4 * i] + rb[4 * i], ra[4 * i + 1] + rb[4 * i + 1], ra[4 * i + 2] + rb[4 * i + 2],
+                                           ra[4 * i + 3] + rb[4 * i + 3]);
                 }
             }
-            mma_commit(&ctl->bar);
-        }
-        if (tile + 1 < t1) gather(tile + 1);
-    }
-    float* slice = partial + (size_t)bid * RP * COUT;
-    if (t0 < t1) {
-        mbar_wait(&ctl->bar, phase);
-        fence_after_sync();
-        const int wp = t >> 5, lane = t & 31, q = wp & 3, half = wp >> 2;
-#pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk) {
-            float r[16];
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * COUT + half * 16), r);
-            const int row = Cfg::row0(blk) + q * 32 + lane;
-            if (blk == 0 || row >= blk * 128) {  // the overlapping part of the last block was already written
-                float4* o = reinterpret_cast<float4*>(slice + (size_t)row * COUT + half * 16);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) o[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-            }
+            fence_before_sync();
+        } else {
+            for (int i = t; i < RP * COUT; i += 256) slice[i] = 0.f;
         }
     } else {
-        for (int i = t; i < RP * COUT; i += 256) slice[i] = 0.f;
+        constexpr uint32_t idesc64 = make_idesc(128, 2 * COUT, 0, 0), idesc32 = make_idesc(128, COUT, 0, 0);
+        const uint32_t base = smem_u32(smem);
+        for (int tile = t0, g = 0; tile < t1; ++tile, ++g) {
+            const int s = g & 1;
+            mbar_wait(&ctl->full[s], (uint32_t)(g >> 1) & 1u);
+            fence_after_sync();
+            if (elect_one()) {
+                const uint32_t a0 = base + (uint32_t)s * (BUF * 4u), b0 = a0 + 2 * A_HALF * 4u;
+#pragma unroll
+                for (int blk = 0; blk < NBLK; ++blk) {
+#pragma unroll
+                    for (int ks = 0; ks < PXT / 8; ++ks) {
+                        const uint32_t ao = a0 + (uint32_t)(2 * ks * RPAD + Cfg::row0(blk)) * 16u;
+                        const uint64_t bd = make_desc(b0 + (uint32_t)(2 * ks * CPAD) * 16u, CPAD * 16u, 128u);
+                        mma_tf32(tmem + (uint32_t)(blk * 64), make_desc(ao, RPAD * 16u, 128u), bd, idesc64, (g > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32(tmem + (uint32_t)(blk * 64), make_desc(ao + A_HALF * 4u, RPAD * 16u, 128u), bd, idesc32, 1u);
+                    }
+                }
+                mma_commit(&ctl->empty[s]);
+                if (tile == t1 - 1) mma_commit(&ctl->done);
+            }
+            __syncwarp();
+        }
     }
-    tc_teardown<TMEM_COLS>(tmem);
 }
 
-// one launch per layer: the first n_w CTAs compute weight-gradient slices, the rest the data gradient
 template <int CIN, int COUT, int HIN>
 constexpr size_t conv_tc_bwd_smem() {
     return conv_tc_wgrad_smem<CIN, COUT>() > conv_tc_dgrad_smem<CIN, COUT>() ? conv_tc_wgrad_smem<CIN, COUT>()
                                                                               : conv_tc_dgrad_smem<CIN, COUT>();
 }
 template <int CIN, int COUT, int HIN>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(288, 1)
 conv_tc_bwd(const float* __restrict__ in, const float* __restrict__ dpre, const float* __restrict__ wprep_dgrad,
             const float* __restrict__ act_in, float* __restrict__ partial, float* __restrict__ din, int n_w, int total_px) {
     extern __shared__ __align__(128) float smem_tc[];
-    __shared__ TcCtl ctl;
+    __shared__ BwdCtl ctl;
+    const int t = threadIdx.x, warp = t >> 5;
+    if (warp == 8) tmem_alloc(&ctl.tmem_base, kBwdTmemCols);
+    if (t == 0) {
+        mbar_init(&ctl.full[0], 256); mbar_init(&ctl.full[1], 256);
+        mbar_init(&ctl.empty[0], 1); mbar_init(&ctl.empty[1], 1);
+        mbar_init(&ctl.done, 1);
+        fence_mbar_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
     if ((int)blockIdx.x < n_w)
         conv_tc_wgrad_body<CIN, COUT, HIN>(blockIdx.x, n_w, in, dpre, partial, total_px, smem_tc, &ctl);
     else
-        conv_tc_dgrad_body<CIN, COUT, HIN>(blockIdx.x - n_w, dpre, wprep_dgrad, act_in, din, total_px, smem_tc, &ctl);
+        conv_tc_dgrad_body<CIN, COUT, HIN>(blockIdx.x - n_w, gridDim.x - n_w, dpre, wprep_dgrad, act_in, din, total_px, smem_tc, &ctl);
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(ctl.tmem_base, kBwdTmemCols);
 }
 
 // sum of the weight-gradient slices of all five layers in index order (deterministic), one launch.

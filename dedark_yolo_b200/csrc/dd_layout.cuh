@@ -41,16 +41,15 @@ inline size_t predictor_acts_bytes(int B) { return predictor_acts_ws_elems(B) * 
 
 // backward scratch: gradients w.r.t. the pre-activations of every layer (same layout as acts) followed by the slice
 // buffers of the weight-gradient kernels (all kept until the single deferred reduction at the end of the backward).
-//   conv1 (CUDA cores): 64 tiles per image x (432 + 16);  conv2..conv5 (tensor cores): slices x RP x 32 with
-//   RP = rows (9*Cin + 1 ones row for the bias) rounded up to 4.
+//   conv1 (CUDA cores): 64 tiles per image x (432 + 16);  conv2..conv5 (tensor cores): one slice [RP][32] per
+//   persistent CTA (at most kTcMaxCtas), RP = rows (9*Cin + 1 ones row for the bias) rounded up to 4.
 constexpr int kWgradC1Slices = 64;
+constexpr int kTcMaxCtas = 148;  // persistent tensor-core kernels run one CTA per SM
 __host__ __device__ constexpr int pred_wgrad_rp(int l) { return (9 * pred_cin(l) + 1 + 3) / 4 * 4; }
-__host__ __device__ constexpr int pred_wgrad_slices_per_image(int l) { return l == 1 ? 16 : l == 2 ? 8 : l == 3 ? 4 : 2; }
 inline size_t pred_wgrad_partial_offset(int l, int B) {  // l in 0..5 (5 = end)
     size_t off = 0;
     for (int i = 0; i < l; ++i)
-        off += i == 0 ? (size_t)B * kWgradC1Slices * (432 + 16)
-                      : (size_t)B * pred_wgrad_slices_per_image(i) * pred_wgrad_rp(i) * 32;
+        off += i == 0 ? (size_t)B * kWgradC1Slices * (432 + 16) : (size_t)kTcMaxCtas * pred_wgrad_rp(i) * 32;
     return off;
 }
 inline size_t predictor_bwd_ws_bytes(int B) {

@@ -284,10 +284,11 @@ static int launch_tc_fwd(const float* in, const float* wprep, const float* bias,
     return DD_OK;
 }
 
-// weight gradient (slices -> `partial`) and data gradient of one layer in one launch
+// weight gradient (one slice per CTA -> `partial`) and data gradient of one layer in one launch of persistent CTAs; the
+// SMs are divided between the two roles in proportion to their estimated MMA time.  Returns the slice count in *n_slices.
 template <int CIN, int COUT, int HIN>
 static int launch_tc_bwd(const float* in, const float* dpre, const float* wprep_dgrad, const float* act_in, float* partial,
-                         float* din, int n_slices, int B, cudaStream_t st) {
+                         float* din, int* n_slices, int B, cudaStream_t st) {
     constexpr int HO = HIN / 2;
     constexpr size_t smem = tc::conv_tc_bwd_smem<CIN, COUT, HIN>();
     auto kern = tc::conv_tc_bwd<CIN, COUT, HIN>;
@@ -297,8 +298,16 @@ static int launch_tc_bwd(const float* in, const float* dpre, const float* wprep_
         return DD_ERR_CUDA;
     }
     const int total = B * HO * HO;
-    kern<<<n_slices + (total + 127) / 128, 256, smem, st>>>(in, dpre, wprep_dgrad, act_in, partial, din, n_slices, total);
+    const int wtiles = (total + tc::WgradCfg<CIN>::PXT - 1) / tc::WgradCfg<CIN>::PXT, dtiles = (total + 127) / 128;
+    const int ctas = sm_count() < kTcMaxCtas ? sm_count() : kTcMaxCtas;
+    const double cw = (double)wtiles * (CIN == 32 ? 1000.0 : 1300.0), cd = (double)dtiles * (CIN == 32 ? 3100.0 : 1600.0);
+    int n_w = (int)(ctas * cw / (cw + cd) + 0.5);
+    n_w = n_w < 1 ? 1 : (n_w > ctas - 1 ? ctas - 1 : n_w);
+    n_w = n_w > wtiles ? wtiles : n_w;
+    const int n_d = dtiles < ctas - n_w ? dtiles : ctas - n_w;
+    kern<<<n_w + n_d, 288, smem, st>>>(in, dpre, wprep_dgrad, act_in, partial, din, n_w, total);
     count_launch();
+    *n_slices = n_w;
     return DD_OK;
 }
 
@@ -384,15 +393,13 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     const float* prep = acts + predictor_acts_elems(B);
     float* pl[5];
     int nsl[5];
-    for (int l = 0; l < 5; ++l) {
-        pl[l] = partial + pred_wgrad_partial_offset(l, B);
-        nsl[l] = B * (l == 0 ? kWgradC1Slices : pred_wgrad_slices_per_image(l));
-    }
+    for (int l = 0; l < 5; ++l) pl[l] = partial + pred_wgrad_partial_offset(l, B);
+    nsl[0] = B * kWgradC1Slices;
     auto dg = [&](int l) { return prep + pred_prep_offset(l) + pred_prep_fwd_elems(l); };
-    if (int e = launch_tc_bwd<32, 32, 16>(a[3], d[4], dg(4), a[3], pl[4], d[3], nsl[4], B, st)) return e;
-    if (int e = launch_tc_bwd<32, 32, 32>(a[2], d[3], dg(3), a[2], pl[3], d[2], nsl[3], B, st)) return e;
-    if (int e = launch_tc_bwd<32, 32, 64>(a[1], d[2], dg(2), a[1], pl[2], d[1], nsl[2], B, st)) return e;
-    if (int e = launch_tc_bwd<16, 32, 128>(a[0], d[1], dg(1), a[0], pl[1], d[0], nsl[1], B, st)) return e;
+    if (int e = launch_tc_bwd<32, 32, 16>(a[3], d[4], dg(4), a[3], pl[4], d[3], &nsl[4], B, st)) return e;
+    if (int e = launch_tc_bwd<32, 32, 32>(a[2], d[3], dg(3), a[2], pl[3], d[2], &nsl[3], B, st)) return e;
+    if (int e = launch_tc_bwd<32, 32, 64>(a[1], d[2], dg(2), a[1], pl[2], d[1], &nsl[2], B, st)) return e;
+    if (int e = launch_tc_bwd<16, 32, 128>(a[0], d[1], dg(1), a[0], pl[1], d[0], &nsl[1], B, st)) return e;
     conv_wgrad_tiled_c3<16, 256, 8, 32><<<nsl[0], 32 * 8, 0, st>>>(r, d[0], pl[0]);  // first layer (CIN = 3)
     {
         tc::ReduceJobs jobs;
