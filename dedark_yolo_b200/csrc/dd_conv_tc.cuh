@@ -32,6 +32,16 @@ __device__ long long g_tc_stamp[64];
     do {                                                                       \
         if (blockIdx.x == 0 && threadIdx.x == 0) g_tc_stamp[(i)] = clock64();  \
     } while (0)
+__device__ long long g_tc_cta_cycles[256];
+#define DD_TC_CTA_BEGIN() const long long cta_t0__ = clock64()
+#define DD_TC_CTA_END()                                                        \
+    do {                                                                       \
+        if (threadIdx.x == 0) g_tc_cta_cycles[blockIdx.x] = clock64() - cta_t0__; \
+    } while (0)
+#define DD_TC_STAMP_C(i, thr, ctaidx)                                              \
+    do {                                                                          \
+        if ((ctaidx) == 0 && threadIdx.x == (thr)) g_tc_stamp[(i)] = clock64();    \
+    } while (0)
 #define DD_TC_STAMP_T(i, thr)                                                     \
     do {                                                                         \
         if (blockIdx.x == 0 && threadIdx.x == (thr)) g_tc_stamp[(i)] = clock64(); \
@@ -42,6 +52,15 @@ __device__ long long g_tc_stamp[64];
     } while (0)
 #define DD_TC_STAMP_T(i, thr) \
     do {                      \
+    } while (0)
+#define DD_TC_STAMP_C(i, thr, ctaidx) \
+    do {                              \
+    } while (0)
+#define DD_TC_CTA_BEGIN() \
+    do {                  \
+    } while (0)
+#define DD_TC_CTA_END() \
+    do {                \
     } while (0)
 #endif
 
@@ -409,7 +428,7 @@ conv_tc_fwd(const float* __restrict__ in, const float* __restrict__ wprep, const
 // slices, the others compute the data gradient (the two are independent given dpre).
 // =============================================================================================================
 struct BwdCtl {
-    uint64_t full[2], empty[2], done;
+    uint64_t full[2], empty[2], done[2], acc_empty[2];
     uint32_t tmem_base;
 };
 constexpr uint32_t kBwdTmemCols = 512;
@@ -419,8 +438,9 @@ constexpr uint32_t kBwdTmemCols = 512;
 //   tile = 128 quads = the 128 TMEM lanes, N = 4*CIN (channel, parity) columns; K = 4*COUT runs in stages of 8 output
 //   channels (32 k = 4 MMA k-steps).  Producer thread (quad m, half h) loads the 2x2 neighbourhoods of 4 channels,
 //   splits them and writes 16 hi + 16 lo values into its TMEM lane (A operand in tensor memory); the prepared
-//   weights of all stages stay in shared memory.  Per k-step:  a_hi x [w_hi | w_lo] (N = 8*CIN)  and  a_lo x w_hi.
-//   TMEM columns: [0, 8*CIN) accumulator, then two A buffers of [32 hi | 32 lo].
+//   weights of all stages stay in shared memory.  Per k-step:  a_lo x w_hi,  a_hi x w_lo,  a_hi x w_hi  (N = 4*CIN).
+//   Two accumulators alternate, so the epilogue of a tile (LeakyReLU mask, 8-byte stores) overlaps the MMAs of the next.
+//   TMEM columns: accumulators [0, 4*CIN) and [4*CIN, 8*CIN), then two A buffers of [32 hi | 32 lo].
 // -------------------------------------------------------------------------------------------------------------
 template <int CIN, int COUT>
 constexpr size_t conv_tc_dgrad_smem() { return (size_t)((COUT / 8) * 8 * 2 * 4 * CIN * 4) * sizeof(float); }
@@ -471,6 +491,7 @@ __device__ __forceinline__ void conv_tc_dgrad_body(const int cta, const int ncta
             const int s = g & 1;
             if (g >= 2) mbar_wait(&ctl->empty[s], (uint32_t)((g >> 1) - 1) & 1u);
             fence_after_sync();
+            if (g < 8) DD_TC_STAMP_C(2 * g, 0, cta);
             float hi[16], lo[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -483,10 +504,59 @@ __device__ __forceinline__ void conv_tc_dgrad_body(const int cta, const int ncta
             tmem_st_wait();
             fence_before_sync();
             mbar_arrive(&ctl->full[s]);
+            if (g < 8) DD_TC_STAMP_C(2 * g + 1, 0, cta);
             gather_ahead(r, it, c);
             ++g;
         };
+        // epilogue of tile `it` (accumulator buffer it & 1): runs while the MMA warp already works on tile it + 1.  This
+        // thread: columns [half*N/2, (half+1)*N/2) = CIN/2 channels x 4 parities.  The activations that gate the
+        // LeakyReLU derivative do not depend on the MMAs: they are requested one tile of stages earlier (load_act).
+        constexpr int NCH = CIN / 2;
+        struct Act { float2 top[NCH], bot[NCH]; };
+        auto out_base = [&](int it, bool& ok) {
+            const int gqe = (cta + it * nctas) * 128 + q * 32 + lane;
+            ok = gqe < total_q;
+            const int be = gqe / (HO * HO), reme = gqe % (HO * HO), ae = reme / HO, ce = reme % HO;
+            return (((size_t)be * CIN + half * NCH) * HIN + 2 * ae) * HIN + 2 * ce;
+        };
+        auto load_act = [&](Act& a, int it) {
+            bool ok;
+            const size_t base0 = out_base(it, ok);
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                a.top[i] = ok ? __ldg(reinterpret_cast<const float2*>(act_in + base0 + (size_t)i * HIN * HIN)) : make_float2(0.f, 0.f);
+                a.bot[i] = ok ? __ldg(reinterpret_cast<const float2*>(act_in + base0 + (size_t)i * HIN * HIN + HIN)) : make_float2(0.f, 0.f);
+            }
+        };
+        auto epilogue = [&](const Act& a, int it) {
+            const int ab = it & 1;
+            bool ok;
+            const size_t base0 = out_base(it, ok);
+            mbar_wait(&ctl->done[ab], (uint32_t)(it >> 1) & 1u);
+            fence_after_sync();
+            if (it < 2) DD_TC_STAMP_C(33 + 3 * it, 0, cta);
+#pragma unroll
+            for (int gg = 0; gg < N / 32; ++gg) {
+                float ra[16];
+                tmem_ld16(tmem + lane_base + (uint32_t)(ab * N + half * (N / 2) + gg * 16), ra);
+                if (ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int ch = gg * 4 + i;
+                        const size_t base = base0 + (size_t)ch * HIN * HIN;
+                        float2 top = make_float2(leaky_grad(a.top[ch].x, ra[4 * i + 0]), leaky_grad(a.top[ch].y, ra[4 * i + 1]));
+                        float2 bot = make_float2(leaky_grad(a.bot[ch].x, ra[4 * i + 2]), leaky_grad(a.bot[ch].y, ra[4 * i + 3]));
+                        *reinterpret_cast<float2*>(din + base) = top;
+                        *reinterpret_cast<float2*>(din + base + HIN) = bot;
+                    }
+                }
+            }
+            fence_before_sync();
+            mbar_arrive(&ctl->acc_empty[ab]);
+            if (it < 2) DD_TC_STAMP_C(34 + 3 * it, 0, cta);
+        };
         Raw r0, r1;
+        Act act;
         if (my_tiles > 0) {
             gather(r0, cta, 0);
             gather(r1, cta, 1);
@@ -494,61 +564,46 @@ __device__ __forceinline__ void conv_tc_dgrad_body(const int cta, const int ncta
         cp_async_wait_all();
         fence_proxy_async();
         for (int it = 0; it < my_tiles; ++it) {
-            const int tile = cta + it * nctas;
+            if (it > 0) load_act(act, it - 1);
 #pragma unroll 1
             for (int c = 0; c < NST; c += 2) {
                 stage(r0, it, c);
                 stage(r1, it, c + 1);
             }
-            mbar_wait(&ctl->done, (uint32_t)it & 1u);
-            fence_after_sync();
-            const int gqe = tile * 128 + q * 32 + lane;
-            const bool ok = gqe < total_q;
-            const int be = gqe / (HO * HO), reme = gqe % (HO * HO), ae = reme / HO, ce = reme % HO;
-            // columns [half*N/2, (half+1)*N/2) (+ N for the hi x lo block): CIN/2 channels x 4 parities, 4 channels per load
-#pragma unroll 1
-            for (int gg = 0; gg < N / 32; ++gg) {
-                float ra[16], rb[16];
-                tmem_ld16(tmem + lane_base + (uint32_t)(half * (N / 2) + gg * 16), ra);
-                tmem_ld16(tmem + lane_base + (uint32_t)(N + half * (N / 2) + gg * 16), rb);
-                if (ok) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int ci = half * (CIN / 2) + gg * 4 + i;
-                        const size_t base = (((size_t)be * CIN + ci) * HIN + 2 * ae) * HIN + 2 * ce;
-                        float2 top = make_float2(ra[4 * i + 0] + rb[4 * i + 0], ra[4 * i + 1] + rb[4 * i + 1]);
-                        float2 bot = make_float2(ra[4 * i + 2] + rb[4 * i + 2], ra[4 * i + 3] + rb[4 * i + 3]);
-                        const float2 at = *reinterpret_cast<const float2*>(act_in + base);
-                        const float2 ab = *reinterpret_cast<const float2*>(act_in + base + HIN);
-                        top.x = leaky_grad(at.x, top.x); top.y = leaky_grad(at.y, top.y);
-                        bot.x = leaky_grad(ab.x, bot.x); bot.y = leaky_grad(ab.y, bot.y);
-                        *reinterpret_cast<float2*>(din + base) = top;
-                        *reinterpret_cast<float2*>(din + base + HIN) = bot;
-                    }
-                }
-            }
-            fence_before_sync();
+            if (it > 0) epilogue(act, it - 1);
+        }
+        if (my_tiles > 0) {
+            load_act(act, my_tiles - 1);
+            epilogue(act, my_tiles - 1);
         }
     } else {
-        constexpr uint32_t idesc_2n = make_idesc(128, 2 * N, 0, 0), idesc_n = make_idesc(128, N, 0, 0);
+        constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
         const uint32_t b_base = smem_u32(sB);
-        const int nstages = my_tiles * NST;
-        for (int g = 0; g < nstages; ++g) {
-            const int s = g & 1, c = g % NST;
-            mbar_wait(&ctl->full[s], (uint32_t)(g >> 1) & 1u);
-            fence_after_sync();
-            if (elect_one()) {
-                const uint32_t a0 = tmem + A_COL0 + (uint32_t)s * A_BUF, b0 = b_base + (uint32_t)c * (B_STAGE * 4u);
+        for (int it = 0, g = 0; it < my_tiles; ++it) {
+            const uint32_t ab = (uint32_t)it & 1u;
+            if (it >= 2) mbar_wait(&ctl->acc_empty[ab], (uint32_t)((it >> 1) - 1) & 1u);  // the epilogue of tile it-2 has read D[ab]
+            for (int c = 0; c < NST; ++c, ++g) {
+                const int s = g & 1;
+                mbar_wait(&ctl->full[s], (uint32_t)(g >> 1) & 1u);
+                fence_after_sync();
+                if (g < 8) DD_TC_STAMP_C(16 + 2 * g, 256, cta);
+                if (elect_one()) {
+                    const uint32_t a0 = tmem + A_COL0 + (uint32_t)s * A_BUF, b0 = b_base + (uint32_t)c * (B_STAGE * 4u);
+                    const uint32_t d = tmem + ab * N;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint64_t bd = make_desc(b0 + (uint32_t)(2 * j) * (2 * N * 16u), 2 * N * 16u, 128u);
-                    mma_tf32_ts(tmem, a0 + 8u * j, bd, idesc_2n, (c > 0 || j > 0) ? 1u : 0u);  // hi x [hi | lo]
-                    mma_tf32_ts(tmem, a0 + A_LO + 8u * j, bd, idesc_n, 1u);                    // lo x hi
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t bo = b0 + (uint32_t)(2 * j) * (2 * N * 16u);
+                        const uint64_t b_hi = make_desc(bo, 2 * N * 16u, 128u), b_lo = make_desc(bo + N * 16u, 2 * N * 16u, 128u);
+                        mma_tf32_ts(d, a0 + A_LO + 8u * j, b_hi, idesc, (c > 0 || j > 0) ? 1u : 0u);  // lo x hi
+                        mma_tf32_ts(d, a0 + 8u * j, b_lo, idesc, 1u);                                 // hi x lo
+                        mma_tf32_ts(d, a0 + 8u * j, b_hi, idesc, 1u);                                 // hi x hi
+                    }
+                    mma_commit(&ctl->empty[s]);
+                    if (c == NST - 1) mma_commit(&ctl->done[ab]);
                 }
-                mma_commit(&ctl->empty[s]);
-                if (c == NST - 1) mma_commit(&ctl->done);
+                if (g < 8) DD_TC_STAMP_C(17 + 2 * g, 256, cta);
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
 }
@@ -682,7 +737,7 @@ __device__ __forceinline__ void conv_tc_wgrad_body(const int cta, const int nsli
             if (tile + 1 < t1) stage(v1, tile + 1);
         }
         if (t0 < t1) {
-            mbar_wait(&ctl->done, 0u);
+            mbar_wait(&ctl->done[0], 0u);
             fence_after_sync();
             const int q = warp & 3, half = warp >> 2;
 #pragma unroll
@@ -723,7 +778,7 @@ __device__ __forceinline__ void conv_tc_wgrad_body(const int cta, const int nsli
                     }
                 }
                 mma_commit(&ctl->empty[s]);
-                if (tile == t1 - 1) mma_commit(&ctl->done);
+                if (tile == t1 - 1) mma_commit(&ctl->done[0]);
             }
             __syncwarp();
         }
@@ -742,11 +797,14 @@ conv_tc_bwd(const float* __restrict__ in, const float* __restrict__ dpre, const 
     extern __shared__ __align__(128) float smem_tc[];
     __shared__ BwdCtl ctl;
     const int t = threadIdx.x, warp = t >> 5;
+    DD_TC_CTA_BEGIN();
+    DD_TC_STAMP_C(63, 0, (int)blockIdx.x - n_w);
     if (warp == 8) tmem_alloc(&ctl.tmem_base, kBwdTmemCols);
     if (t == 0) {
         mbar_init(&ctl.full[0], 256); mbar_init(&ctl.full[1], 256);
         mbar_init(&ctl.empty[0], 1); mbar_init(&ctl.empty[1], 1);
-        mbar_init(&ctl.done, 1);
+        mbar_init(&ctl.done[0], 1); mbar_init(&ctl.done[1], 1);
+        mbar_init(&ctl.acc_empty[0], 256); mbar_init(&ctl.acc_empty[1], 256);
         fence_mbar_init();
     }
     fence_before_sync();
@@ -758,6 +816,7 @@ conv_tc_bwd(const float* __restrict__ in, const float* __restrict__ dpre, const 
         conv_tc_dgrad_body<CIN, COUT, HIN>(blockIdx.x - n_w, gridDim.x - n_w, dpre, wprep_dgrad, act_in, din, total_px, smem_tc, &ctl);
     fence_before_sync();
     __syncthreads();
+    DD_TC_CTA_END();
     if (warp == 8) tmem_dealloc(ctl.tmem_base, kBwdTmemCols);
 }
 

@@ -300,7 +300,7 @@ static int launch_tc_bwd(const float* in, const float* dpre, const float* wprep_
     const int total = B * HO * HO;
     const int wtiles = (total + tc::WgradCfg<CIN>::PXT - 1) / tc::WgradCfg<CIN>::PXT, dtiles = (total + 127) / 128;
     const int ctas = sm_count() < kTcMaxCtas ? sm_count() : kTcMaxCtas;
-    const double cw = (double)wtiles * (CIN == 32 ? 1000.0 : 1300.0), cd = (double)dtiles * (CIN == 32 ? 3100.0 : 1600.0);
+    const double cw = (double)wtiles * 2500.0, cd = (double)dtiles * (CIN == 32 ? 7500.0 : 4500.0);  // measured cycles per tile (profiles/microbench/tc_probe.cu)
     int n_w = (int)(ctas * cw / (cw + cd) + 0.5);
     n_w = n_w < 1 ? 1 : (n_w > ctas - 1 ? ctas - 1 : n_w);
     n_w = n_w > wtiles ? wtiles : n_w;

@@ -45,7 +45,55 @@ static void probe(int B) {
     cudaFree(in); cudaFree(out); cudaFree(w); cudaFree(bias);
 }
 
-int main() {
+template <int CIN, int COUT, int HIN>
+static void probe_bwd(int B, int n_w) {
+    constexpr int HO = HIN / 2;
+    const size_t n_in = (size_t)B * CIN * HIN * HIN, n_out = (size_t)B * COUT * HO * HO;
+    float *in, *dpre, *w, *din, *partial;
+    cudaMalloc(&in, n_in * 4); cudaMalloc(&din, n_in * 4); cudaMalloc(&dpre, n_out * 4); cudaMalloc(&w, 32 * CIN * COUT * 4);
+    cudaMalloc(&partial, (size_t)148 * 300 * 32 * 4);
+    cudaMemset(in, 0, n_in * 4); cudaMemset(w, 0, 32 * CIN * COUT * 4); cudaMemset(dpre, 0, n_out * 4);
+    auto kern = tc::conv_tc_bwd<CIN, COUT, HIN>;
+    constexpr size_t smem = tc::conv_tc_bwd_smem<CIN, COUT, HIN>();
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int total = B * HO * HO;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int it = 0; it < 3; ++it) {
+        cudaEventRecord(e0);
+        kern<<<148, 288, smem>>>(in, dpre, w, in, partial, din, n_w, total);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        long long cy[256];
+        cudaMemcpyFromSymbol(cy, tc::g_tc_cta_cycles, sizeof(cy));
+        long long wmax = 0, wmin = 1ll << 60, dmax = 0, dmin = 1ll << 60;
+        for (int i = 0; i < 148; ++i) {
+            if (i < n_w) { wmax = cy[i] > wmax ? cy[i] : wmax; wmin = cy[i] < wmin ? cy[i] : wmin; }
+            else { dmax = cy[i] > dmax ? cy[i] : dmax; dmin = cy[i] < dmin ? cy[i] : dmin; }
+        }
+        if (it == 2) {
+            long long st[64];
+            cudaMemcpyFromSymbol(st, tc::g_tc_stamp, sizeof(st));
+            for (int g = 0; g < 8; ++g)
+                printf("   dgrad stage %d: producer begin t=%lld split+st+arrive %lld | mma full-seen t=%lld issue %lld\n", g, st[2 * g] - st[63],
+                       st[2 * g + 1] - st[2 * g], st[16 + 2 * g] - st[63], st[17 + 2 * g] - st[16 + 2 * g]);
+            for (int k = 0; k < 2; ++k)
+                printf("   epilogue %d: begin t=%lld done-wait %lld  ld+store %lld\n", k, st[32 + 3 * k] - st[63], st[33 + 3 * k] - st[32 + 3 * k],
+                       st[34 + 3 * k] - st[33 + 3 * k]);
+        }
+        const int wt = (total + tc::WgradCfg<CIN>::PXT - 1) / tc::WgradCfg<CIN>::PXT, dt = (total + 127) / 128;
+        printf("conv_tc_bwd<%d,%d,%d> B=%d n_w=%d: %s, %.1f us; wgrad CTA cycles [%lld, %lld] (%d tiles, %.1f per CTA); dgrad [%lld, %lld] (%d tiles, %.1f per CTA)\n",
+               CIN, COUT, HIN, B, n_w, cudaGetErrorString(e), ms * 1e3f, wmin, wmax, wt, (double)wt / n_w, dmin, dmax, dt, (double)dt / (148 - n_w));
+    }
+    cudaFree(in); cudaFree(din); cudaFree(dpre); cudaFree(w); cudaFree(partial);
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1) {
+        probe_bwd<16, 32, 128>(16, 60);
+        probe_bwd<32, 32, 64>(16, 100);
+        return 0;
+    }
     probe<32, 32, 16>(16);
     probe<32, 32, 64>(16);
     probe<16, 32, 128>(16);
