@@ -211,6 +211,7 @@ struct PrepJobs {
 
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(PrepJobs jobs) {
+    pdl_begin();
     const PrepJob jb = jobs.j[blockIdx.y];
     const int cin = jb.cin, cout = jb.cout;
     const int nf = 9 * cin * cout, nd = 16 * cin * cout;  // hi elements of each table
@@ -264,6 +265,7 @@ template <int CIN, int COUT, int HIN>
 __global__ void __launch_bounds__(288, 1)
 conv_tc_fwd(const float* __restrict__ in, const float* __restrict__ wprep, const float* __restrict__ bias,
             float* __restrict__ out, int total_px) {
+    pdl_begin();
     constexpr int HO = HIN / 2, NST = CIN / 8;
     constexpr int B_STAGE = 18 * 2 * COUT * 4;      // floats: [18 slots][hi rows | lo rows][4]
     constexpr uint32_t TMEM_COLS = 512, A_COL0 = 64, A_BUF = 144, A_LO = 72;
@@ -794,6 +796,7 @@ template <int CIN, int COUT, int HIN>
 __global__ void __launch_bounds__(288, 1)
 conv_tc_bwd(const float* __restrict__ in, const float* __restrict__ dpre, const float* __restrict__ wprep_dgrad,
             const float* __restrict__ act_in, float* __restrict__ partial, float* __restrict__ din, int n_w, int total_px) {
+    pdl_begin();
     extern __shared__ __align__(128) float smem_tc[];
     __shared__ BwdCtl ctl;
     const int t = threadIdx.x, warp = t >> 5;
@@ -834,6 +837,7 @@ struct ReduceJobs {
 };
 __global__ void __launch_bounds__(1024)
 wgrad_reduce_kernel(const ReduceJobs jobs) {
+    pdl_begin();
     __shared__ float s_part[32][33];
     int ji = 0;
 #pragma unroll

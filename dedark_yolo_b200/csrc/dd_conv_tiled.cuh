@@ -88,6 +88,7 @@ template <int CIN, int COUT, int HIN, int TH, int TW, int CICH, int PY>
 __global__ void __launch_bounds__(TW*(TH / PY) * (COUT / 8))
 conv_fwd_tiled(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                float* __restrict__ out) {
+    pdl_begin();
     using T = InTile<TH, TW>;
     constexpr int HO = HIN / 2, TX = HO / TW, TY = HO / TH, NCHUNK = CIN / CICH;
     constexpr int IN_F = (CICH * T::PLANE + 3) & ~3, W_F = CICH * 9 * COUT, CH_F = IN_F + W_F;  // floats per chunk
@@ -321,6 +322,7 @@ __device__ __forceinline__ void conv_wgrad_body(const int bid, const float* __re
 template <int COUT, int HIN, int TH, int TW>
 __global__ void __launch_bounds__(32 * (COUT / 2))
 conv_wgrad_tiled_c3(const float* __restrict__ in, const float* __restrict__ dpre, float* __restrict__ partial) {
+    pdl_begin();
     constexpr int CIN = 3;
     using T = InTile<TH, TW>;
     constexpr int HO = HIN / 2, TX = HO / TW, TY = HO / TH, NW = COUT * CIN * 9;
@@ -383,6 +385,7 @@ template <int CIN, int COUT, int HIN, int WTH, int WTW, int CO_T, int TQH, int T
 __global__ void __launch_bounds__(256)
 conv_bwd_layer(const float* __restrict__ in, const float* __restrict__ dpre, const float* __restrict__ w,
                const float* __restrict__ act_in, float* __restrict__ partial, float* __restrict__ din, int n_wgrad) {
+    pdl_begin();
     static_assert(CIN * (COUT / CO_T) == 256 && TQW * (TQH / QY) * (CIN / 8) == 256, "both halves run with 256 threads");
     if ((int)blockIdx.x < n_wgrad)
         conv_wgrad_body<CIN, COUT, HIN, WTH, WTW, CO_T>(blockIdx.x, in, dpre, partial);
@@ -401,6 +404,7 @@ struct ReduceJobs {
     ReduceJob j[5];
 };
 __global__ void __launch_bounds__(1024) wgrad_reduce_all_kernel(const ReduceJobs jobs) {
+    pdl_begin();
     __shared__ float s_part[32][33];
     int l = 4;
 #pragma unroll

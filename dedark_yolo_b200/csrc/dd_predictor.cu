@@ -31,6 +31,7 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int n, int& i
 
 __global__ void __launch_bounds__(256)
 resize256_kernel(const float* __restrict__ x, float* __restrict__ r, int B, int H, int W) {
+    pdl_begin();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;  // output column (256 per row)
     const int i = blockIdx.y;                              // output row
     const int plane = blockIdx.z;                          // b*3 + ch
@@ -50,6 +51,7 @@ resize256_kernel(const float* __restrict__ x, float* __restrict__ r, int B, int 
 // adjoint as a gather (deterministic): every source pixel sums the output pixels that sampled it
 __global__ void __launch_bounds__(256)
 resize256_bwd_kernel(const float* __restrict__ dr, float* __restrict__ dx, int B, int H, int W) {
+    pdl_begin();
     const int xs = blockIdx.x * blockDim.x + threadIdx.x;
     const int ys = blockIdx.y;
     const int plane = blockIdx.z;
@@ -90,6 +92,7 @@ template <int CIN, int COUT, int HIN, int CI_T>
 __global__ void __launch_bounds__(256)
 conv_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, const float* __restrict__ act_in,
                   float* __restrict__ din, int B) {
+    pdl_begin();
     constexpr int HO = HIN / 2;
     constexpr int CIG = CIN / CI_T;
     __shared__ float sw[COUT * 9 * CIN];  // [co][k][ci]
@@ -154,6 +157,7 @@ conv_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, c
 __global__ void __launch_bounds__(256)
 fc1_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w1, const float* __restrict__ b1,
                float* __restrict__ h, int B) {
+    pdl_begin();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * kFc1Out) return;
     const int b = warp / kFc1Out, o = warp % kFc1Out;
@@ -173,6 +177,7 @@ fc1_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w1, con
 __global__ void __launch_bounds__(256)
 fc2_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2,
                float* __restrict__ feat, int B) {
+    pdl_begin();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * kFeat) return;
     const int b = t / kFeat, j = t % kFeat;
@@ -185,6 +190,7 @@ fc2_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w2, const 
 __global__ void __launch_bounds__(1024)
 fc2_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, const float* __restrict__ w2,
                float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dhpre, int B) {
+    pdl_begin();
     const int t = threadIdx.x;
     if (t < kFeat * kFc1Out) {
         const int j = t / kFc1Out, o = t % kFc1Out;
@@ -209,6 +215,7 @@ fc2_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, con
 __global__ void __launch_bounds__(256)
 fc1_wgrad_kernel(const float* __restrict__ dhpre, const float* __restrict__ flat, float* __restrict__ dw1,
                  float* __restrict__ db1, int B) {
+    pdl_begin();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < kFc1Out * kFc1In) {
         const int o = t / kFc1In, i = t % kFc1In;
@@ -227,6 +234,7 @@ fc1_wgrad_kernel(const float* __restrict__ dhpre, const float* __restrict__ flat
 __global__ void __launch_bounds__(256)
 fc1_dgrad_kernel(const float* __restrict__ dhpre, const float* __restrict__ w1, const float* __restrict__ a5,
                  float* __restrict__ dpre5, int B) {
+    pdl_begin();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * kFc1In) return;
     const int b = t / kFc1In, i = t % kFc1In;
@@ -243,7 +251,7 @@ static void launch_conv_dgrad(const float* dpre, const float* w, const float* ac
                               cudaStream_t st) {
     constexpr int HO = HIN / 2;
     const long long items = (long long)B * HO * HO * (CIN / CI_T);
-    conv_dgrad_kernel<CIN, COUT, HIN, CI_T><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(dpre, w, act_in, din, B);
+    launch_pdl(conv_dgrad_kernel<CIN, COUT, HIN, CI_T>, dim3((unsigned)((items + 255) / 256)), dim3(256), 0, st, dpre, w, act_in, din, B);
     count_launch();
 }
 
@@ -253,8 +261,8 @@ static void launch_fwd_tiled(const float* in, const float* w, const float* b, fl
     constexpr int HO = HIN / 2;
     constexpr size_t smem = conv_fwd_smem<CIN, COUT, TH, TW, CICH>();
     cudaFuncSetAttribute(conv_fwd_tiled<CIN, COUT, HIN, TH, TW, CICH, PY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    conv_fwd_tiled<CIN, COUT, HIN, TH, TW, CICH, PY>
-        <<<B * (HO / TH) * (HO / TW), TW * (TH / PY) * (COUT / 8), smem, st>>>(in, w, b, out);
+    launch_pdl(conv_fwd_tiled<CIN, COUT, HIN, TH, TW, CICH, PY>, dim3(B * (HO / TH) * (HO / TW)), dim3(TW * (TH / PY) * (COUT / 8)), smem, st,
+               in, w, b, out);
     count_launch();
 }
 
@@ -279,7 +287,7 @@ static int launch_tc_fwd(const float* in, const float* wprep, const float* bias,
         return DD_ERR_CUDA;
     }
     const int total = B * HO * HO, ntiles = (total + 127) / 128;
-    kern<<<ntiles < sm_count() ? ntiles : sm_count(), 288, smem, st>>>(in, wprep, bias, out, total);  // persistent: <= 1 CTA per SM
+    launch_pdl(kern, dim3(ntiles < sm_count() ? ntiles : sm_count()), dim3(288), smem, st, in, wprep, bias, out, total);  // persistent: <= 1 CTA per SM
     count_launch();
     return DD_OK;
 }
@@ -305,7 +313,7 @@ static int launch_tc_bwd(const float* in, const float* dpre, const float* wprep_
     n_w = n_w < 1 ? 1 : (n_w > ctas - 1 ? ctas - 1 : n_w);
     n_w = n_w > wtiles ? wtiles : n_w;
     const int n_d = dtiles < ctas - n_w ? dtiles : ctas - n_w;
-    kern<<<n_w + n_d, 288, smem, st>>>(in, dpre, wprep_dgrad, act_in, partial, din, n_w, total);
+    launch_pdl(kern, dim3(n_w + n_d), dim3(288), smem, st, in, dpre, wprep_dgrad, act_in, partial, din, n_w, total);
     count_launch();
     *n_slices = n_w;
     return DD_OK;
@@ -325,7 +333,7 @@ extern "C" int dd_resize256(const float* x, float* r, int B, int H, int W, void*
     DD_REQUIRE(x && r && B > 0 && H > 0 && W > 0, DD_ERR_INVALID, "dd_resize256: bad arguments");
     DD_REQUIRE((long long)B * 3 <= 65535, DD_ERR_INVALID, "dd_resize256: B too large (%d)", B);
     dim3 grid(1, DD_RESIZE, B * 3);
-    resize256_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(x, r, B, H, W);
+    launch_pdl(resize256_kernel, grid, dim3(256), 0, (cudaStream_t)stream_, x, r, B, H, W);
     count_launch();
     return check_launch("dd_resize256");
 }
@@ -335,7 +343,7 @@ extern "C" int dd_resize256_bwd(const float* dr, float* dx, int B, int H, int W,
     DD_REQUIRE(dr && dx && B > 0 && H > 0 && W > 0, DD_ERR_INVALID, "dd_resize256_bwd: bad arguments");
     DD_REQUIRE((long long)B * 3 <= 65535 && H <= 65535, DD_ERR_INVALID, "dd_resize256_bwd: shape too large");
     dim3 grid((W + 255) / 256, H, B * 3);
-    resize256_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(dr, dx, B, H, W);
+    launch_pdl(resize256_bwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream_, dr, dx, B, H, W);
     count_launch();
     return check_launch("dd_resize256_bwd");
 }
@@ -354,15 +362,15 @@ extern "C" int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, f
         for (int l = 1; l < 5; ++l)
             jobs.j[l - 1] = tc::PrepJob{w->conv_w[l], prep + pred_prep_offset(l), prep + pred_prep_offset(l) + pred_prep_fwd_elems(l),
                                         pred_cin(l), pred_cout(l)};
-        tc::prep_weights_kernel<<<dim3(32, 4), 256, 0, st>>>(jobs);
+        launch_pdl(tc::prep_weights_kernel, dim3(32, 4), dim3(256), 0, st, jobs);
         count_launch();
     }
     if (int e = launch_tc_fwd<16, 32, 128>(a[0], prep + pred_prep_offset(1), w->conv_b[1], a[1], B, st)) return e;
     if (int e = launch_tc_fwd<32, 32, 64>(a[1], prep + pred_prep_offset(2), w->conv_b[2], a[2], B, st)) return e;
     if (int e = launch_tc_fwd<32, 32, 32>(a[2], prep + pred_prep_offset(3), w->conv_b[3], a[3], B, st)) return e;
     if (int e = launch_tc_fwd<32, 32, 16>(a[3], prep + pred_prep_offset(4), w->conv_b[4], a[4], B, st)) return e;
-    fc1_fwd_kernel<<<(B * kFc1Out * 32 + 255) / 256, 256, 0, st>>>(a[4], w->fc1_w, w->fc1_b, a[5], B);
-    fc2_fwd_kernel<<<(B * kFeat + 255) / 256, 256, 0, st>>>(a[5], w->fc2_w, w->fc2_b, feat, B);
+    launch_pdl(fc1_fwd_kernel, dim3((B * kFc1Out * 32 + 255) / 256), dim3(256), 0, st, a[4], w->fc1_w, w->fc1_b, a[5], B);
+    launch_pdl(fc2_fwd_kernel, dim3((B * kFeat + 255) / 256), dim3(256), 0, st, a[5], w->fc2_w, w->fc2_b, feat, B);
     count_launch(2);
     return check_launch("dd_predictor_fwd");
 }
@@ -384,9 +392,9 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     }
     float* partial = reinterpret_cast<float*>(ws) + predictor_acts_elems(B);
 
-    fc2_bwd_kernel<<<1, 1024, 0, st>>>(dfeat, a[5], w->fc2_w, g->fc2_w, g->fc2_b, d[5], B);
-    fc1_wgrad_kernel<<<(kFc1Out * kFc1In + 255) / 256, 256, 0, st>>>(d[5], a[4], g->fc1_w, g->fc1_b, B);
-    fc1_dgrad_kernel<<<(B * kFc1In + 255) / 256, 256, 0, st>>>(d[5], w->fc1_w, a[4], d[4], B);
+    launch_pdl(fc2_bwd_kernel, dim3(1), dim3(1024), 0, st, dfeat, a[5], w->fc2_w, g->fc2_w, g->fc2_b, d[5], B);
+    launch_pdl(fc1_wgrad_kernel, dim3((kFc1Out * kFc1In + 255) / 256), dim3(256), 0, st, d[5], a[4], g->fc1_w, g->fc1_b, B);
+    launch_pdl(fc1_dgrad_kernel, dim3((B * kFc1In + 255) / 256), dim3(256), 0, st, d[5], w->fc1_w, a[4], d[4], B);
     count_launch(3);
     // conv5 .. conv2: weight-gradient slices and the data gradient of a layer in one tensor-core launch; conv1: weight
     // gradient on the CUDA cores; one deferred reduction of all slice buffers at the end
@@ -400,7 +408,7 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     if (int e = launch_tc_bwd<32, 32, 32>(a[2], d[3], dg(3), a[2], pl[3], d[2], &nsl[3], B, st)) return e;
     if (int e = launch_tc_bwd<32, 32, 64>(a[1], d[2], dg(2), a[1], pl[2], d[1], &nsl[2], B, st)) return e;
     if (int e = launch_tc_bwd<16, 32, 128>(a[0], d[1], dg(1), a[0], pl[1], d[0], &nsl[1], B, st)) return e;
-    conv_wgrad_tiled_c3<16, 256, 8, 32><<<nsl[0], 32 * 8, 0, st>>>(r, d[0], pl[0]);  // first layer (CIN = 3)
+    launch_pdl(conv_wgrad_tiled_c3<16, 256, 8, 32>, dim3(nsl[0]), dim3(32 * 8), 0, st, r, d[0], pl[0]);  // first layer (CIN = 3)
     {
         tc::ReduceJobs jobs;
         int block0 = 0;
@@ -410,7 +418,7 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
                                       l == 0 ? 0 : pred_cin(l), 432, block0};
             block0 += (n + 31) / 32;
         }
-        tc::wgrad_reduce_kernel<<<block0, 1024, 0, st>>>(jobs);
+        launch_pdl(tc::wgrad_reduce_kernel, dim3(block0), dim3(1024), 0, st, jobs);
     }
     count_launch(2);
     if (dr) launch_conv_dgrad<3, 16, 256, 3>(d[0], w->conv_w[0], nullptr, dr, B, st);

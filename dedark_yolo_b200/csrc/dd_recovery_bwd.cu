@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 recovery_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
                     const float* __restrict__ feat, const float* __restrict__ g, float* __restrict__ part,
                     float* __restrict__ Spart, float* __restrict__ dx, int B, int H, int W) {
+    pdl_begin();
     extern __shared__ __align__(16) float smem[];
     float* XS = smem;                   // g, zero outside the image
     float* HS = XS + kXRingB * kXP;
@@ -331,6 +332,7 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
                              const float* __restrict__ IcA, const float* __restrict__ feat,
                              const float* __restrict__ part, const float* __restrict__ Spart,
                              float* __restrict__ dfeat, float* __restrict__ dx, int B, int H, int W) {
+    pdl_begin();
     __shared__ ImgParams sp;
     __shared__ double s_red[32];
     const int tid = threadIdx.x, b = blockIdx.x;
@@ -426,8 +428,8 @@ static int launch_bwd3(const float* x, const float* A, const float* IcA, const f
     float* part = ws;
     float* Spart = part + (size_t)(sc.G + sc.nPS) * kBwdSums;
     if (int e = set_smem(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED>, kBwdSmem)) return e;
-    recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED><<<sc.G, kThreads, kBwdSmem, st>>>(x, A, IcA, feat, g, part, Spart, dx, B, H, W);
-    recovery_bwd_finalize_kernel<HAS_ICA, FAST><<<B, kFinThreads, 0, st>>>(x, A, IcA, feat, part, Spart, dfeat, dx, B, H, W);
+    launch_pdl(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED>, dim3(sc.G), dim3(kThreads), kBwdSmem, st, x, A, IcA, feat, g, part, Spart, dx, B, H, W);
+    launch_pdl(recovery_bwd_finalize_kernel<HAS_ICA, FAST>, dim3(B), dim3(kFinThreads), 0, st, x, A, IcA, feat, (const float*)part, (const float*)Spart, dfeat, dx, B, H, W);
     count_launch(2);
     return check_launch("dd_recovery_bwd");
 }

@@ -31,6 +31,7 @@ template <bool HAS_ICA, bool FAST, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads, 2)
 recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
                     const float* __restrict__ feat, float* __restrict__ y, int B, int H, int W) {
+    pdl_begin();
     extern __shared__ __align__(16) float smem[];
     float* XS2 = smem;
     float* HS = XS2 + kPairs * kXP2;
@@ -223,7 +224,7 @@ static int launch_fwd3(const float* x, const float* A, const float* IcA, const f
                        int W, cudaStream_t st) {
     const Sched sc = make_sched(B, H, W);
     if (int e = set_smem(recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED>, kFwdSmem)) return e;
-    recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED><<<sc.G, kThreads, kFwdSmem, st>>>(x, A, IcA, feat, y, B, H, W);
+    launch_pdl(recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED>, dim3(sc.G), dim3(kThreads), kFwdSmem, st, x, A, IcA, feat, y, B, H, W);
     count_launch();
     return check_launch("dd_recovery_fwd");
 }
