@@ -5,13 +5,14 @@ Public surface (mirrors the reference's names):
     preprocess_batch           synthesis + recovery loss (models/yolo/detect/train.py:70-111)
     apply_lowlight             offline darkener          (utils/lowlight_process.py)
     add_recovery_term          loss term                 (utils/loss.py:393-416)
+    HostBatchPrefetcher        double-buffered H2D staging of the dataloader's pinned uint8 batches
     RecoveryPipeline           device-resident synth -> fwd -> bwd step used by bench.py
 
 Importing this package loads ``lib/libdedark_b200.so`` and fails loudly if it has not been built.
 """
 from ._lib import launch_count, lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
 from .llie import ConvBlock, ExtractParameters2, lowlight_recovery  # noqa: F401
-from .lowlight import add_recovery_term, apply_lowlight, preprocess_batch  # noqa: F401
+from .lowlight import HostBatchPrefetcher, add_recovery_term, apply_lowlight, preprocess_batch  # noqa: F401
 from .pipeline import RecoveryPipeline  # noqa: F401
 
 __version__ = "0.1.0"

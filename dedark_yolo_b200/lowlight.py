@@ -47,6 +47,55 @@ def preprocess_batch(batch: dict, device, dark_param: float = 15.0, lowlight_FLA
     return batch
 
 
+class HostBatchPrefetcher:
+    """Double-buffered host -> device staging of the dataloader's pinned uint8 batches (train.py:72 does the same
+    ``.to(device, non_blocking=True)`` on the compute stream, where it serialises with the step).
+
+    ``submit(host_u8)`` enqueues the copy on a private copy stream; ``get()`` orders the current stream after the
+    oldest outstanding copy and returns that device tensor.  Submitting batch i+1 right after ``get()`` of batch i
+    overlaps its PCIe transfer (19.7 MB for 16x3x640x640) with the kernels of step i.  A slot is only overwritten
+    after everything enqueued up to the following ``get()`` has finished reading it.
+    """
+
+    def __init__(self, device, depth: int = 2):
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise RuntimeError("HostBatchPrefetcher needs a CUDA device")
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.buf = [None] * depth
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.consumed = [None] * depth
+        self.n_sub = 0
+        self.n_get = 0
+
+    def submit(self, host_u8: torch.Tensor) -> None:
+        if self.n_sub - self.n_get >= self.depth:
+            raise RuntimeError("HostBatchPrefetcher: all slots are in flight; call get() first")
+        k = self.n_sub % self.depth
+        if self.buf[k] is None or self.buf[k].shape != host_u8.shape or self.buf[k].dtype != host_u8.dtype:
+            self.buf[k] = torch.empty(host_u8.shape, dtype=host_u8.dtype, device=self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            if self.consumed[k] is not None:
+                self.copy_stream.wait_event(self.consumed[k])
+            self.buf[k].copy_(host_u8, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        self.n_sub += 1
+
+    def get(self) -> torch.Tensor:
+        if self.n_get >= self.n_sub:
+            raise RuntimeError("HostBatchPrefetcher: nothing submitted")
+        cur = torch.cuda.current_stream(self.dev)
+        if self.n_get > 0:  # the previous slot has been consumed by everything enqueued so far
+            j = (self.n_get - 1) % self.depth
+            self.consumed[j] = torch.cuda.Event()
+            self.consumed[j].record(cur)
+        k = self.n_get % self.depth
+        cur.wait_event(self.ready[k])
+        self.n_get += 1
+        return self.buf[k]
+
+
 def apply_lowlight(u8: torch.Tensor, lowlight_param: float = 7.5, lut: Optional[torch.Tensor] = None) -> torch.Tensor:
     """uint8 RGB NCHW -> darkened uint8 (``(pow(u8/255, p) * 255).astype(uint8)``, truncation).  This is the array
     the reference hands to ``cv2.imwrite`` (before the RGB->BGR flip and the JPEG encoder)."""
