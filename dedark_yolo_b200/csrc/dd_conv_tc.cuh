@@ -20,6 +20,7 @@
 //             row of ones yields the bias gradient)
 // M index = 128 consecutive pixels (or quads) in (b, row, col) raster order, so any batch size works.
 #pragma once
+#include "dd_async.cuh"
 #include "dd_common.cuh"
 
 namespace dd {
@@ -64,33 +65,6 @@ __device__ long long g_tc_cta_cycles[256];
     } while (0)
 #endif
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// ---- mbarrier ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-// bounded spin: a lost arrival traps (the launch fails with an error) instead of hanging the device
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-        if (spin > (1u << 24)) __trap();
-}
-
 // ---- 16-byte asynchronous global -> shared copies (LDGSTS) ----------------------------------------------------
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -116,8 +90,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// generic-proxy shared-memory writes -> visible to the async proxy (the tensor core reads operands through it)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // 16 consecutive fp32 columns of this warp's 32 TMEM lanes: thread i gets lane (lane base + i)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {

@@ -195,12 +195,17 @@ __device__ __forceinline__ void hpass8(const float* __restrict__ xrow, float out
 
 // 2 adjacent columns x 8 vertically adjacent outputs; Q[i] = ring row (first - 12 + i), columns (col2, col2+1)
 __device__ __forceinline__ void vpass8x2(const float* __restrict__ HS, int base_slot, int col2, u64 out[8]) {
-    // scatter form: each staged row is consumed as soon as it arrives (few live registers, 8 independent FMA chains)
+    // scatter form: each staged row is consumed as soon as it arrives (few live registers, 8 independent FMA chains).
+    // base_slot is a multiple of 8 and the ring depth is too: a group of 8 rows never wraps, so four group pointers
+    // (computed once) and immediate offsets replace 32 per-load ring computations.
 #pragma unroll
     for (int r = 0; r < 8; ++r) out[r] = pk(0.f, 0.f);
+    const float* grp[4];
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) grp[gi] = HS + ((base_slot + 8 * gi) & (kHRing - 1)) * kHP + col2;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        const u64 q = *reinterpret_cast<const u64*>(HS + ((base_slot + i) & (kHRing - 1)) * kHP + col2);
+        const u64 q = *reinterpret_cast<const u64*>(grp[i >> 3] + (i & 7) * kHP);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int j = i - r;

@@ -17,6 +17,9 @@
 //      the row sum S = sum_w g4 x3 (the rgb2lum quirk couples every pixel of a row to columns 0..2) by warp shuffle.
 // Per (CTA, plane-strip) partial sums and per-row S go to the workspace; a fixed-order finalize kernel (one CTA per
 // image, no float atomics) adds them up, applies the column 0..2 fix-up and the regressor Jacobians.
+#include <cstring>
+
+#include "dd_async.cuh"
 #include "dd_recovery.cuh"
 
 namespace dd {
@@ -106,13 +109,25 @@ __device__ __forceinline__ float px_bwd(float x0, float ica, float g5, float bt,
     return g1 * inv;
 }
 
-template <bool HAS_ICA, bool FAST, bool ALIGNED>
+// TMA: the g halo tile of every row-block arrives as two 16-row x 156-column boxes (cp.async.bulk.tensor through a tensor
+// map of the [planes][H][W] cotangent; everything outside the image is zero-filled by the copy engine), issued by one
+// thread and counted on an mbarrier: no per-thread address arithmetic, no staging instructions at all.
+template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2)
-recovery_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
-                    const float* __restrict__ feat, const float* __restrict__ g, float* __restrict__ part,
-                    float* __restrict__ Spart, float* __restrict__ dx, int B, int H, int W) {
+recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __restrict__ x, const float* __restrict__ A,
+                    const float* __restrict__ IcA, const float* __restrict__ feat, const float* __restrict__ g,
+                    float* __restrict__ part, float* __restrict__ Spart, float* __restrict__ dx, int B, int H, int W) {
     pdl_begin();
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t tma_bar;
+    uint32_t tma_phase = 0;
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&tma_bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
     float* XS = smem;                   // g, zero outside the image
     float* HS = XS + kXRingB * kXP;
     float* BT = HS + kHRing * kHP;      // B^T g5 for the 32 output rows of the current block
@@ -154,6 +169,17 @@ recovery_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
 
         // g block n -> ring XS (rows outside the image and columns outside [0, W) are zero)
         auto stage = [&](int n) {
+            if (TMA) {
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&tma_bar, 2u * 16u * kXP * 4u);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int v0 = n * kRB + 16 * hh;
+                        tma_load_3d(XS + (v0 % kXRingB) * kXP, &gmap, u.c0 - kRadius, u.r0 - kRadius + v0, u.plane, &tma_bar);
+                    }
+                }
+                return;
+            }
 #pragma unroll
             for (int k = 0; k < kStage4; ++k) {
                 const int f = tid + k * kThreads;
@@ -203,7 +229,12 @@ recovery_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
         }
 
         for (int n = 0; n < u.nB; ++n) {
-            cp_async_wait_all();
+            if (TMA) {
+                mbar_wait(&tma_bar, tma_phase);
+                tma_phase ^= 1u;
+            } else {
+                cp_async_wait_all();
+            }
             __syncthreads();  // g block n visible; previous pointwise phase done with BT / XS centre rows / MS
             if (n + 1 < u.nB) stage(n + 1);
 
@@ -298,12 +329,18 @@ recovery_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
                     }
                     // columns beyond W - 1 (only when W % 4 != 0): g5 and bt are zero-padded there, but bt is not
                     // (it is a blur of real data), so mask their cotangents explicitly
-                    const float l1 = gc + 1 < W ? 1.f : 0.f, l2 = gc + 2 < W ? 1.f : 0.f, l3 = gc + 3 < W ? 1.f : 0.f;
                     float4 d;
                     d.x = px_bwd<HAS_ICA, FAST>(x0.x, ic.x, g5.x, bt.x, m, q1, ck, pp, acc, srow);
-                    d.y = px_bwd<HAS_ICA, FAST>(x0.y, ic.y, g5.y * l1, bt.y * l1, m, q1, ck, pp, acc, srow);
-                    d.z = px_bwd<HAS_ICA, FAST>(x0.z, ic.z, g5.z * l2, bt.z * l2, m, q1, ck, pp, acc, srow);
-                    d.w = px_bwd<HAS_ICA, FAST>(x0.w, ic.w, g5.w * l3, bt.w * l3, m, q1, ck, pp, acc, srow);
+                    if (ALIGNED) {  // W % 4 == 0: a float4 that starts inside the image ends inside it
+                        d.y = px_bwd<HAS_ICA, FAST>(x0.y, ic.y, g5.y, bt.y, m, q1, ck, pp, acc, srow);
+                        d.z = px_bwd<HAS_ICA, FAST>(x0.z, ic.z, g5.z, bt.z, m, q1, ck, pp, acc, srow);
+                        d.w = px_bwd<HAS_ICA, FAST>(x0.w, ic.w, g5.w, bt.w, m, q1, ck, pp, acc, srow);
+                    } else {
+                        const float l1 = gc + 1 < W ? 1.f : 0.f, l2 = gc + 2 < W ? 1.f : 0.f, l3 = gc + 3 < W ? 1.f : 0.f;
+                        d.y = px_bwd<HAS_ICA, FAST>(x0.y, ic.y, g5.y * l1, bt.y * l1, m, q1, ck, pp, acc, srow);
+                        d.z = px_bwd<HAS_ICA, FAST>(x0.z, ic.z, g5.z * l2, bt.z * l2, m, q1, ck, pp, acc, srow);
+                        d.w = px_bwd<HAS_ICA, FAST>(x0.w, ic.w, g5.w * l3, bt.w * l3, m, q1, ck, pp, acc, srow);
+                    }
                     if (dx) {
                         float* dp = dx + (size_t)u.plane * H * W + off;
                         if (ALIGNED) {
@@ -421,14 +458,28 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
 
 constexpr size_t kBwdSmem = (size_t)(kXRingB * kXP + kHRing * kHP + kRB * kBP + 2 * kMaxU) * sizeof(float);
 
+template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA>
+static int launch_bwd4(const CUtensorMap& gmap, const float* x, const float* A, const float* IcA, const float* feat, const float* g,
+                       float* part, float* Spart, float* dx, int B, int H, int W, const Sched& sc, cudaStream_t st) {
+    if (int e = set_smem(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>, kBwdSmem)) return e;
+    launch_pdl(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>, dim3(sc.G), dim3(kThreads), kBwdSmem, st, gmap, x, A, IcA, feat, g, part,
+               Spart, dx, B, H, W);
+    return DD_OK;
+}
+
 template <bool HAS_ICA, bool FAST, bool ALIGNED>
 static int launch_bwd3(const float* x, const float* A, const float* IcA, const float* feat, const float* g, float* dfeat,
                        float* dx, int B, int H, int W, float* ws, cudaStream_t st) {
     const Sched sc = make_sched(B, H, W);
     float* part = ws;
     float* Spart = part + (size_t)(sc.G + sc.nPS) * kBwdSums;
-    if (int e = set_smem(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED>, kBwdSmem)) return e;
-    launch_pdl(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED>, dim3(sc.G), dim3(kThreads), kBwdSmem, st, x, A, IcA, feat, g, part, Spart, dx, B, H, W);
+    CUtensorMap gmap;
+    memset(&gmap, 0, sizeof(gmap));
+    // TMA staging needs 16-byte aligned rows (ALIGNED) and an image at least one box large; otherwise cp.async / scalar
+    const bool tma = ALIGNED && W >= kXP && H >= 16 && make_tensor_map_3d(&gmap, g, B * 3, H, W, kXP, 16);
+    if (int e = tma ? launch_bwd4<HAS_ICA, FAST, ALIGNED, ALIGNED>(gmap, x, A, IcA, feat, g, part, Spart, dx, B, H, W, sc, st)
+                    : launch_bwd4<HAS_ICA, FAST, ALIGNED, false>(gmap, x, A, IcA, feat, g, part, Spart, dx, B, H, W, sc, st))
+        return e;
     launch_pdl(recovery_bwd_finalize_kernel<HAS_ICA, FAST>, dim3(B), dim3(kFinThreads), 0, st, x, A, IcA, feat, (const float*)part, (const float*)Spart, dfeat, dx, B, H, W);
     count_launch(2);
     return check_launch("dd_recovery_bwd");
