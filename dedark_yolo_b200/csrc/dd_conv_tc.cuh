@@ -181,13 +181,12 @@ struct PrepJobs {
     PrepJob j[4];
 };
 
-__global__ void __launch_bounds__(256)
-prep_weights_kernel(PrepJobs jobs) {
-    pdl_begin();
-    const PrepJob jb = jobs.j[blockIdx.y];
+constexpr int kPrepBlocksPerJob = 32;  // CTAs (of 256 threads) per layer; 4 layers
+__device__ __forceinline__ void prep_weights_body(const PrepJobs& jobs, const int vblock) {
+    const PrepJob jb = jobs.j[vblock / kPrepBlocksPerJob];
     const int cin = jb.cin, cout = jb.cout;
     const int nf = 9 * cin * cout, nd = 16 * cin * cout;  // hi elements of each table
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += gridDim.x * blockDim.x) {
+    for (int i = (vblock % kPrepBlocksPerJob) * 256 + threadIdx.x; i < nf + nd; i += kPrepBlocksPerJob * 256) {
         float v;
         float *hi, *lo;
         if (i < nf) {

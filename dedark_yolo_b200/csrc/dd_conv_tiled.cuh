@@ -85,15 +85,13 @@ __device__ __forceinline__ void stage_input_tile(float* __restrict__ s, const fl
 // forward: thread = PY output rows x 1 output column x 8 output channels; CTA = TH x TW outputs x all COUT channels
 // -------------------------------------------------------------------------------------------------------------
 template <int CIN, int COUT, int HIN, int TH, int TW, int CICH, int PY>
-__global__ void __launch_bounds__(TW*(TH / PY) * (COUT / 8))
-conv_fwd_tiled(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-               float* __restrict__ out) {
-    pdl_begin();
+__device__ __forceinline__ void conv_fwd_tiled_body(const int bid, const float* __restrict__ in, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, float* __restrict__ out) {
     using T = InTile<TH, TW>;
     constexpr int HO = HIN / 2, TX = HO / TW, TY = HO / TH, NCHUNK = CIN / CICH;
     constexpr int IN_F = (CICH * T::PLANE + 3) & ~3, W_F = CICH * 9 * COUT, CH_F = IN_F + W_F;  // floats per chunk
     extern __shared__ __align__(16) float smem_f[];
-    const int tile = blockIdx.x % (TX * TY), b = blockIdx.x / (TX * TY);
+    const int tile = bid % (TX * TY), b = bid / (TX * TY);
     const int oh0 = (tile / TX) * TH, ow0 = (tile % TX) * TW;
     const int col = threadIdx.x % TW, rg = (threadIdx.x / TW) % (TH / PY), cog = threadIdx.x / (TW * (TH / PY));
     const float* in_img = in + (size_t)b * CIN * HIN * HIN;

@@ -10,6 +10,8 @@
 // Layout: every tensor NCHW fp32.  Activations live in the caller's workspace (dd_layout.cuh).  All
 // reductions are fixed-order (per-thread serial loops, block_sum, split partials summed in index
 // order): bit-reproducible run to run.
+#include <cooperative_groups.h>
+
 #include "dd_common.cuh"
 #include "dd_conv_tc.cuh"
 #include "dd_conv_tiled.cuh"
@@ -153,37 +155,52 @@ conv_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, c
 // -------------------------------------------------------------------------------------------------
 // fully connected layers
 // -------------------------------------------------------------------------------------------------
-// h[b][o] = leaky(flat[b] . W1[o] + b1[o]); one warp per (b, o)
+// fc1 + fc2 of one image per CLUSTER of 4 CTAs: CTA r computes h[b][16r .. 16r+15] = leaky(flat[b] . W1[o] + b1[o])
+// (warp w: outputs 16r+2w, 16r+2w+1; all 32 weight loads of a lane in flight at once), the four quarters meet through
+// distributed shared memory, and CTA 0 finishes feat[b][j] = h[b] . W2[j] + b2[j].
+constexpr int kFcCluster = 4;
 __global__ void __launch_bounds__(256)
-fc1_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w1, const float* __restrict__ b1,
-               float* __restrict__ h, int B) {
+fc_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w1, const float* __restrict__ b1,
+              const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ h, float* __restrict__ feat) {
     pdl_begin();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B * kFc1Out) return;
-    const int b = warp / kFc1Out, o = warp % kFc1Out;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int PER_CTA = kFc1Out / kFcCluster;  // 16
+    __shared__ float s_h[PER_CTA];
+    __shared__ float s_all[kFc1Out];
+    const int b = blockIdx.x / kFcCluster, r = (int)cluster.block_rank(), lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const float4* f = reinterpret_cast<const float4*>(flat + (size_t)b * kFc1In);
-    const float4* w = reinterpret_cast<const float4*>(w1 + (size_t)o * kFc1In);
-    float acc = 0.f;
-#pragma unroll 4
-    for (int i = lane; i < kFc1In / 4; i += 32) {
-        const float4 a = __ldg(f + i), c = __ldg(w + i);
-        acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+    const int o0 = r * PER_CTA + 2 * wid;
+    const float4* wa = reinterpret_cast<const float4*>(w1 + (size_t)o0 * kFc1In);
+    const float4* wb = wa + kFc1In / 4;
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kFc1In / 128; ++i) {
+        const float4 x = __ldg(f + lane + 32 * i), c0 = __ldg(wa + lane + 32 * i), c1 = __ldg(wb + lane + 32 * i);
+        acc0 = fmaf(x.x, c0.x, acc0); acc0 = fmaf(x.y, c0.y, acc0); acc0 = fmaf(x.z, c0.z, acc0); acc0 = fmaf(x.w, c0.w, acc0);
+        acc1 = fmaf(x.x, c1.x, acc1); acc1 = fmaf(x.y, c1.y, acc1); acc1 = fmaf(x.z, c1.z, acc1); acc1 = fmaf(x.w, c1.w, acc1);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) h[warp] = leaky(acc + __ldg(b1 + o));
-}
-
-// feat[b][j] = h[b] . W2[j] + b2[j]
-__global__ void __launch_bounds__(256)
-fc2_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2,
-               float* __restrict__ feat, int B) {
-    pdl_begin();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B * kFeat) return;
-    const int b = t / kFeat, j = t % kFeat;
-    float acc = 0.f;
-    for (int o = 0; o < kFc1Out; ++o) acc = fmaf(__ldg(h + b * kFc1Out + o), __ldg(w2 + j * kFc1Out + o), acc);
-    feat[t] = acc + __ldg(b2 + j);
+    acc0 = warp_sum(acc0);
+    acc1 = warp_sum(acc1);
+    if (lane == 0) {
+        const float v0 = leaky(acc0 + __ldg(b1 + o0)), v1 = leaky(acc1 + __ldg(b1 + o0 + 1));
+        s_h[2 * wid] = v0;
+        s_h[2 * wid + 1] = v1;
+        h[b * kFc1Out + o0] = v0;
+        h[b * kFc1Out + o0 + 1] = v1;
+    }
+    cluster.sync();
+    if (r == 0) {
+        if (threadIdx.x < kFc1Out) s_all[threadIdx.x] = cluster.map_shared_rank(s_h, threadIdx.x / PER_CTA)[threadIdx.x % PER_CTA];
+        __syncthreads();
+        if (threadIdx.x < kFeat) {
+            const int j = threadIdx.x;
+            float acc = 0.f;
+            for (int o = 0; o < kFc1Out; ++o) acc = fmaf(s_all[o], __ldg(w2 + j * kFc1Out + o), acc);
+            feat[b * kFeat + j] = acc + __ldg(b2 + j);
+        }
+    }
+    cluster.sync();  // keep the peers' shared memory alive until CTA 0 has read it
 }
 
 // dW2, db2 and dhpre = leaky'(h) * (dfeat . W2); single CTA
@@ -211,36 +228,34 @@ fc2_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, con
     }
 }
 
-// dW1[o][i] = sum_b dhpre[b][o] flat[b][i];  db1[o] = sum_b dhpre[b][o]
+// fc1 backward in one launch: CTAs [0, n_w) compute dW1[o][i] = sum_b dhpre[b][o] flat[b][i] and db1[o] = sum_b dhpre[b][o];
+// the others dpre5[b][i] = leaky'(a5[b][i]) * sum_o dhpre[b][o] W1[o][i]  (independent given dhpre).
 __global__ void __launch_bounds__(256)
-fc1_wgrad_kernel(const float* __restrict__ dhpre, const float* __restrict__ flat, float* __restrict__ dw1,
-                 float* __restrict__ db1, int B) {
+fc1_bwd_kernel(const float* __restrict__ dhpre, const float* __restrict__ flat, const float* __restrict__ w1,
+               float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dpre5, int B, int n_w) {
     pdl_begin();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < kFc1Out * kFc1In) {
-        const int o = t / kFc1In, i = t % kFc1In;
+    if ((int)blockIdx.x < n_w) {
+        const int t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t < kFc1Out * kFc1In) {
+            const int o = t / kFc1In, i = t % kFc1In;
+            float acc = 0.f;
+            for (int b = 0; b < B; ++b) acc = fmaf(__ldg(dhpre + b * kFc1Out + o), __ldg(flat + (size_t)b * kFc1In + i), acc);
+            dw1[t] = acc;
+        }
+        if (t < kFc1Out) {
+            float acc = 0.f;
+            for (int b = 0; b < B; ++b) acc += dhpre[b * kFc1Out + t];
+            db1[t] = acc;
+        }
+    } else {
+        const int t = ((int)blockIdx.x - n_w) * blockDim.x + threadIdx.x;
+        if (t >= B * kFc1In) return;
+        const int b = t / kFc1In, i = t % kFc1In;
         float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc = fmaf(__ldg(dhpre + b * kFc1Out + o), __ldg(flat + (size_t)b * kFc1In + i), acc);
-        dw1[t] = acc;
+#pragma unroll 8
+        for (int o = 0; o < kFc1Out; ++o) acc = fmaf(__ldg(dhpre + b * kFc1Out + o), __ldg(w1 + (size_t)o * kFc1In + i), acc);
+        dpre5[t] = leaky_grad(flat[t], acc);
     }
-    if (t < kFc1Out) {
-        float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc += dhpre[b * kFc1Out + t];
-        db1[t] = acc;
-    }
-}
-
-// dpre5[b][i] = leaky'(a5[b][i]) * sum_o dhpre[b][o] W1[o][i]
-__global__ void __launch_bounds__(256)
-fc1_dgrad_kernel(const float* __restrict__ dhpre, const float* __restrict__ w1, const float* __restrict__ a5,
-                 float* __restrict__ dpre5, int B) {
-    pdl_begin();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B * kFc1In) return;
-    const int b = t / kFc1In, i = t % kFc1In;
-    float acc = 0.f;
-    for (int o = 0; o < kFc1Out; ++o) acc = fmaf(__ldg(dhpre + b * kFc1Out + o), __ldg(w1 + (size_t)o * kFc1In + i), acc);
-    dpre5[t] = leaky_grad(a5[t], acc);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -255,15 +270,32 @@ static void launch_conv_dgrad(const float* dpre, const float* w, const float* ac
     count_launch();
 }
 
-// ---- conv1: shared-memory-tiled CUDA-core kernel (dd_conv_tiled.cuh) ------------------------------
+// ---- conv1: shared-memory-tiled CUDA-core kernel (dd_conv_tiled.cuh).  The same launch carries, in extra CTAs, the
+// preparation of the tensor-core weights of conv2..conv5 (independent of conv1; one launch less on the critical path).
 template <int CIN, int COUT, int HIN, int TH, int TW, int CICH, int PY>
-static void launch_fwd_tiled(const float* in, const float* w, const float* b, float* out, int B, cudaStream_t st) {
+__global__ void __launch_bounds__(256)
+conv1_fwd_prep_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ out, int n_conv, const tc::PrepJobs jobs) {
+    static_assert(TW * (TH / PY) * (COUT / 8) == 256, "block size");
+    pdl_begin();
+    if ((int)blockIdx.x < n_conv) conv_fwd_tiled_body<CIN, COUT, HIN, TH, TW, CICH, PY>(blockIdx.x, in, w, bias, out);
+    else tc::prep_weights_body(jobs, (int)blockIdx.x - n_conv);
+}
+
+template <int CIN, int COUT, int HIN, int TH, int TW, int CICH, int PY>
+static int launch_conv1_prep(const float* in, const float* w, const float* b, float* out, const tc::PrepJobs& jobs, int B, cudaStream_t st) {
     constexpr int HO = HIN / 2;
     constexpr size_t smem = conv_fwd_smem<CIN, COUT, TH, TW, CICH>();
-    cudaFuncSetAttribute(conv_fwd_tiled<CIN, COUT, HIN, TH, TW, CICH, PY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_pdl(conv_fwd_tiled<CIN, COUT, HIN, TH, TW, CICH, PY>, dim3(B * (HO / TH) * (HO / TW)), dim3(TW * (TH / PY) * (COUT / 8)), smem, st,
-               in, w, b, out);
+    auto kern = conv1_fwd_prep_kernel<CIN, COUT, HIN, TH, TW, CICH, PY>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(conv1_fwd_prep_kernel): %s", cudaGetErrorString(e));
+        return DD_ERR_CUDA;
+    }
+    const int n_conv = B * (HO / TH) * (HO / TW);
+    launch_pdl(kern, dim3(n_conv + 4 * tc::kPrepBlocksPerJob), dim3(256), smem, st, in, w, b, out, n_conv, jobs);
     count_launch();
+    return DD_OK;
 }
 
 // ---- conv2..conv5: tensor-core kernels (dd_conv_tc.cuh) --------------------------------------------
@@ -355,23 +387,21 @@ extern "C" int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, f
     DD_REQUIRE(r && acts && feat && B > 0 && tensors_ok(w), DD_ERR_INVALID, "dd_predictor_fwd: bad arguments");
     float* a[6];
     for (int l = 0; l < 6; ++l) a[l] = acts + pred_act_offset(l, B);
-    launch_fwd_tiled<3, 16, 256, 16, 32, 3, 4>(r, w->conv_w[0], w->conv_b[0], a[0], B, st);
     float* prep = acts + predictor_acts_elems(B);
     {
         tc::PrepJobs jobs;
         for (int l = 1; l < 5; ++l)
             jobs.j[l - 1] = tc::PrepJob{w->conv_w[l], prep + pred_prep_offset(l), prep + pred_prep_offset(l) + pred_prep_fwd_elems(l),
                                         pred_cin(l), pred_cout(l)};
-        launch_pdl(tc::prep_weights_kernel, dim3(32, 4), dim3(256), 0, st, jobs);
-        count_launch();
+        if (int e = launch_conv1_prep<3, 16, 256, 16, 32, 3, 4>(r, w->conv_w[0], w->conv_b[0], a[0], jobs, B, st)) return e;
     }
     if (int e = launch_tc_fwd<16, 32, 128>(a[0], prep + pred_prep_offset(1), w->conv_b[1], a[1], B, st)) return e;
     if (int e = launch_tc_fwd<32, 32, 64>(a[1], prep + pred_prep_offset(2), w->conv_b[2], a[2], B, st)) return e;
     if (int e = launch_tc_fwd<32, 32, 32>(a[2], prep + pred_prep_offset(3), w->conv_b[3], a[3], B, st)) return e;
     if (int e = launch_tc_fwd<32, 32, 16>(a[3], prep + pred_prep_offset(4), w->conv_b[4], a[4], B, st)) return e;
-    launch_pdl(fc1_fwd_kernel, dim3((B * kFc1Out * 32 + 255) / 256), dim3(256), 0, st, a[4], w->fc1_w, w->fc1_b, a[5], B);
-    launch_pdl(fc2_fwd_kernel, dim3((B * kFeat + 255) / 256), dim3(256), 0, st, a[5], w->fc2_w, w->fc2_b, feat, B);
-    count_launch(2);
+    launch_pdl_cluster(fc_fwd_kernel, dim3(B * kFcCluster), dim3(256), 0, st, kFcCluster, (const float*)a[4], (const float*)w->fc1_w, (const float*)w->fc1_b,
+               (const float*)w->fc2_w, (const float*)w->fc2_b, a[5], feat);
+    count_launch();
     return check_launch("dd_predictor_fwd");
 }
 
@@ -393,9 +423,12 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     float* partial = reinterpret_cast<float*>(ws) + predictor_acts_elems(B);
 
     launch_pdl(fc2_bwd_kernel, dim3(1), dim3(1024), 0, st, dfeat, a[5], w->fc2_w, g->fc2_w, g->fc2_b, d[5], B);
-    launch_pdl(fc1_wgrad_kernel, dim3((kFc1Out * kFc1In + 255) / 256), dim3(256), 0, st, d[5], a[4], g->fc1_w, g->fc1_b, B);
-    launch_pdl(fc1_dgrad_kernel, dim3((B * kFc1In + 255) / 256), dim3(256), 0, st, d[5], w->fc1_w, a[4], d[4], B);
-    count_launch(3);
+    {
+        const int n_w = (kFc1Out * kFc1In + 255) / 256, n_d = (B * kFc1In + 255) / 256;
+        launch_pdl(fc1_bwd_kernel, dim3(n_w + n_d), dim3(256), 0, st, (const float*)d[5], a[4], (const float*)w->fc1_w, g->fc1_w, g->fc1_b,
+                   d[4], B, n_w);
+    }
+    count_launch(2);
     // conv5 .. conv2: weight-gradient slices and the data gradient of a layer in one tensor-core launch; conv1: weight
     // gradient on the CUDA cores; one deferred reduction of all slice buffers at the end
     const float* prep = acts + predictor_acts_elems(B);
