@@ -435,13 +435,22 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     float* pl[5];
     int nsl[5];
     for (int l = 0; l < 5; ++l) pl[l] = partial + pred_wgrad_partial_offset(l, B);
-    nsl[0] = B * kWgradC1Slices;
+    nsl[0] = B * kWgradC1Slices < kTcMaxCtas ? B * kWgradC1Slices : kTcMaxCtas;  // persistent: one slice per CTA
     auto dg = [&](int l) { return prep + pred_prep_offset(l) + pred_prep_fwd_elems(l); };
     if (int e = launch_tc_bwd<32, 32, 16>(a[3], d[4], dg(4), a[3], pl[4], d[3], &nsl[4], B, st)) return e;
     if (int e = launch_tc_bwd<32, 32, 32>(a[2], d[3], dg(3), a[2], pl[3], d[2], &nsl[3], B, st)) return e;
     if (int e = launch_tc_bwd<32, 32, 64>(a[1], d[2], dg(2), a[1], pl[2], d[1], &nsl[2], B, st)) return e;
     if (int e = launch_tc_bwd<16, 32, 128>(a[0], d[1], dg(1), a[0], pl[1], d[0], &nsl[1], B, st)) return e;
-    launch_pdl(conv_wgrad_tiled_c3<16, 256, 8, 32>, dim3(nsl[0]), dim3(32 * 8), 0, st, r, d[0], pl[0]);  // first layer (CIN = 3)
+    {   // first layer (CIN = 3): persistent CUDA-core kernel
+        constexpr size_t smem = conv_wgrad_c3_smem<16, 8, 32>();
+        auto kern = conv_wgrad_c3_kernel<16, 256, 8, 32>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_wgrad_c3_kernel): %s", cudaGetErrorString(e));
+            return DD_ERR_CUDA;
+        }
+        launch_pdl(kern, dim3(nsl[0]), dim3(256), smem, st, r, (const float*)d[0], pl[0], B * kWgradC1Slices);
+    }
     {
         tc::ReduceJobs jobs;
         int block0 = 0;
