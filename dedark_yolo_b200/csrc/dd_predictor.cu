@@ -203,58 +203,66 @@ fc_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w1, cons
     cluster.sync();  // keep the peers' shared memory alive until CTA 0 has read it
 }
 
-// dW2, db2 and dhpre = leaky'(h) * (dfeat . W2); single CTA
-__global__ void __launch_bounds__(1024)
-fc2_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, const float* __restrict__ w2,
-               float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dhpre, int B) {
-    pdl_begin();
-    const int t = threadIdx.x;
-    if (t < kFeat * kFc1Out) {
-        const int j = t / kFc1Out, o = t % kFc1Out;
-        float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc = fmaf(dfeat[b * kFeat + j], h[b * kFc1Out + o], acc);
-        dw2[t] = acc;
-    }
-    if (t < kFeat) {
-        float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc += dfeat[b * kFeat + t];
-        db2[t] = acc;
-    }
-    for (int i = t; i < B * kFc1Out; i += blockDim.x) {
-        const int b = i / kFc1Out, o = i % kFc1Out;
-        float acc = 0.f;
-        for (int j = 0; j < kFeat; ++j) acc = fmaf(dfeat[b * kFeat + j], w2[j * kFc1Out + o], acc);
-        dhpre[i] = leaky_grad(h[i], acc);
-    }
-}
-
-// fc1 backward in one launch: CTAs [0, n_w) compute dW1[o][i] = sum_b dhpre[b][o] flat[b][i] and db1[o] = sum_b dhpre[b][o];
-// the others dpre5[b][i] = leaky'(a5[b][i]) * sum_o dhpre[b][o] W1[o][i]  (independent given dhpre).
+// The whole FC backward in ONE launch.  dhpre[b][o] = leaky'(h[b][o]) * sum_j dfeat[b][j] W2[j][o] is so cheap (15 MACs)
+// that every CTA recomputes the few values it needs in shared memory instead of waiting for a separate kernel:
+//   CTAs [0, n_w)         dW1[o][i] = sum_b dhpre[b][o] flat[b][i]  (256 consecutive i of ONE o per CTA), db1[o]
+//   CTAs [n_w, n_w + n_d) dpre5[b][i] = leaky'(a5[b][i]) * sum_o dhpre[b][o] W1[o][i]  (256 consecutive i of ONE image)
+//   last CTA              dW2[j][o] = sum_b dfeat[b][j] h[b][o],  db2[j] = sum_b dfeat[b][j]
 __global__ void __launch_bounds__(256)
-fc1_bwd_kernel(const float* __restrict__ dhpre, const float* __restrict__ flat, const float* __restrict__ w1,
-               float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dpre5, int B, int n_w) {
+fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, const float* __restrict__ w2,
+              const float* __restrict__ flat, const float* __restrict__ w1, float* __restrict__ dw2, float* __restrict__ db2,
+              float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dpre5, int B, int n_w, int n_d) {
     pdl_begin();
-    if ((int)blockIdx.x < n_w) {
-        const int t = blockIdx.x * blockDim.x + threadIdx.x;
-        if (t < kFc1Out * kFc1In) {
-            const int o = t / kFc1In, i = t % kFc1In;
-            float acc = 0.f;
-            for (int b = 0; b < B; ++b) acc = fmaf(__ldg(dhpre + b * kFc1Out + o), __ldg(flat + (size_t)b * kFc1In + i), acc);
-            dw1[t] = acc;
+    static_assert(kFc1In % 256 == 0, "a CTA never straddles two rows of W1");
+    __shared__ float s_dh[256];
+    const int tid = threadIdx.x, bid = blockIdx.x;
+    if (bid < n_w) {
+        const int t = bid * 256 + tid, o = t / kFc1In, i = t % kFc1In;
+        float acc = 0.f, bsum = 0.f;
+        for (int b0 = 0; b0 < B; b0 += 256) {
+            const int nb = min(256, B - b0);
+            if (tid < nb) {
+                const int b = b0 + tid;
+                float v = 0.f;
+#pragma unroll
+                for (int j = 0; j < kFeat; ++j) v = fmaf(__ldg(dfeat + b * kFeat + j), __ldg(w2 + j * kFc1Out + o), v);
+                s_dh[tid] = leaky_grad(__ldg(h + b * kFc1Out + o), v);
+            }
+            __syncthreads();
+            for (int bb = 0; bb < nb; ++bb) {
+                acc = fmaf(s_dh[bb], __ldg(flat + (size_t)(b0 + bb) * kFc1In + i), acc);
+                bsum += s_dh[bb];
+            }
+            __syncthreads();
         }
-        if (t < kFc1Out) {
-            float acc = 0.f;
-            for (int b = 0; b < B; ++b) acc += dhpre[b * kFc1Out + t];
-            db1[t] = acc;
+        dw1[t] = acc;
+        if (i == 0) db1[o] = bsum;
+    } else if (bid < n_w + n_d) {
+        const int t = (bid - n_w) * 256 + tid, b = t / kFc1In, i = t % kFc1In;  // b is the same for the whole CTA
+        if (tid < kFc1Out && b < B) {
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < kFeat; ++j) v = fmaf(__ldg(dfeat + b * kFeat + j), __ldg(w2 + j * kFc1Out + tid), v);
+            s_dh[tid] = leaky_grad(__ldg(h + b * kFc1Out + tid), v);
         }
-    } else {
-        const int t = ((int)blockIdx.x - n_w) * blockDim.x + threadIdx.x;
-        if (t >= B * kFc1In) return;
-        const int b = t / kFc1In, i = t % kFc1In;
+        __syncthreads();
+        if (b >= B) return;
         float acc = 0.f;
 #pragma unroll 8
-        for (int o = 0; o < kFc1Out; ++o) acc = fmaf(__ldg(dhpre + b * kFc1Out + o), __ldg(w1 + (size_t)o * kFc1In + i), acc);
+        for (int o = 0; o < kFc1Out; ++o) acc = fmaf(s_dh[o], __ldg(w1 + (size_t)o * kFc1In + i), acc);
         dpre5[t] = leaky_grad(flat[t], acc);
+    } else {
+        for (int t = tid; t < kFeat * kFc1Out; t += 256) {
+            const int j = t / kFc1Out, o = t % kFc1Out;
+            float acc = 0.f;
+            for (int b = 0; b < B; ++b) acc = fmaf(__ldg(dfeat + b * kFeat + j), __ldg(h + b * kFc1Out + o), acc);
+            dw2[t] = acc;
+        }
+        if (tid < kFeat) {
+            float acc = 0.f;
+            for (int b = 0; b < B; ++b) acc += __ldg(dfeat + b * kFeat + tid);
+            db2[tid] = acc;
+        }
     }
 }
 
@@ -422,13 +430,12 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     }
     float* partial = reinterpret_cast<float*>(ws) + predictor_acts_elems(B);
 
-    launch_pdl(fc2_bwd_kernel, dim3(1), dim3(1024), 0, st, dfeat, a[5], w->fc2_w, g->fc2_w, g->fc2_b, d[5], B);
     {
-        const int n_w = (kFc1Out * kFc1In + 255) / 256, n_d = (B * kFc1In + 255) / 256;
-        launch_pdl(fc1_bwd_kernel, dim3(n_w + n_d), dim3(256), 0, st, (const float*)d[5], a[4], (const float*)w->fc1_w, g->fc1_w, g->fc1_b,
-                   d[4], B, n_w);
+        const int n_w = kFc1Out * kFc1In / 256, n_d = (B * kFc1In + 255) / 256;
+        launch_pdl(fc_bwd_kernel, dim3(n_w + n_d + 1), dim3(256), 0, st, dfeat, a[5], (const float*)w->fc2_w, a[4], (const float*)w->fc1_w,
+                   g->fc2_w, g->fc2_b, g->fc1_w, g->fc1_b, d[4], B, n_w, n_d);
     }
-    count_launch(2);
+    count_launch();
     // conv5 .. conv2: weight-gradient slices and the data gradient of a layer in one tensor-core launch; conv1: weight
     // gradient on the CUDA cores; one deferred reduction of all slice buffers at the end
     const float* prep = acts + predictor_acts_elems(B);

@@ -371,21 +371,77 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
                              float* __restrict__ dfeat, float* __restrict__ dx, int B, int H, int W) {
     pdl_begin();
     __shared__ ImgParams sp;
-    __shared__ double s_red[32];
+    __shared__ double s_red[32][7];
     const int tid = threadIdx.x, b = blockIdx.x;
     const Sched sc = make_sched(B, H, W);
     if (tid == 0) regress(feat + b * kFeat, sp);
-    __syncthreads();
-    const float pg = sp.gamma, pc = sp.c;
     double dp = 0, dc = 0, dg = 0, dw = 0, ds[3] = {0, 0, 0};
+    const float kappa[3] = {kLumR, kLumG, kLumB};
+
+    // rows of the column 0..2 fix-up, two per thread and pass: every load is issued before anything that needs the
+    // regressed parameters (this kernel is a chain of dependent latencies, not of arithmetic)
+    for (int i0 = 0; i0 < 3 * H; i0 += 2 * kFinThreads) {
+        float S[2], x0[2][3], ica[2][3];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = i0 + e * kFinThreads + tid;
+            S[e] = 0.f;
+            if (i < 3 * H) {
+                const int ch = i / H, row = i - ch * H, plane = 3 * b + ch;
+                for (int st = 0; st < sc.strips; ++st) S[e] += Spart[((size_t)plane * H + row) * sc.strips + st];
+                const size_t off = ((size_t)plane * H + row) * W;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    x0[e][k] = __ldg(x + off + k);
+                    ica[e][k] = HAS_ICA ? __ldg(IcA + ((size_t)b * H + row) * W + k) : kDefaultIcA;
+                }
+            }
+        }
+        if (i0 == 0) __syncthreads();  // sp
+        const float pg = sp.gamma, pc = sp.c;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = i0 + e * kFinThreads + tid;
+            if (i >= 3 * H) continue;
+            const int ch = i / H, row = i - ch * H, plane = 3 * b + ch;
+            const float a = A ? __ldg(A + b * 3 + ch) : kDefaultA;
+            const ChainK ck = make_chain(sp, ch, a);
+            const size_t off = ((size_t)plane * H + row) * W;
+            float tx[3], txc[3], x1[3], x2[3], x2c[3], x3[3], l2[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                tx[k] = 1.f - ck.w * ica[e][k];
+                txc[k] = fmaxf(tx[k], kTxMin);
+                x1[k] = (x0[e][k] - a) / txc[k] + a;
+                x2[k] = x1[k] * ck.s;
+                x2c[k] = fmaxf(x2[k], kGammaClamp);
+                x3[k] = gamma_pow<FAST>(x2c[k], pg, &l2[k]);
+            }
+            const RowLum rl = row_lum<false>(x3[0], x3[1], x3[2]);
+            if (rl.lraw >= 0.f && rl.lraw <= 1.f) {
+                const float dq = 0.5f * kPi * sinf(kPi * rl.lum) / rl.denom - rl.cl / (rl.denom * rl.denom);
+                const float glum = pc * dq * S[e];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float e3 = kappa[k] * glum;
+                    dg += (double)(e3 * x3[k] * l2[k]) * 0.69314718055994530942;
+                    const float e2 = x2[k] >= kGammaClamp ? e3 * pg * x3[k] / x2c[k] : 0.f;
+                    ds[ch] += (double)(e2 * x1[k]);
+                    const float e1 = e2 * ck.s;
+                    if (tx[k] >= kTxMin) dw += (double)(e1 * (x0[e][k] - a) * ica[e][k] / (txc[k] * txc[k]));
+                    if (dx) dx[off + k] += e1 / txc[k];
+                }
+            }
+        }
+    }
 
     // partial sums: plane-strip ps of this image was processed by CTAs c_of(first block) .. c_of(last block)
     for (int i = tid; i < 3 * sc.strips; i += kFinThreads) {
         const int ps = 3 * b * sc.strips + i;
         const int ch = i / sc.strips;
-        const long long x0 = (long long)ps * sc.nRB, x1 = x0 + sc.nRB - 1;
-        const int c_first = (int)(((x0 + 1) * sc.G + sc.N - 1) / sc.N) - 1;
-        const int c_last = (int)(((x1 + 1) * sc.G + sc.N - 1) / sc.N) - 1;
+        const long long x0b = (long long)ps * sc.nRB, x1b = x0b + sc.nRB - 1;
+        const int c_first = (int)(((x0b + 1) * sc.G + sc.N - 1) / sc.N) - 1;
+        const int c_last = (int)(((x1b + 1) * sc.G + sc.N - 1) / sc.N) - 1;
         // default-IcA constants folded out of the kernel's acc.w
         const float txc = fmaxf(1.f - sp.w * kDefaultIcA, kTxMin);
         const float wk = HAS_ICA ? 1.f : ((1.f - sp.w * kDefaultIcA >= kTxMin) ? kDefaultIcA / (txc * txc) : 0.f);
@@ -394,49 +450,24 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
             dp += q[0]; dc += q[1]; dg += (double)q[2] * 0.69314718055994530942; ds[ch] += q[3]; dw += (double)q[4] * wk;
         }
     }
-    const float kappa[3] = {kLumR, kLumG, kLumB};
-    for (int i = tid; i < 3 * H; i += kFinThreads) {
-        const int ch = i / H, row = i - ch * H, plane = 3 * b + ch;
-        float S = 0.f;
-        for (int st = 0; st < sc.strips; ++st) S += Spart[((size_t)plane * H + row) * sc.strips + st];
-        const float a = A ? __ldg(A + b * 3 + ch) : kDefaultA;
-        const ChainK ck = make_chain(sp, ch, a);
-        const size_t off = ((size_t)plane * H + row) * W;
-        float x0[3], ica[3], tx[3], txc[3], x1[3], x2[3], x2c[3], x3[3], l2[3];
+    {   // the seven block sums in one pass: lanes (shuffles), then warps in index order (deterministic)
+        double v[7] = {dp, dc, dg, dw, ds[0], ds[1], ds[2]};
+        const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            x0[k] = __ldg(x + off + k);
-            ica[k] = HAS_ICA ? __ldg(IcA + ((size_t)b * H + row) * W + k) : kDefaultIcA;
-            tx[k] = 1.f - ck.w * ica[k];
-            txc[k] = fmaxf(tx[k], kTxMin);
-            x1[k] = (x0[k] - a) / txc[k] + a;
-            x2[k] = x1[k] * ck.s;
-            x2c[k] = fmaxf(x2[k], kGammaClamp);
-            x3[k] = gamma_pow<FAST>(x2c[k], pg, &l2[k]);
+        for (int k = 0; k < 7; ++k) {
+            v[k] = warp_sum(v[k]);
+            if (lane == 0) s_red[wid][k] = v[k];
         }
-        const RowLum rl = row_lum<false>(x3[0], x3[1], x3[2]);
-        if (rl.lraw >= 0.f && rl.lraw <= 1.f) {
-            const float dq = 0.5f * kPi * sinf(kPi * rl.lum) / rl.denom - rl.cl / (rl.denom * rl.denom);
-            const float glum = pc * dq * S;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float e3 = kappa[k] * glum;
-                dg += (double)(e3 * x3[k] * l2[k]) * 0.69314718055994530942;
-                const float e2 = x2[k] >= kGammaClamp ? e3 * pg * x3[k] / x2c[k] : 0.f;
-                ds[ch] += (double)(e2 * x1[k]);
-                const float e1 = e2 * ck.s;
-                if (tx[k] >= kTxMin) dw += (double)(e1 * (x0[k] - a) * ica[k] / (txc[k] * txc[k]));
-                if (dx) dx[off + k] += e1 / txc[k];
-            }
+        __syncthreads();
+        if (tid < 7) {
+            double r = 0.0;
+            for (int w = 0; w < kFinThreads / 32; ++w) r += s_red[w][tid];
+            s_red[0][tid] = r;
         }
+        __syncthreads();
+        dp = s_red[0][0]; dc = s_red[0][1]; dg = s_red[0][2]; dw = s_red[0][3];
+        ds[0] = s_red[0][4]; ds[1] = s_red[0][5]; ds[2] = s_red[0][6];
     }
-    dp = block_sum<double>(dp, s_red);
-    dc = block_sum<double>(dc, s_red);
-    dg = block_sum<double>(dg, s_red);
-    dw = block_sum<double>(dw, s_red);
-    ds[0] = block_sum<double>(ds[0], s_red);
-    ds[1] = block_sum<double>(ds[1], s_red);
-    ds[2] = block_sum<double>(ds[2], s_red);
     if (tid == 0) {
         float* o = dfeat + b * kFeat;
         for (int i = 0; i < kFeat; ++i) o[i] = 0.f;
