@@ -51,6 +51,17 @@ BYTES_SYNTH = 12 * N_PIX + 12 * N_PIX        # fp32 clean in, dark out
 BYTES_RESIZE_TAPS = 3 * 256 * 256 * 4 * 4
 
 
+def load_traffic(kernel: str):
+    """Measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture,
+    profiles/r01_traffic.json, written from the committed ncu summaries); None when no capture exists."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)["dram_bytes_per_launch"].get(kernel)
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -298,7 +309,8 @@ def run_ours(args):
     achieved = alg[dominant] / (stage_us[dominant] * 1e-6) / 1e9
     roofline = {
         "bound": "hbm", "kernel": {"filters_fwd": "recovery_fwd_kernel", "filters_bwd": "recovery_bwd_kernel (+finalize)"}[dominant],
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": load_traffic({"filters_fwd": "recovery_fwd_kernel", "filters_bwd": "recovery_bwd_kernel"}[dominant]),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dominant],
         "kernel_us": stage_us[dominant],
         "all_stages_us": stage_us,
@@ -340,8 +352,19 @@ def run_ours(args):
         e2e_step(i)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    # the pinned-host -> device copy alone (what bounds the overlapped pipeline): 5 copies of one batch, CUDA events
+    h2d0, h2d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_u8 = torch.empty_like(host_u8[0], device=dev)
+    dev_u8.copy_(host_u8[0], non_blocking=True)
+    h2d0.record()
+    for _ in range(5):
+        dev_u8.copy_(host_u8[0], non_blocking=True)
+    h2d1.record()
+    torch.cuda.synchronize(dev)
+    h2d_gbs = 5 * host_u8[0].numel() / (h2d0.elapsed_time(h2d1) * 1e-3) / 1e9
     e2e = {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 3 * H * W,
            "d2h_bytes_per_step": 8, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "h2d_gbs_measured": h2d_gbs, "h2d_ms_per_step_alone": B * 3 * H * W / (h2d_gbs * 1e9) * 1e3,
            "api": "HostBatchPrefetcher(uint8 pinned host batch, H2D of step i+1 overlapped with step i) -> preprocess_batch -> "
                   "lowlight_recovery(nn.Module) fwd -> autograd bwd -> D2H(recovery loss, grad norm) + stream sync every step"}
 

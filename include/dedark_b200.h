@@ -40,7 +40,7 @@ extern "C" {
 
 /* workspace kinds for dd_workspace_bytes */
 #define DD_WS_SYNTH 0          /* dd_synth_fwd partial sums                                        */
-#define DD_WS_PREDICTOR_ACTS 1 /* activations kept from dd_predictor_fwd for dd_predictor_bwd     */
+#define DD_WS_PREDICTOR_ACTS 1 /* activations + prepared tensor-core weights kept from dd_predictor_fwd for dd_predictor_bwd */
 #define DD_WS_PREDICTOR_BWD 2  /* scratch of dd_predictor_bwd                                      */
 #define DD_WS_RECOVERY_BWD 3   /* partial sums of dd_recovery_bwd                                  */
 
@@ -91,10 +91,13 @@ typedef struct dd_predictor_tensors {
     float* fc2_b;
 } dd_predictor_tensors;
 
-/* r [B,3,256,256] -> feat [B,15]; acts: DD_WS_PREDICTOR_ACTS bytes, kept by the caller for bwd. */
+/* r [B,3,256,256] -> feat [B,15]; acts: DD_WS_PREDICTOR_ACTS bytes, kept by the caller for bwd.  conv2..conv5 run on the
+ * tensor cores (tcgen05, split-TF32 operands, fp32 accumulation); behind the activations `acts` also receives the
+ * weights of those layers re-laid-out for the tensor-core operands, which dd_predictor_bwd of the SAME weights reuses. */
 int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, float* acts, float* feat, int B,
                      void* stream);
-/* dfeat [B,15] -> grads (all 14 tensors overwritten) and, if dr != NULL, dL/dr [B,3,256,256]. */
+/* dfeat [B,15] -> grads (all 14 tensors overwritten) and, if dr != NULL, dL/dr [B,3,256,256].  `acts` must come from
+ * dd_predictor_fwd called with the same `w` (it carries the prepared weights).  Deterministic (fixed-order sums). */
 int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, const float* acts,
                      const float* dfeat, const dd_predictor_tensors* grads, float* dr, int B,
                      void* ws, size_t ws_bytes, void* stream);

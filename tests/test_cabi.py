@@ -30,8 +30,12 @@ def test_workspace_sizes():
     from dedark_yolo_b200 import _lib
     acts = _lib.workspace_bytes(_lib.WS_PREDICTOR_ACTS, 16)
     per_img = 16 * 128 * 128 + 32 * 64 * 64 + 32 * 32 * 32 + 32 * 16 * 16 + 32 * 8 * 8 + 64
-    assert acts == 16 * per_img * 4
-    assert _lib.workspace_bytes(_lib.WS_PREDICTOR_BWD, 16) > acts
+    # + the prepared tensor-core weights of conv2..conv5: (18 + 32) * Cin * Cout floats per layer (hi and lo halves of the
+    # forward and data-gradient operand layouts), independent of the batch size
+    prep = (18 + 32) * (16 * 32 + 3 * 32 * 32)
+    assert acts == (16 * per_img + prep) * 4
+    assert _lib.workspace_bytes(_lib.WS_PREDICTOR_ACTS, 1) == (per_img + prep) * 4
+    assert _lib.workspace_bytes(_lib.WS_PREDICTOR_BWD, 16) > 16 * per_img * 4
     assert _lib.workspace_bytes(_lib.WS_SYNTH, 1) >= 8 * 148
     small = _lib.workspace_bytes(_lib.WS_RECOVERY_BWD, 1, 13, 13)
     big = _lib.workspace_bytes(_lib.WS_RECOVERY_BWD, 16, 640, 640)

@@ -303,3 +303,42 @@ def test_pipeline_step_matches_module(dd):
     y_g, rec_g, flat_g = pipe8.replay("k")
     torch.cuda.synchronize()
     assert torch.equal(y_e, y_g) and torch.equal(flat_e, flat_g) and torch.equal(rec_e, rec_g)
+
+
+# ---- host staging + determinism ---------------------------------------------------------------------------------------
+def test_host_batch_prefetcher_overlapped_copies_are_exact(dd):
+    """Every batch comes out of the double-buffered H2D staging bit-identical and in order, also when a slot is
+    reused while later work is still enqueued."""
+    gen = torch.Generator().manual_seed(9)
+    host = [torch.randint(0, 256, (2, 3, 40, 48), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(5)]
+    pf = dd.HostBatchPrefetcher("cuda")
+    pf.submit(host[0])
+    outs = []
+    for i in range(5):
+        src = pf.get()
+        if i + 1 < 5:
+            pf.submit(host[i + 1])
+        batch = dd.preprocess_batch({"img": src}, "cuda", dark_param=5.0)
+        outs.append(batch["clean_img"].clone())
+    torch.cuda.synchronize()
+    for i in range(5):
+        assert torch.equal(outs[i].cpu(), host[i].float() / 255), f"batch {i}"
+    with pytest.raises(RuntimeError):
+        pf.get()  # nothing outstanding
+
+
+def test_predictor_is_bit_reproducible(ops):
+    """Fixed-order reductions everywhere (slices summed in index order, no float atomics): two runs agree bit for bit."""
+    w = golden_weights(1.0)
+    gen = torch.Generator().manual_seed(33)
+    r = torch.rand(5, 3, 256, 256, generator=gen).cuda()
+    dfeat = torch.randn(5, 15, generator=gen).cuda()
+    params = cuda_params(w)
+    runs = []
+    for _ in range(2):
+        feat, acts = ops.predictor_forward(r, params)
+        grads, _ = ops.predictor_backward(r, params, acts, dfeat)
+        runs.append((feat.clone(), [g.clone() for g in grads]))
+    assert torch.equal(runs[0][0], runs[1][0])
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert torch.equal(a, b)
