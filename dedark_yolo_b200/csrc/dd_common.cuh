@@ -57,6 +57,23 @@ int check_launch(const char* what);  // cudaGetLastError -> DD_OK / DD_ERR_CUDA
         }                                \
     } while (0)
 
+// opt a kernel into > 48 KB of dynamic shared memory once per (call site, device): the attribute call costs a few
+// microseconds of host time, which matters for eager launches (the static lives in the enclosing template instance)
+#define DD_ENSURE_SMEM(kern, bytes, what)                                                                   \
+    do {                                                                                                    \
+        static unsigned long long dd_mask__ = 0ull;                                                         \
+        int dd_dev__ = 0;                                                                                   \
+        cudaGetDevice(&dd_dev__);                                                                           \
+        if (!((dd_mask__ >> (dd_dev__ & 63)) & 1ull)) {                                                     \
+            cudaError_t dd_e__ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+            if (dd_e__ != cudaSuccess) {                                                                    \
+                dd::set_error("cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(dd_e__));            \
+                return DD_ERR_CUDA;                                                                         \
+            }                                                                                               \
+            dd_mask__ |= 1ull << (dd_dev__ & 63);                                                           \
+        }                                                                                                   \
+    } while (0)
+
 // ---- programmatic dependent launch ---------------------------------------------------------------
 // Every kernel of the library is launched with the programmatic-stream-serialization attribute and starts with
 // pdl_begin(): the next kernel in the stream may be scheduled as soon as all CTAs of this one have started (its CTAs

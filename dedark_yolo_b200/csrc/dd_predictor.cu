@@ -295,11 +295,7 @@ static int launch_conv1_prep(const float* in, const float* w, const float* b, fl
     constexpr int HO = HIN / 2;
     constexpr size_t smem = conv_fwd_smem<CIN, COUT, TH, TW, CICH>();
     auto kern = conv1_fwd_prep_kernel<CIN, COUT, HIN, TH, TW, CICH, PY>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(conv1_fwd_prep_kernel): %s", cudaGetErrorString(e));
-        return DD_ERR_CUDA;
-    }
+    DD_ENSURE_SMEM(kern, smem, "conv1_fwd_prep_kernel");
     const int n_conv = B * (HO / TH) * (HO / TW);
     launch_pdl(kern, dim3(n_conv + 4 * tc::kPrepBlocksPerJob), dim3(256), smem, st, in, w, b, out, n_conv, jobs);
     count_launch();
@@ -321,11 +317,7 @@ static int launch_tc_fwd(const float* in, const float* wprep, const float* bias,
     constexpr int HO = HIN / 2;
     constexpr size_t smem = tc::conv_tc_fwd_smem<CIN, COUT>();
     auto kern = tc::conv_tc_fwd<CIN, COUT, HIN>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(conv_tc_fwd): %s", cudaGetErrorString(e));
-        return DD_ERR_CUDA;
-    }
+    DD_ENSURE_SMEM(kern, smem, "conv_tc_fwd");
     const int total = B * HO * HO, ntiles = (total + 127) / 128;
     launch_pdl(kern, dim3(ntiles < sm_count() ? ntiles : sm_count()), dim3(288), smem, st, in, wprep, bias, out, total);  // persistent: <= 1 CTA per SM
     count_launch();
@@ -340,11 +332,7 @@ static int launch_tc_bwd(const float* in, const float* dpre, const float* wprep_
     constexpr int HO = HIN / 2;
     constexpr size_t smem = tc::conv_tc_bwd_smem<CIN, COUT, HIN>();
     auto kern = tc::conv_tc_bwd<CIN, COUT, HIN>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(conv_tc_bwd): %s", cudaGetErrorString(e));
-        return DD_ERR_CUDA;
-    }
+    DD_ENSURE_SMEM(kern, smem, "conv_tc_bwd");
     const int total = B * HO * HO;
     const int wtiles = (total + tc::WgradCfg<CIN>::PXT - 1) / tc::WgradCfg<CIN>::PXT, dtiles = (total + 127) / 128;
     const int ctas = sm_count() < kTcMaxCtas ? sm_count() : kTcMaxCtas;
@@ -451,11 +439,7 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     {   // first layer (CIN = 3): persistent CUDA-core kernel
         constexpr size_t smem = conv_wgrad_c3_smem<16, 8, 32>();
         auto kern = conv_wgrad_c3_kernel<16, 256, 8, 32>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(conv_wgrad_c3_kernel): %s", cudaGetErrorString(e));
-            return DD_ERR_CUDA;
-        }
+        DD_ENSURE_SMEM(kern, smem, "conv_wgrad_c3_kernel");
         launch_pdl(kern, dim3(nsl[0]), dim3(256), smem, st, r, (const float*)d[0], pl[0], B * kWgradC1Slices);
     }
     {

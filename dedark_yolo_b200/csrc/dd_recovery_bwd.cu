@@ -492,7 +492,7 @@ constexpr size_t kBwdSmem = (size_t)(kXRingB * kXP + kHRing * kHP + kRB * kBP + 
 template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA>
 static int launch_bwd4(const CUtensorMap& gmap, const float* x, const float* A, const float* IcA, const float* feat, const float* g,
                        float* part, float* Spart, float* dx, int B, int H, int W, const Sched& sc, cudaStream_t st) {
-    if (int e = set_smem(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>, kBwdSmem)) return e;
+    DD_ENSURE_SMEM((recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>), kBwdSmem, "recovery kernel");
     launch_pdl(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>, dim3(sc.G), dim3(kThreads), kBwdSmem, st, gmap, x, A, IcA, feat, g, part,
                Spart, dx, B, H, W);
     return DD_OK;

@@ -223,7 +223,7 @@ template <bool HAS_ICA, bool FAST, bool ALIGNED>
 static int launch_fwd3(const float* x, const float* A, const float* IcA, const float* feat, float* y, int B, int H,
                        int W, cudaStream_t st) {
     const Sched sc = make_sched(B, H, W);
-    if (int e = set_smem(recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED>, kFwdSmem)) return e;
+    DD_ENSURE_SMEM((recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED>), kFwdSmem, "recovery kernel");
     launch_pdl(recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED>, dim3(sc.G), dim3(kThreads), kFwdSmem, st, x, A, IcA, feat, y, B, H, W);
     count_launch();
     return check_launch("dd_recovery_fwd");

@@ -322,7 +322,7 @@ def test_host_batch_prefetcher_overlapped_copies_are_exact(dd):
         outs.append(batch["clean_img"].clone())
     torch.cuda.synchronize()
     for i in range(5):
-        assert torch.equal(outs[i].cpu(), host[i].float() / 255), f"batch {i}"
+        assert torch.equal(outs[i], host[i].cuda().float() / 255), f"batch {i}"  # the reference's expression on this GPU
     with pytest.raises(RuntimeError):
         pf.get()  # nothing outstanding
 
