@@ -99,6 +99,30 @@ __device__ inline void regress(const float* __restrict__ f, ImgParams& P) {
     P.p = P.t[kSlotUsm] * 5.0f / 2.0f + 2.5f;
 }
 
+// The same regressors computed by one WARP (all 32 lanes call it): the seven tanh and the four exp run in two parallel
+// levels instead of eleven dependent libm calls on one thread while the whole CTA waits (the values are bit-identical:
+// same expressions, same order of the final sums).
+__device__ inline void regress_warp(const float* __restrict__ f, ImgParams& P) {
+    const int lane = threadIdx.x & 31;
+    if (lane < kFeat) {
+        const bool wb = lane >= kSlotWb && lane < kSlotWb + 3;
+        const bool live = lane == kSlotDedark || wb || lane == kSlotGamma || lane == kSlotContrast || lane == kSlotUsm;
+        float t = 0.f;
+        if (live) t = tanhf(wb ? f[lane] * (lane == kSlotWb ? 0.f : 1.f) : f[lane]);
+        P.t[lane] = t;
+        if (wb) P.cs[lane - kSlotWb] = expf(t * 1.0f / 2.0f);
+        if (lane == kSlotGamma) P.gamma = expf(t * kLn3);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        P.w = P.t[kSlotDedark] * 0.9f / 2.0f + 0.55f;
+        P.Z = kWbEps + kLumR * P.cs[0] + kLumG * P.cs[1] + kLumB * P.cs[2];
+        for (int j = 0; j < 3; ++j) P.s[j] = P.cs[j] / P.Z;
+        P.c = P.t[kSlotContrast];
+        P.p = P.t[kSlotUsm] * 5.0f / 2.0f + 2.5f;
+    }
+}
+
 // Per-(image, channel) constants of the pointwise chain.  With the default IcA (a constant 0.5) DeDark and WB
 // collapse into one FMA:  x2 = x0 * k1 + k0,  k1 = s / txc,  k0 = (a - a / txc) * s.
 struct ChainK {

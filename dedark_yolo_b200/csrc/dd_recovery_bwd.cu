@@ -159,7 +159,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         if (cur_ps >= 0 && u.ps != cur_ps) flush();
         cur_ps = u.ps;
         __syncthreads();
-        if (tid == 0) regress(feat + u.b * kFeat, sp);
+        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
         __syncthreads();
         const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
         const float pc = sp.c, pp = sp.p;
@@ -210,22 +210,37 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         };
         stage(0);
 
-        for (int v = tid; v < u.nU; v += kThreads) {
-            const int row = u.r0 - kRadius + v;
-            float m = 0.f, q1 = 0.f;
-            if (row >= 0 && row < H) {
-                float x3[3];
+        {   // per-row contrast scalars of the segment: all loads first (<= 3 rows per thread), then the arithmetic
+            constexpr int kPer = (kMaxU + kThreads - 1) / kThreads;
+            float x0r[kPer][3], icr[kPer][3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float ica = HAS_ICA ? __ldg(ip + (size_t)row * W + k) : kDefaultIcA;
-                    x3[k] = chain_x3<HAS_ICA, FAST>(ck, __ldg(xp + (size_t)row * W + k), ica);
+            for (int k = 0; k < kPer; ++k) {
+                const int v = tid + k * kThreads, row = u.r0 - kRadius + v;
+                if (v < u.nU && row >= 0 && row < H) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        x0r[k][c] = __ldg(xp + (size_t)row * W + c);
+                        icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
+                    }
                 }
-                const RowLum rl = row_lum<false>(x3[0], x3[1], x3[2]);
-                q1 = rl.q - 1.f;
-                m = (1.f - pc) + pc * rl.q;
             }
-            MSm[v] = m;
-            MSq[v] = q1;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int v = tid + k * kThreads, row = u.r0 - kRadius + v;
+                if (v < u.nU) {
+                    float m = 0.f, q1 = 0.f;
+                    if (row >= 0 && row < H) {
+                        float x3[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) x3[c] = chain_x3<HAS_ICA, FAST>(ck, x0r[k][c], icr[k][c]);
+                        const RowLum rl = row_lum<false>(x3[0], x3[1], x3[2]);
+                        q1 = rl.q - 1.f;
+                        m = (1.f - pc) + pc * rl.q;
+                    }
+                    MSm[v] = m;
+                    MSq[v] = q1;
+                }
+            }
         }
 
         for (int n = 0; n < u.nB; ++n) {
@@ -374,7 +389,7 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
     __shared__ double s_red[32][7];
     const int tid = threadIdx.x, b = blockIdx.x;
     const Sched sc = make_sched(B, H, W);
-    if (tid == 0) regress(feat + b * kFeat, sp);
+    if (tid < 32) regress_warp(feat + b * kFeat, sp);
     double dp = 0, dc = 0, dg = 0, dw = 0, ds[3] = {0, 0, 0};
     const float kappa[3] = {kLumR, kLumG, kLumB};
 

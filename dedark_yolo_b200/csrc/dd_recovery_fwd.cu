@@ -48,7 +48,7 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
         const Seg u = next_seg(blk, blk_end, sc, H);
         blk += seg_blocks(u);
         __syncthreads();  // previous segment fully consumed (rings, MS, sp)
-        if (tid == 0) regress(feat + u.b * kFeat, sp);
+        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
         __syncthreads();
         const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
         const float pc = sp.c, pp = sp.p;
@@ -56,16 +56,32 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
         const float* ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
         float* yp = y + (size_t)u.plane * H * W;
 
-        for (int v = tid; v < u.nU; v += kThreads) {
-            const int row = reflect(u.r0 - kRadius + v, H);
-            float x3[3];
+        {   // per-row contrast scalars of the segment: all loads first (<= 3 rows per thread), then the arithmetic
+            constexpr int kPer = (kMaxU + kThreads - 1) / kThreads;
+            float x0r[kPer][3], icr[kPer][3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float ica = HAS_ICA ? __ldg(ip + (size_t)row * W + k) : kDefaultIcA;
-                x3[k] = chain_x3<HAS_ICA, FAST>(ck, __ldg(xp + (size_t)row * W + k), ica);
+            for (int k = 0; k < kPer; ++k) {
+                const int v = tid + k * kThreads;
+                if (v < u.nU) {
+                    const int row = reflect(u.r0 - kRadius + v, H);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        x0r[k][c] = __ldg(xp + (size_t)row * W + c);
+                        icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
+                    }
+                }
             }
-            const RowLum rl = row_lum<true>(x3[0], x3[1], x3[2]);
-            MS[v] = (1.f - pc) + pc * rl.q;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int v = tid + k * kThreads;
+                if (v < u.nU) {
+                    float x3[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) x3[c] = chain_x3<HAS_ICA, FAST>(ck, x0r[k][c], icr[k][c]);
+                    const RowLum rl = row_lum<true>(x3[0], x3[1], x3[2]);
+                    MS[v] = (1.f - pc) + pc * rl.q;
+                }
+            }
         }
 
         // item (k) of a thread: row pair rp (2 rows) x float4 column c4; fixed across blocks
