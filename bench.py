@@ -223,7 +223,24 @@ def run_ours(args):
     B = B_PER_GPU
     torch.manual_seed(0)
     module = dd.lowlight_recovery(3).to(dev).train()
-    pipe = dd.RecoveryPipeline(module, B, H, W, dark_param=DARK_PARAM, allreduce=world > 1)
+    # N > 1: the predictor backward exchanges its gradients itself over peer memory (dd_predictor_bwd_allreduce); only if
+    # the buffers cannot be shared between the processes does the step fall back to one NCCL all-reduce (and says so)
+    exchange, exchange_how = None, "none (single GPU)"
+    if world > 1 and os.environ.get("DEDARK_EXCHANGE", "peer") == "nccl":
+        exchange_how = "NCCL all-reduce(sum) of the flat gradient (DEDARK_EXCHANGE=nccl)"
+    elif world > 1:
+        ok = torch.zeros(1, device=dev)
+        try:
+            from dedark_yolo_b200.dist import GradExchange
+            exchange = GradExchange(dev)
+            exchange_how = f"fused into the predictor backward over peer memory ({exchange.how}), no collective library call"
+            ok += 1
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] rank {rank}: peer exchange unavailable ({e!r}); using NCCL all-reduce", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1:
+            exchange, exchange_how = None, "NCCL all-reduce(sum) of the flat gradient (peer buffers could not be shared)"
+    pipe = dd.RecoveryPipeline(module, B, H, W, dark_param=DARK_PARAM, allreduce=world > 1, exchange=exchange)
 
     # input ring: RING distinct (clean, g) sets; one step touches ~390 MB, so a set is long gone from L2 when reused
     RING = 4
@@ -388,7 +405,7 @@ def run_ours(args):
     # the same host-to-host step through the C-ABI pipeline object (RecoveryPipeline): the uint8 batch lands in one of the
     # prefetcher's two device slots, the step that reads that slot is a captured CUDA graph (one graph per slot), the
     # result (recovery loss, gradient norm) is copied back and awaited every step.  No autograd / Python per kernel.
-    pipe8 = dd.RecoveryPipeline(module, B, H, W, dark_param=DARK_PARAM, src_dtype=torch.uint8, allreduce=False)
+    pipe8 = dd.RecoveryPipeline(module, B, H, W, dark_param=DARK_PARAM, src_dtype=torch.uint8, allreduce=False, exchange=exchange)
     pf2 = dd.HostBatchPrefetcher(dev)
     for k in range(2):  # allocate both slots, then capture one graph per slot
         pf2.submit(host_u8[k])
@@ -404,7 +421,7 @@ def run_ours(args):
         assert src.data_ptr() == slots[i % 2].data_ptr()
         pf2.submit(host_u8[(i + 1) % 2])
         pipe8.graphs[("u8", i % 2)].replay()
-        if world > 1:
+        if world > 1 and exchange is None:
             dist.all_reduce(pipe8.flat_grad)
         res_dev[0] = pipe8.rec
         res_dev[1] = pipe8.flat_grad.norm()
@@ -452,7 +469,8 @@ def run_ours(args):
             "config": {
                 "workload": "configs[1]: lowlight_recovery fwd+bwd + recovery_loss, batch 16x3x640x640 fp32 synthetic per GPU "
                             "(synthesis clean**15 + mse, resize, predictor fwd, fused filters fwd, fused filters bwd, predictor bwd"
-                            + (", NCCL all-reduce of 164943 grads)" if world > 1 else ")"),
+                            + (", all-reduce of 164943 grads)" if world > 1 else ")"),
+                "gradient_exchange": exchange_how,
                 "global_batch": world * B, "parallelism": f"dp{world}", "launch": "cuda_graph" if use_graph else "eager",
                 "l2": f"inputs rotate over a ring of {RING} (clean, g) sets = {RING * 2 * B * 3 * H * W * 4 / 1e6:.0f} MB + "
                       f"{2 * B * 3 * H * W * 4 / 1e6:.0f} MB of outputs per step (L2 = 126 MB); no explicit flush",

@@ -17,7 +17,9 @@ SRC_U8, SRC_F32 = 0, 1
 EXPORTS = (
     "dd_version", "dd_last_error", "dd_launch_count", "dd_workspace_bytes", "dd_synth_fwd", "dd_resize256",
     "dd_resize256_bwd", "dd_predictor_fwd", "dd_predictor_bwd", "dd_recovery_fwd", "dd_recovery_bwd",
+    "dd_predictor_bwd_allreduce", "dd_exchange_bytes",
 )
+MAX_PEERS = 8
 
 
 class PredictorTensors(C.Structure):
@@ -34,6 +36,21 @@ class PredictorTensors(C.Structure):
             t.conv_b[i] = tensors[2 * i + 1].data_ptr()
         t.fc1_w, t.fc1_b, t.fc2_w, t.fc2_b = (tensors[k].data_ptr() for k in (10, 11, 12, 13))
         return t
+
+
+class PeerExchange(C.Structure):
+    """``dd_peer_exchange``: this rank, the world size and every rank's exchange buffer as addressed from this process."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("buf", C.c_void_p * MAX_PEERS)]
+
+    @classmethod
+    def from_pointers(cls, rank: int, ptrs):
+        if not (1 <= len(ptrs) <= MAX_PEERS and 0 <= rank < len(ptrs)):
+            raise ValueError(f"peer exchange: rank {rank} / world {len(ptrs)} (at most {MAX_PEERS} peers)")
+        px = cls()
+        px.rank, px.world = rank, len(ptrs)
+        for i, q in enumerate(ptrs):
+            px.buf[i] = int(q)
+        return px
 
 
 def _load():
@@ -55,7 +72,11 @@ def _load():
     lib.dd_predictor_bwd.argtypes = [vp, C.POINTER(PredictorTensors), vp, vp, C.POINTER(PredictorTensors), vp, i, vp, sz, vp]
     lib.dd_recovery_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
     lib.dd_recovery_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, vp, sz, vp]
-    for name in EXPORTS[4:]:
+    lib.dd_predictor_bwd_allreduce.argtypes = [vp, C.POINTER(PredictorTensors), vp, vp, C.POINTER(PredictorTensors), i, vp, sz,
+                                               C.POINTER(PeerExchange), vp]
+    lib.dd_exchange_bytes.restype = sz
+    lib.dd_exchange_bytes.argtypes = []
+    for name in EXPORTS[4:-1]:
         getattr(lib, name).restype = i
     return lib
 

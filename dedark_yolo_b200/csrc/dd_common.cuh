@@ -120,6 +120,32 @@ inline cudaError_t launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 bl
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// ---- peer exchange (dd_predictor_bwd_allreduce) ----------------------------------------------------
+// world <= 1: no exchange.  Otherwise gradient element `off` (canonical flat order) is also stored into slot [rank] of
+// the current parity in every rank's exchange buffer (peer memory over NVLink) as ONE 8-byte word {value, tag}: the tag
+// (epoch + 1) travels with the data, so the receiver polls the element itself -- no fence, no separate flag, no second
+// NVLink round trip (the "LL" idea of collective libraries).
+struct PushCtx {
+    int rank, world;
+    unsigned char* buf[8];
+};
+__device__ __forceinline__ uint2* exchange_slot(unsigned char* buf, unsigned int parity, int rank) {
+    constexpr size_t kHdr = 256, kPitch = 164944, kPeers = 8;
+    return reinterpret_cast<uint2*>(buf + kHdr) + ((size_t)parity * kPeers + rank) * kPitch;
+}
+__device__ __forceinline__ void push_grad(const PushCtx& px, unsigned int tag, int off, float v) {
+    const uint2 word = make_uint2(__float_as_uint(v), tag);
+#pragma unroll 1
+    for (int p = 0; p < px.world; ++p) {
+        uint2* dst = exchange_slot(px.buf[p], (tag - 1u) & 1u, px.rank) + off;
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(word.x), "r"(word.y) : "memory");
+    }
+}
+// tag of the exchange in progress = epoch of the local buffer + 1 (stable during a step); 0 when there is no exchange
+__device__ __forceinline__ unsigned int push_tag(const PushCtx& px) {
+    return px.world > 1 ? *reinterpret_cast<const volatile unsigned int*>(px.buf[px.rank]) + 1u : 0u;
+}
+
 // ---- device helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

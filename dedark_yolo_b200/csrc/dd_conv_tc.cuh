@@ -22,6 +22,7 @@
 #pragma once
 #include "dd_async.cuh"
 #include "dd_common.cuh"
+#include "dd_layout.cuh"
 
 namespace dd {
 namespace tc {
@@ -802,14 +803,16 @@ struct ReduceJob {
     float* dw;
     float* db;
     int nslices, n, stride, cin, nw, block0;  // n live outputs per slice, stride floats between slices
+    int off_w, off_b;                         // offsets of dw / db in the canonical flat gradient (peer exchange)
 };
 struct ReduceJobs {
     ReduceJob j[5];
 };
 __global__ void __launch_bounds__(1024)
-wgrad_reduce_kernel(const ReduceJobs jobs) {
+wgrad_reduce_kernel(const ReduceJobs jobs, const PushCtx px) {
     pdl_begin();
     __shared__ float s_part[32][33];
+    const unsigned int tag = push_tag(px);
     int ji = 0;
 #pragma unroll
     for (int k = 1; k < 5; ++k)
@@ -834,13 +837,70 @@ wgrad_reduce_kernel(const ReduceJobs jobs) {
         float r = 0.f;
 #pragma unroll
         for (int k = 0; k < 32; ++k) r += s_part[k][lane];
+        int off;  // canonical flat offset of this output
         if (jb.cin == 0) {
-            if (i < jb.nw) jb.dw[i] = r; else jb.db[i - jb.nw] = r;
+            if (i < jb.nw) { jb.dw[i] = r; off = jb.off_w + i; } else { jb.db[i - jb.nw] = r; off = jb.off_b + i - jb.nw; }
         } else {
             const int row = i >> 5, co = i & 31;
-            if (row == 9 * jb.cin) jb.db[co] = r;
-            else jb.dw[((size_t)co * jb.cin + row % jb.cin) * 9 + row / jb.cin] = r;
+            if (row == 9 * jb.cin) { jb.db[co] = r; off = jb.off_b + co; }
+            else {
+                const int e = (co * jb.cin + row % jb.cin) * 9 + row / jb.cin;
+                jb.dw[e] = r;
+                off = jb.off_w + e;
+            }
         }
+        if (px.world > 1) push_grad(px, tag, off, r);  // straight into every peer's slot (peer exchange, see below)
+    }
+}
+
+// Final kernel of dd_predictor_bwd_allreduce.  Every gradient element was stored into slot [rank] of every peer by the
+// kernel that produced it: the FC gradients (80 % of the bytes) by fc_bwd_kernel at the START of the backward, overlapped
+// with the whole convolution backward, the convolution gradients by the deferred slice reduction.  This kernel
+//   1. for every gradient element polls the 8-byte {value, tag} words of all ranks until they carry this exchange's tag
+//      and adds them in rank order (bitwise identical on every rank), written through the 14 tensor pointers;
+//   2. its last CTA closes the exchange (epoch + 1).
+struct GradPtrs {
+    float* p[14];  // state-dict order
+};
+__global__ void __launch_bounds__(512)
+allreduce_exchange_kernel(const PushCtx px, const GradPtrs gp) {
+    pdl_begin();
+    ExchangeHeader* me = reinterpret_cast<ExchangeHeader*>(px.buf[px.rank]);
+    const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&me->epoch), tag = e + 1u;
+    constexpr int kOff[15] = {grad_off_conv_w(0), grad_off_conv_b(0), grad_off_conv_w(1), grad_off_conv_b(1), grad_off_conv_w(2),
+                              grad_off_conv_b(2), grad_off_conv_w(3), grad_off_conv_b(3), grad_off_conv_w(4), grad_off_conv_b(4),
+                              kGradOffFc1W, kGradOffFc1B, kGradOffFc2W, kGradOffFc2B, kNumGrads};
+    auto segment = [&](int i) {
+        int seg = 0;
+#pragma unroll
+        for (int k = 1; k < 14; ++k)
+            if (i >= kOff[k]) seg = k;
+        return seg;
+    };
+    const uint2* slots = exchange_slot(px.buf[px.rank], e & 1u, 0);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNumGrads; i += gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < px.world; ++r) {
+            const uint2* src = slots + (size_t)r * kGradPad + i;
+            uint2 wv;
+            unsigned int spin = 0;
+            do {
+                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(wv.x), "=r"(wv.y) : "l"(src) : "memory");
+                if (++spin > (1u << 27)) __trap();  // a peer never arrived (about a minute): fail the launch instead of hanging the device
+            } while (wv.y != tag);
+            acc += __uint_as_float(wv.x);
+        }
+        const int seg = segment(i);
+        gp.p[seg][i - kOff[seg]] = acc;
+    }
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&me->blocks_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {  // every element of every rank has been read: the exchange is complete on this rank
+        me->blocks_done = 0u;
+        __threadfence();
+        *reinterpret_cast<volatile unsigned int*>(&me->epoch) = tag;
     }
 }
 

@@ -56,6 +56,26 @@ inline size_t predictor_bwd_ws_bytes(int B) {
     return (predictor_acts_elems(B) + pred_wgrad_partial_offset(5, B)) * sizeof(float);
 }
 
+// ---- peer exchange of the predictor gradient ----------------------------------------------
+// canonical flat order = state-dict order: [w0 b0 w1 b1 w2 b2 w3 b3 w4 b4 | fc1_w fc1_b fc2_w fc2_b], 164 943 floats
+constexpr int kNumGrads = 164943;
+constexpr int kGradPad = 164944;  // slot pitch (floats), 16-byte multiple
+__host__ __device__ constexpr int grad_off_conv_w(int l) {
+    return l == 0 ? 0 : l == 1 ? 448 : 448 + 4640 + (l - 2) * 9248;
+}
+__host__ __device__ constexpr int grad_off_conv_b(int l) { return grad_off_conv_w(l) + 9 * pred_cin(l) * pred_cout(l); }
+constexpr int kGradOffFc1W = 448 + 4640 + 3 * 9248, kGradOffFc1B = kGradOffFc1W + kFc1Out * kFc1In;
+constexpr int kGradOffFc2W = kGradOffFc1B + kFc1Out, kGradOffFc2B = kGradOffFc2W + 15 * kFc1Out;
+static_assert(kGradOffFc2B + 15 == kNumGrads, "flat gradient layout");
+constexpr int kMaxPeers = 8;
+// exchange buffer of one rank: header (256 B) + slots[2 parities][kMaxPeers][kGradPad] of 8-byte words {value, tag}
+struct ExchangeHeader {
+    unsigned int epoch;        // completed exchanges on this rank; the exchange in progress carries tag epoch + 1, parity epoch & 1
+    unsigned int blocks_done;  // last-block counter of the exchange kernel
+};
+constexpr size_t kExchangeHeaderBytes = 256;
+inline size_t exchange_bytes() { return kExchangeHeaderBytes + (size_t)2 * kMaxPeers * kGradPad * 8; }
+
 // ---- fused filter chain --------------------------------------------------------------------------
 // Work space of dd_recovery_fwd/bwd: every (image plane b*3+ch, 128-column strip) -- a "plane-strip" -- is cut
 // into row-blocks of 32 output rows.  The N = nPS * nRB row-blocks are dealt out in contiguous, equal ranges to

@@ -11,6 +11,7 @@
 // reductions are fixed-order (per-thread serial loops, block_sum, split partials summed in index
 // order): bit-reproducible run to run.
 #include <cooperative_groups.h>
+#include <cstring>
 
 #include "dd_common.cuh"
 #include "dd_conv_tc.cuh"
@@ -211,9 +212,11 @@ fc_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w1, cons
 __global__ void __launch_bounds__(256)
 fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, const float* __restrict__ w2,
               const float* __restrict__ flat, const float* __restrict__ w1, float* __restrict__ dw2, float* __restrict__ db2,
-              float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dpre5, int B, int n_w, int n_d) {
+              float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dpre5, int B, int n_w, int n_d,
+              const PushCtx px) {
     pdl_begin();
     static_assert(kFc1In % 256 == 0, "a CTA never straddles two rows of W1");
+    const unsigned int tag = push_tag(px);
     __shared__ float s_dh[256];
     const int tid = threadIdx.x, bid = blockIdx.x;
     if (bid < n_w) {
@@ -237,6 +240,10 @@ fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, cons
         }
         dw1[t] = acc;
         if (i == 0) db1[o] = bsum;
+        if (px.world > 1) {
+            push_grad(px, tag, kGradOffFc1W + t, acc);
+            if (i == 0) push_grad(px, tag, kGradOffFc1B + o, bsum);
+        }
     } else if (bid < n_w + n_d) {
         const int t = (bid - n_w) * 256 + tid, b = t / kFc1In, i = t % kFc1In;  // b is the same for the whole CTA
         if (tid < kFc1Out && b < B) {
@@ -257,12 +264,15 @@ fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, cons
             float acc = 0.f;
             for (int b = 0; b < B; ++b) acc = fmaf(__ldg(dfeat + b * kFeat + j), __ldg(h + b * kFc1Out + o), acc);
             dw2[t] = acc;
+            if (px.world > 1) push_grad(px, tag, kGradOffFc2W + t, acc);
         }
         if (tid < kFeat) {
             float acc = 0.f;
             for (int b = 0; b < B; ++b) acc += __ldg(dfeat + b * kFeat + tid);
             db2[tid] = acc;
+            if (px.world > 1) push_grad(px, tag, kGradOffFc2B + tid, acc);
         }
+
     }
 }
 
@@ -401,11 +411,17 @@ extern "C" int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, f
     return check_launch("dd_predictor_fwd");
 }
 
-extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, const float* acts,
-                                const float* dfeat, const dd_predictor_tensors* g, float* dr, int B, void* ws,
-                                size_t ws_bytes, void* stream_) {
-    using namespace dd;
-    cudaStream_t st = (cudaStream_t)stream_;
+namespace dd {
+static int predictor_bwd_impl(const float* r, const dd_predictor_tensors* w, const float* acts, const float* dfeat,
+                              const dd_predictor_tensors* g, float* dr, int B, void* ws, size_t ws_bytes,
+                              const dd_peer_exchange* pxh, cudaStream_t st) {
+    PushCtx px;
+    memset(&px, 0, sizeof(px));
+    if (pxh && pxh->world > 1) {
+        px.rank = pxh->rank;
+        px.world = pxh->world;
+        for (int i = 0; i < pxh->world; ++i) px.buf[i] = reinterpret_cast<unsigned char*>(pxh->buf[i]);
+    }
     DD_REQUIRE(r && acts && dfeat && B > 0 && tensors_ok(w) && tensors_ok(g), DD_ERR_INVALID,
                "dd_predictor_bwd: bad arguments");
     DD_REQUIRE(ws && ws_bytes >= predictor_bwd_ws_bytes(B), DD_ERR_WORKSPACE, "dd_predictor_bwd: workspace %zu < %zu",
@@ -421,7 +437,7 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
     {
         const int n_w = kFc1Out * kFc1In / 256, n_d = (B * kFc1In + 255) / 256;
         launch_pdl(fc_bwd_kernel, dim3(n_w + n_d + 1), dim3(256), 0, st, dfeat, a[5], (const float*)w->fc2_w, a[4], (const float*)w->fc1_w,
-                   g->fc2_w, g->fc2_b, g->fc1_w, g->fc1_b, d[4], B, n_w, n_d);
+                   g->fc2_w, g->fc2_b, g->fc1_w, g->fc1_b, d[4], B, n_w, n_d, px);
     }
     count_launch();
     // conv5 .. conv2: weight-gradient slices and the data gradient of a layer in one tensor-core launch; conv1: weight
@@ -448,12 +464,42 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
         for (int l = 0; l < 5; ++l) {
             const int n = l == 0 ? 432 + 16 : (9 * pred_cin(l) + 1) * 32;
             jobs.j[l] = tc::ReduceJob{pl[l], g->conv_w[l], g->conv_b[l], nsl[l], n, l == 0 ? n : pred_wgrad_rp(l) * 32,
-                                      l == 0 ? 0 : pred_cin(l), 432, block0};
+                                      l == 0 ? 0 : pred_cin(l), 432, block0, grad_off_conv_w(l), grad_off_conv_b(l)};
             block0 += (n + 31) / 32;
         }
-        launch_pdl(tc::wgrad_reduce_kernel, dim3(block0), dim3(1024), 0, st, jobs);
+        launch_pdl(tc::wgrad_reduce_kernel, dim3(block0), dim3(1024), 0, st, jobs, px);
     }
     count_launch(2);
+    if (px.world > 1) {
+        tc::GradPtrs gp;
+        for (int l = 0; l < 5; ++l) {
+            gp.p[2 * l] = g->conv_w[l];
+            gp.p[2 * l + 1] = g->conv_b[l];
+        }
+        gp.p[10] = g->fc1_w; gp.p[11] = g->fc1_b; gp.p[12] = g->fc2_w; gp.p[13] = g->fc2_b;
+        launch_pdl(tc::allreduce_exchange_kernel, dim3(sm_count()), dim3(512), 0, st, px, gp);
+        count_launch();
+    }
     if (dr) launch_conv_dgrad<3, 16, 256, 3>(d[0], w->conv_w[0], nullptr, dr, B, st);
     return check_launch("dd_predictor_bwd");
+}
+}  // namespace dd
+
+extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, const float* acts,
+                                const float* dfeat, const dd_predictor_tensors* g, float* dr, int B, void* ws,
+                                size_t ws_bytes, void* stream_) {
+    return dd::predictor_bwd_impl(r, w, acts, dfeat, g, dr, B, ws, ws_bytes, nullptr, (cudaStream_t)stream_);
+}
+
+extern "C" size_t dd_exchange_bytes(void) { return dd::exchange_bytes(); }
+
+extern "C" int dd_predictor_bwd_allreduce(const float* r, const dd_predictor_tensors* w, const float* acts,
+                                          const float* dfeat, const dd_predictor_tensors* g, int B, void* ws,
+                                          size_t ws_bytes, const dd_peer_exchange* px, void* stream_) {
+    using namespace dd;
+    DD_REQUIRE(px && px->world >= 1 && px->world <= DD_MAX_PEERS && px->rank >= 0 && px->rank < px->world, DD_ERR_INVALID,
+               "dd_predictor_bwd_allreduce: bad peer exchange descriptor");
+    for (int i = 0; i < px->world; ++i)
+        DD_REQUIRE(px->buf[i] != nullptr, DD_ERR_INVALID, "dd_predictor_bwd_allreduce: peer buffer %d is null", i);
+    return predictor_bwd_impl(r, w, acts, dfeat, g, nullptr, B, ws, ws_bytes, px, (cudaStream_t)stream_);
 }

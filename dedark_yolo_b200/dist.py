@@ -39,6 +39,56 @@ def init_from_env(backend: str = "nccl"):
     return rank, local_rank, world
 
 
+class GradExchange:
+    """Peer-memory exchange buffers for ``dd_predictor_bwd_allreduce``.
+
+    Every rank allocates one exchange buffer (``dd_exchange_bytes()``, zero-filled) that all ranks of the node map into
+    their address space: through ``torch.distributed._symmetric_memory`` when it is available, otherwise through CUDA IPC
+    handles of a plain allocation.  ``self.px`` is the descriptor the C-ABI takes; the predictor backward then stores its
+    gradients straight into the peers' buffers and sums the world's contributions itself -- no collective library call.
+    Raises if the buffers cannot be shared (the caller then keeps the NCCL all-reduce and says so)."""
+
+    def __init__(self, device, group=None):
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("GradExchange needs an initialised process group")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.MAX_PEERS:
+            raise RuntimeError(f"GradExchange: world size {self.world} > {_lib.MAX_PEERS}")
+        dev = torch.device(device)
+        nbytes = int(_lib.lib.dd_exchange_bytes())
+        self.how, self._keep = None, []
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            self._keep += [buf, hdl]
+            self.how = "symmetric_memory"
+        except Exception as e_symm:  # pragma: no cover - depends on driver / fabric support
+            try:
+                buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+                info = buf.untyped_storage()._share_cuda_()
+                infos = [None] * self.world
+                dist.all_gather_object(infos, info, group=group)
+                ptrs = []
+                for r, inf in enumerate(infos):
+                    if r == self.rank:
+                        ptrs.append(buf.data_ptr())
+                    else:
+                        st = torch.UntypedStorage._new_shared_cuda(*inf)
+                        self._keep.append(st)
+                        ptrs.append(st.data_ptr())
+                self._keep.append(buf)
+                self.how = "cuda_ipc"
+            except Exception as e_ipc:
+                raise RuntimeError(f"GradExchange: cannot share buffers (symmetric memory: {e_symm!r}; CUDA IPC: {e_ipc!r})")
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)  # every buffer is zero-filled and mapped before anyone stores into it
+        self.px = _lib.PeerExchange.from_pointers(self.rank, ptrs)
+
+
 def allreduce_flat_(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
     """In-place all-reduce(sum) of the flat gradient buffer; a no-op for a single process."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

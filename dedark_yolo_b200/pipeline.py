@@ -27,7 +27,8 @@ def _p(t):
 
 class RecoveryPipeline:
     def __init__(self, module: lowlight_recovery, B: int, H: int, W: int, dark_param: float = 15.0,
-                 src_dtype: torch.dtype = torch.float32, device=None, process_group=None, allreduce: bool = False):
+                 src_dtype: torch.dtype = torch.float32, device=None, process_group=None, allreduce: bool = False,
+                 exchange=None):
         dev = torch.device(device if device is not None else next(module.parameters()).device)
         if dev.type != "cuda":
             raise RuntimeError("RecoveryPipeline needs a CUDA device (no CPU fallback)")
@@ -58,6 +59,9 @@ class RecoveryPipeline:
         self._g = PredictorTensors.from_tensors(self.grads)
         self.allreduce = allreduce
         self.pg = process_group
+        # exchange: a dist.GradExchange (or any object with a ``px`` descriptor).  With it the predictor backward itself
+        # exchanges and sums the gradients over peer memory (dd_predictor_bwd_allreduce) and no NCCL call is made.
+        self.exchange = exchange
         self.graphs = {}
 
     # -- individual stages (each is one C-ABI call) -------------------------------------------------------
@@ -76,8 +80,12 @@ class RecoveryPipeline:
         B, H, W = self.B, self.H, self.W
         check(lib.dd_recovery_bwd(_p(self.dark), _p(A), _p(IcA), _p(self.feat), _p(g), _p(self.dfeat), None, B, H, W,
                                   _p(self._ws_rb), self._ws_rb.numel(), st))
-        check(lib.dd_predictor_bwd(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.dfeat), C.byref(self._g), None, B,
-                                   _p(self._ws_pb), self._ws_pb.numel(), st))
+        if self.exchange is not None:
+            check(lib.dd_predictor_bwd_allreduce(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.dfeat), C.byref(self._g), B,
+                                                 _p(self._ws_pb), self._ws_pb.numel(), C.byref(self.exchange.px), st))
+        else:
+            check(lib.dd_predictor_bwd(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.dfeat), C.byref(self._g), None, B,
+                                       _p(self._ws_pb), self._ws_pb.numel(), st))
 
     def step(self, src: torch.Tensor, g: torch.Tensor):
         """One full pass: ``src`` is the clean batch (uint8 or fp32 [B,3,H,W]), ``g`` the cotangent dL/dy."""
@@ -87,7 +95,7 @@ class RecoveryPipeline:
             self.synth(src, st)
             self.forward(st)
             self.backward(g, st)
-            if self.allreduce:
+            if self.allreduce and self.exchange is None:
                 torch.distributed.all_reduce(self.flat_grad, group=self.pg)
         return self.y, self.rec, self.flat_grad
 
@@ -108,6 +116,6 @@ class RecoveryPipeline:
 
     def replay(self, key):
         self.graphs[key].replay()
-        if self.allreduce:
+        if self.allreduce and self.exchange is None:
             torch.distributed.all_reduce(self.flat_grad, group=self.pg)
         return self.y, self.rec, self.flat_grad

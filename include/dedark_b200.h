@@ -102,6 +102,26 @@ int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, const float*
                      const float* dfeat, const dd_predictor_tensors* grads, float* dr, int B,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* ---- 8(e): predictor backward fused with the exchange of its gradients over peer memory ----------------------
+ * One process per GPU on one NVLink/NVSwitch node.  Every rank owns an exchange buffer of dd_exchange_bytes() bytes
+ * (zero-filled once by the caller, then owned by the library) that is mapped into every peer (CUDA IPC / symmetric
+ * memory: done by the host layer); buf[r] is rank r's buffer as addressed from THIS process.
+ * dd_predictor_bwd_allreduce == dd_predictor_bwd followed by all-reduce(sum) of the 14 gradient tensors, as ONE
+ * stream-ordered sequence with no collective library call: the kernels that produce the gradients (the FC backward at
+ * the start of the backward, 80 % of the bytes; the deferred weight-gradient slice reduction at its end) store every
+ * value as one 8-byte {value, tag} word straight into slot [rank] of every peer's buffer over NVLink, and a final kernel
+ * polls the world's words element by element and sums them in rank order (deterministic, identical on every rank).
+ * Replaces DDP's bucketed all-reduce of these parameters (engine/trainer.py:223) for the stand-alone pipeline. */
+#define DD_MAX_PEERS 8
+typedef struct dd_peer_exchange {
+    int rank, world;
+    void* buf[DD_MAX_PEERS];
+} dd_peer_exchange;
+size_t dd_exchange_bytes(void);
+int dd_predictor_bwd_allreduce(const float* r, const dd_predictor_tensors* w, const float* acts,
+                               const float* dfeat, const dd_predictor_tensors* grads, int B, void* ws,
+                               size_t ws_bytes, const dd_peer_exchange* px, void* stream);
+
 /* ---- a6..a12: regressors + DeDark -> WB -> Gamma -> Contrast -> USM, one fused pass -------------
  * Replaces the body of lowlight_recovery.forward after the predictor (llie.py:34-40,49-52;
  * filtersB.py:32-37,144-259,289-303; util_filters.py:270-273,295-304,316-317).

@@ -60,3 +60,21 @@ def test_shape_errors_mirror_reference_without_touching_the_gpu():
     with pytest.raises(RuntimeError, match="workspace"):
         _lib.check(_lib.lib.dd_recovery_bwd(one, None, None, one, one, one, None, 1, 64, 64, one, 8, None))
     assert b"workspace" in _lib.lib.dd_last_error()
+
+
+def test_peer_exchange_descriptor_is_validated_without_touching_the_gpu():
+    from dedark_yolo_b200 import _lib
+    assert _lib.lib.dd_exchange_bytes() == 256 + 2 * 8 * 164944 * 8  # header + [2 parities][8 peers] slots of {value, tag} words
+    one = C.c_void_p(16)  # never dereferenced: validation fails first
+    t = _lib.PredictorTensors.from_tensors([type("T", (), {"data_ptr": lambda self: 16})() for _ in range(14)])
+    bad = _lib.PeerExchange()
+    bad.rank, bad.world = 3, 2  # rank outside the world
+    bad.buf[0], bad.buf[1] = 16, 16
+    with pytest.raises(ValueError):
+        _lib.check(_lib.lib.dd_predictor_bwd_allreduce(one, C.byref(t), one, one, C.byref(t), 1, one, 1 << 30, C.byref(bad), None))
+    hole = _lib.PeerExchange.from_pointers(0, [16, 16])
+    hole.buf[1] = None  # a peer buffer that was never mapped
+    with pytest.raises(ValueError):
+        _lib.check(_lib.lib.dd_predictor_bwd_allreduce(one, C.byref(t), one, one, C.byref(t), 1, one, 1 << 30, C.byref(hole), None))
+    with pytest.raises(ValueError):
+        _lib.PeerExchange.from_pointers(0, list(range(1, 10)))  # more than 8 peers

@@ -342,3 +342,49 @@ def test_predictor_is_bit_reproducible(ops):
     assert torch.equal(runs[0][0], runs[1][0])
     for a, b in zip(runs[0][1], runs[1][1]):
         assert torch.equal(a, b)
+
+
+# ---- 8(e): predictor backward fused with the gradient exchange over peer memory ------------------------------------------
+def test_fused_gradient_exchange_two_virtual_ranks(ops):
+    """dd_predictor_bwd_allreduce with world = 2 emulated on ONE GPU (two exchange buffers, two streams): both ranks end with
+    the bitwise identical sum of the two per-rank gradients (slots are added in rank order), for three consecutive steps
+    (the slot parity alternates), and it equals the separately computed gradients added on the host side."""
+    import ctypes as C
+    from dedark_yolo_b200 import _lib
+    from dedark_yolo_b200._lib import PeerExchange, PredictorTensors, check, lib
+    dev = torch.device("cuda")
+    w = golden_weights(1.0)
+    params = cuda_params(w)
+    nbytes = int(lib.dd_exchange_bytes())
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    pxs = [PeerExchange.from_pointers(k, [b.data_ptr() for b in bufs]) for k in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    B = 3
+    ws_bytes = _lib.workspace_bytes(_lib.WS_PREDICTOR_BWD, B)
+    gen = torch.Generator().manual_seed(77)
+    for step in range(3):
+        rs = [torch.rand(B, 3, 256, 256, generator=gen).cuda() for _ in range(2)]
+        dfs = [torch.randn(B, 15, generator=gen).cuda() for _ in range(2)]
+        fwd = [ops.predictor_forward(rs[k], params) for k in range(2)]
+        ref = [ops.predictor_backward(rs[k], params, fwd[k][1], dfs[k])[0] for k in range(2)]
+        expect = [a + b for a, b in zip(ref[0], ref[1])]
+        outs, keep = [], []
+        torch.cuda.synchronize()
+        for k in range(2):
+            flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+            grads, off = [], 0
+            for p in params:
+                grads.append(flat[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            wt, gt = PredictorTensors.from_tensors(params), PredictorTensors.from_tensors(grads)
+            keep += [ws, wt, gt]
+            with torch.cuda.stream(streams[k]):
+                check(lib.dd_predictor_bwd_allreduce(C.c_void_p(rs[k].data_ptr()), C.byref(wt), C.c_void_p(fwd[k][1].data_ptr()),
+                                                     C.c_void_p(dfs[k].data_ptr()), C.byref(gt), B, C.c_void_p(ws.data_ptr()), ws_bytes,
+                                                     C.byref(pxs[k]), streams[k].cuda_stream))
+            outs.append(grads)
+        torch.cuda.synchronize()
+        for i, key in enumerate(O.STATE_KEYS):
+            assert torch.equal(outs[0][i], outs[1][i]), f"step {step}: ranks disagree on {key}"
+            assert torch.equal(outs[0][i], expect[i]), f"step {step}: {key} is not the sum of the per-rank gradients"
