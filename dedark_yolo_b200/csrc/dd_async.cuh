@@ -48,10 +48,10 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-// ---- host: tensor map of a contiguous [planes][H][W] fp32 tensor with a [1][box_h][box_w] box ---------------------
+// ---- host: tensor map of a contiguous [planes][H][W] fp32 tensor with a [box_d][box_h][box_w] box ---------------------
 // Returns false when the driver entry point is missing or the shape does not meet the TMA alignment rules
 // (base and row pitch multiples of 16 bytes).
-inline bool make_tensor_map_3d(CUtensorMap* map, const float* base, int planes, int H, int W, int box_w, int box_h) {
+inline bool make_tensor_map_3d(CUtensorMap* map, const float* base, int planes, int H, int W, int box_w, int box_h, int box_d = 1) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -65,7 +65,7 @@ inline bool make_tensor_map_3d(CUtensorMap* map, const float* base, int planes, 
     if (!encode || (reinterpret_cast<uintptr_t>(base) & 15) || (W & 3) || box_w > 256 || box_h > 256 || ((box_w * 4) & 15)) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_d};
     const cuuint32_t estr[3] = {1, 1, 1};
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -96,7 +97,20 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    // DEDARK_SYNC=1 (debugging aid): synchronise after every launch and name the first one that fails
+    static const bool dbg = [] { const char* v = getenv("DEDARK_SYNC"); return v && v[0] == '1'; }();
+    if (dbg) {
+        static int seq = 0;
+        ++seq;
+        const cudaError_t se = cudaDeviceSynchronize();
+        if (e != cudaSuccess || se != cudaSuccess)
+            fprintf(stderr, "[dedark] launch #%d of this call site (grid %u, block %u, smem %zu) failed: %s / %s\n", seq, grid.x, block.x, smem,
+                    cudaGetErrorString(e), cudaGetErrorString(se));
+        else
+            fprintf(stderr, "[dedark] ok: grid %u block %u smem %zu\n", grid.x, block.x, smem);
+    }
+    return e;
 }
 
 // same, as thread-block clusters of `cluster_x` CTAs (distributed shared memory between the CTAs of a cluster)

@@ -1,116 +1,79 @@
-// dd_conv_tiled.cuh -- shared-memory-tiled CUDA-core kernels of the predictor's FIRST layer (3 -> 16 channels, K = 27:
-// too thin for the tensor cores, nn/modules/common.py:9-23): forward (+bias +LeakyReLU) and weight/bias gradient.  fp32.
+// dd_conv_tiled.cuh -- CUDA-core kernels of the predictor's FIRST layer (3 -> 16 channels, 3x3 / stride 2 / pad 1, K = 27:
+// too thin for the tensor cores, nn/modules/common.py:9-23): forward (+bias +LeakyReLU) and weight/bias gradient, fp32.
 // (conv2..conv5 live in dd_conv_tc.cuh.)
 //
-// Common idea: a CTA owns one spatial tile of one image; its operands are staged cooperatively in shared memory with
-// all global loads in flight at once (the first version walked ~100 dependent L2 round trips per thread), and every
-// thread keeps a register tile so that one shared-memory operand feeds 4..8 FMAs.  Input tiles are stored with the
-// image columns split by parity ([even | odd] halves per row): a stride-2 convolution then reads consecutive
-// addresses across the lanes of a warp (no bank conflicts).
+// Both kernels are persistent (CTA c walks the tiles c, c + grid, ...) and their tiles arrive by TMA: one
+// cp.async.bulk.tensor box per operand and tile, issued by one thread into one of two shared-memory buffers and counted
+// on an mbarrier.  The box of the input starts at row 2*oh0 - 1 and column 2*ow0 - 4 (the innermost box origin must be
+// 16-byte aligned -- an origin of -1 raises "illegal instruction", profiles/microbench/tma_probe.cu -- so the box carries
+// three spare columns), and the convolution's zero padding is the copy engine's out-of-bounds fill: no thread spends an
+// instruction on staging (the previous versions spent a third of theirs on 4-byte cp.async address arithmetic).
+// Window access: lane = output column; taps kw = 1, 2 come from one aligned 64-bit shared load, kw = 0 from the
+// previous lane (shuffle).
 #pragma once
+#include "dd_async.cuh"
 #include "dd_common.cuh"
 
 namespace dd {
 
-// staged input tile: rows 2*oh0-1 .. 2*(oh0+TH-1)+1, columns 2*ow0-1 .. 2*(ow0+TW-1)+1 (zero outside the image).
-// local column lc (0 .. 2TW) has image column 2*ow0 - 1 + lc: even lc -> odd image column, slot TW + lc/2;
-// odd lc -> even image column, slot (lc-1)/2.  So for output column ow0 + c:  tap kw=0 -> odd slot TW + c,
-// kw=1 -> even slot c, kw=2 -> odd slot TW + c + 1.
-template <int TH, int TW>
-struct InTile {
-    static constexpr int ROWS = 2 * TH + 1;
-    static constexpr int COLS = 2 * TW + 1;
-    static constexpr int PITCH = 2 * TW + 2;
-    static constexpr int PLANE = ROWS * PITCH + 1;  // odd plane stride: lanes that differ in channel hit different banks
-};
+constexpr int kC1In = 3, kC1Out = 16, kC1HIn = 256, kC1HOut = 128;
+constexpr int kC1TW = 32;             // output columns per tile = lanes
+constexpr int kC1BoxW = 72;           // input columns 2*ow0 - 4 .. 2*ow0 + 67 (3 spare on the left for alignment, 65 live, 4 pad)
+__host__ __device__ constexpr int c1_tile_bytes(int th) { return ((kC1In * (2 * th + 1) * kC1BoxW * 4) + 127) / 128 * 128; }
 
-// 4-byte async global->shared copy (LDGSTS), zero-fill when !valid.  All staging below is asynchronous: every
-// chunk of every operand is requested up front (one commit group per chunk) and consumed as it lands.
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src, bool valid) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cp_wait_dyn(int pending) {  // pending in 0..3 (compile-time after unrolling)
-    switch (pending) {
-        case 0: cp_wait<0>(); break;
-        case 1: cp_wait<1>(); break;
-        case 2: cp_wait<2>(); break;
-        default: cp_wait<3>(); break;
-    }
-}
-
-template <int TH, int TW, int NCH, int HIN>
-__device__ __forceinline__ void stage_input_tile_async(float* __restrict__ s, const float* __restrict__ in_img, int c0,
-                                                       int oh0, int ow0) {
-    using T = InTile<TH, TW>;
-    for (int idx = threadIdx.x; idx < NCH * T::ROWS * T::COLS; idx += blockDim.x) {
-        const int lc = idx % T::COLS, t = idx / T::COLS, lr = t % T::ROWS, ci = t / T::ROWS;
-        const int gy = 2 * oh0 - 1 + lr, gx = 2 * ow0 - 1 + lc;
-        const bool ok = gy >= 0 && gy < HIN && gx >= 0 && gx < HIN;
-        cp_async4(s + ci * T::PLANE + lr * T::PITCH + ((lc & 1) ? (lc >> 1) : TW + (lc >> 1)),
-                  ok ? in_img + ((size_t)(c0 + ci) * HIN + gy) * HIN + gx : in_img, ok);
-    }
+// the three taps of one window row for output column `lane`
+__device__ __forceinline__ void c1_window_row(const float* __restrict__ row, int lane, float& a, float& b, float& c) {
+    const float2 bc = *reinterpret_cast<const float2*>(row + 2 * lane + 4);  // image columns 2*ow, 2*ow + 1
+    b = bc.x;
+    c = bc.y;
+    a = __shfl_up_sync(0xffffffffu, bc.y, 1);                               // image column 2*ow - 1
+    if (lane == 0) a = row[3];
 }
 
 // -------------------------------------------------------------------------------------------------------------
-// forward: thread = PY output rows x 1 output column x 8 output channels; CTA = TH x TW outputs x all COUT channels
+// forward: tile = 16 x 32 outputs x all 16 channels; thread = 4 rows x 1 column x 8 channels (256 threads)
 // -------------------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, int HIN, int TH, int TW, int CICH, int PY>
-__device__ __forceinline__ void conv_fwd_tiled_body(const int bid, const float* __restrict__ in, const float* __restrict__ w,
-                                                    const float* __restrict__ bias, float* __restrict__ out) {
-    using T = InTile<TH, TW>;
-    constexpr int HO = HIN / 2, TX = HO / TW, TY = HO / TH, NCHUNK = CIN / CICH;
-    constexpr int IN_F = (CICH * T::PLANE + 3) & ~3, W_F = CICH * 9 * COUT, CH_F = IN_F + W_F;  // floats per chunk
-    extern __shared__ __align__(16) float smem_f[];
-    const int tile = bid % (TX * TY), b = bid / (TX * TY);
-    const int oh0 = (tile / TX) * TH, ow0 = (tile % TX) * TW;
-    const int col = threadIdx.x % TW, rg = (threadIdx.x / TW) % (TH / PY), cog = threadIdx.x / (TW * (TH / PY));
-    const float* in_img = in + (size_t)b * CIN * HIN * HIN;
+constexpr int kC1FwdTH = 16, kC1FwdPY = 4;
+constexpr size_t conv1_fwd_smem() { return (size_t)2 * c1_tile_bytes(kC1FwdTH) + (size_t)kC1In * 9 * kC1Out * 4; }
 
+__device__ __forceinline__ void conv1_fwd_body(const int cta, const int nctas, const CUtensorMap* rmap, const float* __restrict__ w,
+                                               const float* __restrict__ bias, float* __restrict__ out, int ntiles,
+                                               unsigned char* smem, uint64_t* full) {
+    constexpr int TH = kC1FwdTH, PY = kC1FwdPY, TX = kC1HOut / kC1TW, TY = kC1HOut / TH, ROWS = 2 * TH + 1;
+    constexpr int TILE_B = c1_tile_bytes(TH);
+    float* s_w = reinterpret_cast<float*>(smem + 2 * TILE_B);  // [ci*9 + k][co]
+    const int tid = threadIdx.x, lane = tid & 31, rg = (tid >> 5) & 3, cog = tid >> 7;
+    for (int i = tid; i < kC1In * 9 * kC1Out; i += 256) s_w[i] = __ldg(w + (i % kC1Out) * (kC1In * 9) + i / kC1Out);
+    auto issue = [&](int it) {
+        const int tl = cta + it * nctas, tile = tl % (TX * TY), b = tl / (TX * TY);
+        const int oh0 = (tile / TX) * TH, ow0 = (tile % TX) * kC1TW;
+        mbar_arrive_expect_tx(&full[it & 1], kC1In * ROWS * kC1BoxW * 4);
+        tma_load_3d(smem + (it & 1) * TILE_B, rmap, 2 * ow0 - 4, 2 * oh0 - 1, b * kC1In, &full[it & 1]);
+    };
+    const int my = cta < ntiles ? (ntiles - 1 - cta) / nctas + 1 : 0;
+    if (tid == 0 && my > 0) issue(0);
+    __syncthreads();  // weights
+    for (int it = 0; it < my; ++it) {
+        if (tid == 0 && it + 1 < my) issue(it + 1);  // its buffer was released by the barrier that ended iteration it - 1
+        mbar_wait(&full[it & 1], (uint32_t)(it >> 1) & 1u);
+        const float* s_in = reinterpret_cast<const float*>(smem + (it & 1) * TILE_B);
+        float acc[PY][8];
 #pragma unroll
-    for (int ch = 0; ch < NCHUNK; ++ch) {
-        float* s_in = smem_f + ch * CH_F;
-        float* s_w = s_in + IN_F;
-        stage_input_tile_async<TH, TW, CICH, HIN>(s_in, in_img, ch * CICH, oh0, ow0);
-        for (int idx = threadIdx.x; idx < W_F; idx += blockDim.x) {  // s_w[ci][k][co], co fastest
-            const int co = idx % COUT, t = idx / COUT, k = t % 9, ci = t / 9;
-            cp_async4(s_w + idx, w + ((size_t)co * CIN + ch * CICH + ci) * 9 + k, true);
-        }
-        cp_commit();
-    }
-
-    float acc[PY][8];
+        for (int j = 0; j < PY; ++j)
 #pragma unroll
-    for (int j = 0; j < PY; ++j)
+            for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
-
-#pragma unroll
-    for (int ch = 0; ch < NCHUNK; ++ch) {
-        const float* s_in = smem_f + ch * CH_F;
-        const float* s_w = s_in + IN_F;
-        cp_wait_dyn(NCHUNK - 1 - ch);
-        __syncthreads();
-#pragma unroll 1
-        for (int ci = 0; ci < CICH; ++ci) {
-            const float* sp = s_in + ci * T::PLANE + (2 * PY * rg) * T::PITCH;
+        for (int ci = 0; ci < kC1In; ++ci) {
+            const float* sp = s_in + (ci * ROWS + 2 * PY * rg) * kC1BoxW;
             float v[2 * PY + 1][3];
 #pragma unroll
-            for (int lr = 0; lr < 2 * PY + 1; ++lr) {
-                v[lr][0] = sp[lr * T::PITCH + TW + col];
-                v[lr][1] = sp[lr * T::PITCH + col];
-                v[lr][2] = sp[lr * T::PITCH + TW + col + 1];
-            }
+            for (int lr = 0; lr < 2 * PY + 1; ++lr) c1_window_row(sp + lr * kC1BoxW, lane, v[lr][0], v[lr][1], v[lr][2]);
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
-                    const float4 wa = *reinterpret_cast<const float4*>(s_w + (ci * 9 + kh * 3 + kw) * COUT + 8 * cog);
-                    const float4 wb = *reinterpret_cast<const float4*>(s_w + (ci * 9 + kh * 3 + kw) * COUT + 8 * cog + 4);
+                    const float4 wa = *reinterpret_cast<const float4*>(s_w + (ci * 9 + kh * 3 + kw) * kC1Out + 8 * cog);
+                    const float4 wb = *reinterpret_cast<const float4*>(s_w + (ci * 9 + kh * 3 + kw) * kC1Out + 8 * cog + 4);
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
                         const float a = v[2 * j + kh][kw];
@@ -121,61 +84,54 @@ __device__ __forceinline__ void conv_fwd_tiled_body(const int bid, const float* 
                     }
                 }
         }
-    }
+        const int tl = cta + it * nctas, tile = tl % (TX * TY), b = tl / (TX * TY);
+        const int oh0 = (tile / TX) * TH, ow0 = (tile % TX) * kC1TW;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int co = 8 * cog + c;
-        const float bv = __ldg(bias + co);
-        float* o = out + (((size_t)b * COUT + co) * HO + oh0 + PY * rg) * HO + ow0 + col;
+        for (int c = 0; c < 8; ++c) {
+            const int co = 8 * cog + c;
+            const float bv = __ldg(bias + co);
+            float* o = out + (((size_t)b * kC1Out + co) * kC1HOut + oh0 + PY * rg) * kC1HOut + ow0 + lane;
 #pragma unroll
-        for (int j = 0; j < PY; ++j) o[(size_t)j * HO] = leaky(acc[j][c] + bv);
-    }
-}
-
-
-template <int CIN, int COUT, int TH, int TW, int CICH>
-constexpr size_t conv_fwd_smem() {
-    return (size_t)(CIN / CICH) * (((CICH * InTile<TH, TW>::PLANE + 3) & ~3) + CICH * 9 * COUT) * sizeof(float);
-}
-
-// -------------------------------------------------------------------------------------------------------------
-// weight + bias gradient of the first layer (CIN = 3), persistent: CTA c walks the tiles c, c + grid, ... (a tile =
-// TH x TW output pixels of one image), keeping its 4 x 27 (+4 bias) sums per thread in registers across tiles, and
-// writes ONE slice [COUT*27 + COUT] at the end (summed in index order by the deferred reduction).
-//   warp = (group of 4 output channels, half of the tile's rows), lane = output column: per pixel 27 window loads +
-//   4 cotangent loads feed 112 FMAs.  Input and cotangent tiles are double-buffered with cp.async.
-// -------------------------------------------------------------------------------------------------------------
-template <int COUT, int TH, int TW>
-constexpr size_t conv_wgrad_c3_smem() {
-    return (size_t)2 * (((3 * InTile<TH, TW>::PLANE + 3) & ~3) + COUT * TH * TW) * sizeof(float);
-}
-
-template <int COUT, int HIN, int TH, int TW>
-__global__ void __launch_bounds__(256, 1)
-conv_wgrad_c3_kernel(const float* __restrict__ in, const float* __restrict__ dpre, float* __restrict__ partial, int ntiles) {
-    pdl_begin();
-    constexpr int CIN = 3;
-    using T = InTile<TH, TW>;
-    constexpr int HO = HIN / 2, TX = HO / TW, TY = HO / TH, NW = COUT * CIN * 9;
-    constexpr int IN_F = (CIN * T::PLANE + 3) & ~3, D_F = COUT * TH * TW, BUF = IN_F + D_F;
-    static_assert(COUT == 16 && TW == 32 && TH == 8, "warp mapping: 4 channel groups x 2 row halves, lane = column");
-    extern __shared__ __align__(16) float smem_w[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, cog = wid & 3, half = wid >> 2;
-
-    auto stage = [&](int buf, int tl) {
-        const int tile = tl % (TX * TY), b = tl / (TX * TY);
-        const int oh0 = (tile / TX) * TH, ow0 = (tile % TX) * TW;
-        float* s_in = smem_w + buf * BUF;
-        float* s_d = s_in + IN_F;
-        stage_input_tile_async<TH, TW, CIN, HIN>(s_in, in + (size_t)b * CIN * HIN * HIN, 0, oh0, ow0);
-        for (int idx = threadIdx.x; idx < D_F / 4; idx += blockDim.x) {  // [co][row][TW] rows of 32 contiguous floats
-            const int c4 = idx % (TW / 4), t = idx / (TW / 4), lr = t % TH, co = t / TH;
-            const unsigned d = (unsigned)__cvta_generic_to_shared(s_d + 4 * idx);
-            const float* src = dpre + (((size_t)b * COUT + co) * HO + oh0 + lr) * HO + ow0 + 4 * c4;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+            for (int j = 0; j < PY; ++j) o[(size_t)j * kC1HOut] = leaky(acc[j][c] + bv);
         }
-        cp_commit();
+        __syncthreads();  // everyone is done with this buffer before the next-but-one tile lands in it
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// weight + bias gradient: tile = 8 x 32 output pixels; every thread keeps 4 x 27 (+4 bias) sums in registers across all of
+// its CTA's tiles; ONE slice [16*27 + 16] per CTA at the end (summed in index order by the deferred reduction).
+//   warp = (group of 4 output channels, half of the tile's rows), lane = output column.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int kC1WgTH = 8;
+constexpr int kC1DTileB = kC1Out * kC1WgTH * kC1TW * 4;  // 16 KB cotangent tile [co][row][32]
+constexpr size_t conv1_wgrad_smem() { return (size_t)2 * (c1_tile_bytes(kC1WgTH) + kC1DTileB); }
+
+__global__ void __launch_bounds__(256, 1)
+conv1_wgrad_kernel(const __grid_constant__ CUtensorMap rmap, const __grid_constant__ CUtensorMap dmap, float* __restrict__ partial,
+                   int ntiles) {
+    pdl_begin();
+    constexpr int TH = kC1WgTH, TX = kC1HOut / kC1TW, TY = kC1HOut / TH, ROWS = 2 * TH + 1, NW = kC1Out * kC1In * 9;
+    constexpr int IN_B = c1_tile_bytes(TH), BUF_B = IN_B + kC1DTileB;
+    extern __shared__ __align__(128) unsigned char smem_c1[];
+    __shared__ __align__(8) uint64_t full[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, cog = wid & 3, half = wid >> 2;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int it) {
+        const int tl = blockIdx.x + it * gridDim.x, tile = tl % (TX * TY), b = tl / (TX * TY);
+        const int oh0 = (tile / TX) * TH, ow0 = (tile % TX) * kC1TW;
+        unsigned char* buf = smem_c1 + (it & 1) * BUF_B;
+        mbar_arrive_expect_tx(&full[it & 1], kC1In * ROWS * kC1BoxW * 4 + kC1DTileB);
+        tma_load_3d(buf, &rmap, 2 * ow0 - 4, 2 * oh0 - 1, b * kC1In, &full[it & 1]);
+        tma_load_3d(buf + IN_B, &dmap, ow0, oh0, b * kC1Out, &full[it & 1]);
     };
+    const int my = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (tid == 0 && my > 0) issue(0);
 
     float acc[4][27], accb[4];
 #pragma unroll
@@ -184,41 +140,33 @@ conv_wgrad_c3_kernel(const float* __restrict__ in, const float* __restrict__ dpr
 #pragma unroll
         for (int k = 0; k < 27; ++k) acc[t][k] = 0.f;
     }
-    int buf = 0;
-    if ((int)blockIdx.x < ntiles) stage(0, blockIdx.x);
-    for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
-        const bool more = tl + (int)gridDim.x < ntiles;
-        if (more) stage(buf ^ 1, tl + gridDim.x);
-        if (more) cp_wait<1>(); else cp_wait<0>();
-        __syncthreads();
-        const float* s_in = smem_w + buf * BUF;
-        const float* s_d = s_in + IN_F;
-#pragma unroll 1
+    for (int it = 0; it < my; ++it) {
+        if (tid == 0 && it + 1 < my) issue(it + 1);
+        mbar_wait(&full[it & 1], (uint32_t)(it >> 1) & 1u);
+        const float* s_in = reinterpret_cast<const float*>(smem_c1 + (it & 1) * BUF_B);
+        const float* s_d = reinterpret_cast<const float*>(smem_c1 + (it & 1) * BUF_B + IN_B);
+#pragma unroll 4
         for (int j = 0; j < TH / 2; ++j) {
             const int oh = half * (TH / 2) + j;
             float v[27];
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                    const float* rp = s_in + ci * T::PLANE + (2 * oh + kh) * T::PITCH;
-                    v[ci * 9 + kh * 3 + 0] = rp[TW + lane];
-                    v[ci * 9 + kh * 3 + 1] = rp[lane];
-                    v[ci * 9 + kh * 3 + 2] = rp[TW + lane + 1];
-                }
+                for (int kh = 0; kh < 3; ++kh)
+                    c1_window_row(s_in + (ci * ROWS + 2 * oh + kh) * kC1BoxW, lane, v[ci * 9 + kh * 3], v[ci * 9 + kh * 3 + 1],
+                                  v[ci * 9 + kh * 3 + 2]);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const float d = s_d[((cog * 4 + t) * TH + oh) * TW + lane];
+                const float d = s_d[((cog * 4 + t) * TH + oh) * kC1TW + lane];
                 accb[t] += d;
 #pragma unroll
                 for (int k = 0; k < 27; ++k) acc[t][k] = fmaf(d, v[k], acc[t][k]);
             }
         }
         __syncthreads();  // everyone is done with this buffer before it is refilled
-        buf ^= 1;
     }
     // lanes -> one value per warp (fixed order), the two row halves through shared memory
-    float* s_red = smem_w;  // [4 channel groups][112]
+    float* s_red = reinterpret_cast<float*>(smem_c1);  // [4 channel groups][112]
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
 #pragma unroll
@@ -233,13 +181,13 @@ conv_wgrad_c3_kernel(const float* __restrict__ in, const float* __restrict__ dpr
     }
     __syncthreads();
     if (half == 0 && lane == 0) {
-        float* out = partial + (size_t)blockIdx.x * (NW + COUT);
+        float* o = partial + (size_t)blockIdx.x * (NW + kC1Out);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int co = cog * 4 + t;
 #pragma unroll
-            for (int k = 0; k < 27; ++k) out[co * 27 + k] = acc[t][k] + s_red[cog * 112 + t * 28 + k];  // (co*3 + ci)*9 + kk, k = ci*9 + kk
-            out[NW + co] = accb[t] + s_red[cog * 112 + t * 28 + 27];
+            for (int k = 0; k < 27; ++k) o[co * 27 + k] = acc[t][k] + s_red[cog * 112 + t * 28 + k];  // (co*3 + ci)*9 + kk, k = ci*9 + kk
+            o[NW + co] = accb[t] + s_red[cog * 112 + t * 28 + 27];
         }
     }
 }

@@ -288,26 +288,40 @@ static void launch_conv_dgrad(const float* dpre, const float* w, const float* ac
     count_launch();
 }
 
-// ---- conv1: shared-memory-tiled CUDA-core kernel (dd_conv_tiled.cuh).  The same launch carries, in extra CTAs, the
-// preparation of the tensor-core weights of conv2..conv5 (independent of conv1; one launch less on the critical path).
-template <int CIN, int COUT, int HIN, int TH, int TW, int CICH, int PY>
+// ---- conv1: persistent CUDA-core kernel with TMA-staged tiles (dd_conv_tiled.cuh).  The same launch carries, in extra
+// CTAs, the preparation of the tensor-core weights of conv2..conv5 (independent of conv1; one launch less on the
+// critical path).
 __global__ void __launch_bounds__(256)
-conv1_fwd_prep_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                      float* __restrict__ out, int n_conv, const tc::PrepJobs jobs) {
-    static_assert(TW * (TH / PY) * (COUT / 8) == 256, "block size");
+conv1_fwd_prep_kernel(const __grid_constant__ CUtensorMap rmap, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ out, int ntiles, int n_conv, const tc::PrepJobs jobs) {
     pdl_begin();
-    if ((int)blockIdx.x < n_conv) conv_fwd_tiled_body<CIN, COUT, HIN, TH, TW, CICH, PY>(blockIdx.x, in, w, bias, out);
-    else tc::prep_weights_body(jobs, (int)blockIdx.x - n_conv);
+    extern __shared__ __align__(128) unsigned char smem_c1f[];
+    __shared__ __align__(8) uint64_t full[2];
+    if ((int)blockIdx.x < n_conv) {
+        if (threadIdx.x == 0) {
+            mbar_init(&full[0], 1);
+            mbar_init(&full[1], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        conv1_fwd_body(blockIdx.x, n_conv, &rmap, w, bias, out, ntiles, smem_c1f, full);
+    } else {
+        tc::prep_weights_body(jobs, (int)blockIdx.x - n_conv);
+    }
 }
 
-template <int CIN, int COUT, int HIN, int TH, int TW, int CICH, int PY>
+static int sm_count();
 static int launch_conv1_prep(const float* in, const float* w, const float* b, float* out, const tc::PrepJobs& jobs, int B, cudaStream_t st) {
-    constexpr int HO = HIN / 2;
-    constexpr size_t smem = conv_fwd_smem<CIN, COUT, TH, TW, CICH>();
-    auto kern = conv1_fwd_prep_kernel<CIN, COUT, HIN, TH, TW, CICH, PY>;
-    DD_ENSURE_SMEM(kern, smem, "conv1_fwd_prep_kernel");
-    const int n_conv = B * (HO / TH) * (HO / TW);
-    launch_pdl(kern, dim3(n_conv + 4 * tc::kPrepBlocksPerJob), dim3(256), smem, st, in, w, b, out, n_conv, jobs);
+    constexpr size_t smem = conv1_fwd_smem();
+    DD_ENSURE_SMEM(conv1_fwd_prep_kernel, smem, "conv1_fwd_prep_kernel");
+    CUtensorMap rmap;
+    if (!make_tensor_map_3d(&rmap, in, B * kC1In, kC1HIn, kC1HIn, kC1BoxW, 2 * kC1FwdTH + 1, kC1In)) {
+        set_error("dd_predictor_fwd: cannot encode the TMA tensor map of the resized batch (r must be 16-byte aligned)");
+        return DD_ERR_CUDA;
+    }
+    const int ntiles = B * (kC1HOut / kC1FwdTH) * (kC1HOut / kC1TW);
+    const int n_conv = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
+    launch_pdl(conv1_fwd_prep_kernel, dim3(n_conv + 4 * tc::kPrepBlocksPerJob), dim3(256), smem, st, rmap, w, b, out, ntiles, n_conv, jobs);
     count_launch();
     return DD_OK;
 }
@@ -399,7 +413,7 @@ extern "C" int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, f
         for (int l = 1; l < 5; ++l)
             jobs.j[l - 1] = tc::PrepJob{w->conv_w[l], prep + pred_prep_offset(l), prep + pred_prep_offset(l) + pred_prep_fwd_elems(l),
                                         pred_cin(l), pred_cout(l)};
-        if (int e = launch_conv1_prep<3, 16, 256, 16, 32, 3, 4>(r, w->conv_w[0], w->conv_b[0], a[0], jobs, B, st)) return e;
+        if (int e = launch_conv1_prep(r, w->conv_w[0], w->conv_b[0], a[0], jobs, B, st)) return e;
     }
     if (int e = launch_tc_fwd<16, 32, 128>(a[0], prep + pred_prep_offset(1), w->conv_b[1], a[1], B, st)) return e;
     if (int e = launch_tc_fwd<32, 32, 64>(a[1], prep + pred_prep_offset(2), w->conv_b[2], a[2], B, st)) return e;
@@ -452,11 +466,16 @@ static int predictor_bwd_impl(const float* r, const dd_predictor_tensors* w, con
     if (int e = launch_tc_bwd<32, 32, 32>(a[2], d[3], dg(3), a[2], pl[3], d[2], &nsl[3], B, st)) return e;
     if (int e = launch_tc_bwd<32, 32, 64>(a[1], d[2], dg(2), a[1], pl[2], d[1], &nsl[2], B, st)) return e;
     if (int e = launch_tc_bwd<16, 32, 128>(a[0], d[1], dg(1), a[0], pl[1], d[0], &nsl[1], B, st)) return e;
-    {   // first layer (CIN = 3): persistent CUDA-core kernel
-        constexpr size_t smem = conv_wgrad_c3_smem<16, 8, 32>();
-        auto kern = conv_wgrad_c3_kernel<16, 256, 8, 32>;
-        DD_ENSURE_SMEM(kern, smem, "conv_wgrad_c3_kernel");
-        launch_pdl(kern, dim3(nsl[0]), dim3(256), smem, st, r, (const float*)d[0], pl[0], B * kWgradC1Slices);
+    {   // first layer (CIN = 3): persistent CUDA-core kernel, tiles of r and of d(conv1) by TMA
+        constexpr size_t smem = conv1_wgrad_smem();
+        DD_ENSURE_SMEM(conv1_wgrad_kernel, smem, "conv1_wgrad_kernel");
+        CUtensorMap rmap, dmap;
+        if (!make_tensor_map_3d(&rmap, r, B * kC1In, kC1HIn, kC1HIn, kC1BoxW, 2 * kC1WgTH + 1, kC1In) ||
+            !make_tensor_map_3d(&dmap, d[0], B * kC1Out, kC1HOut, kC1HOut, kC1TW, kC1WgTH, kC1Out)) {
+            set_error("dd_predictor_bwd: cannot encode the TMA tensor maps (r and the workspace must be 16-byte aligned)");
+            return DD_ERR_CUDA;
+        }
+        launch_pdl(conv1_wgrad_kernel, dim3(nsl[0]), dim3(256), smem, st, rmap, dmap, pl[0], B * kWgradC1Slices);
     }
     {
         tc::ReduceJobs jobs;
