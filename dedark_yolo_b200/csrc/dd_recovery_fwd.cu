@@ -18,6 +18,9 @@
 // The vertical halo (24 rows) is paid once per CTA range.  The blur is FMA-pipe bound (50 FMA per pixel ~ 28 us per
 // 16x3x640^2 at the measured 35 TFMA/s); FFMA2 halves its issue slots so loads, MUFU and index arithmetic issue in the
 // shadow of the FMA pipe.
+#include <cstring>
+
+#include "dd_async.cuh"
 #include "dd_recovery.cuh"
 
 namespace dd {
@@ -26,17 +29,31 @@ constexpr int kPairs = 32;              // XS2 ring depth in row pairs (64 rows)
 constexpr int kXP2 = 308;               // XS2 pitch (floats per row pair): 2*152 + 4, (kXP2/4) odd -> conflict-free LDS.128
 constexpr int kHRows = kHRing + 24;     // HS rows: 64-row ring + the first 24 rows mirrored behind it
 constexpr int kStage2 = (16 * kXW4 + kThreads - 1) / kThreads;  // (row pair, float4 column) items per thread per block (3)
+constexpr int kXRP = 160;               // pitch (floats) of the TMA staging rows: 640 B, a multiple of the 128 B TMA alignment
 
-template <bool HAS_ICA, bool FAST, bool ALIGNED>
+// TMA: the raw x rows of every row-block arrive by cp.async.bulk.tensor, one 156-column row box per (reflected) image row,
+// issued by the lanes of warp 0 one block ahead into a staging tile and counted on an mbarrier: no register prefetch, no
+// per-thread address arithmetic, and the stage phase never waits for DRAM.
+template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2)
-recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
-                    const float* __restrict__ feat, float* __restrict__ y, int B, int H, int W) {
+recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ x, const float* __restrict__ A,
+                    const float* __restrict__ IcA, const float* __restrict__ feat, float* __restrict__ y, int B, int H, int W) {
     pdl_begin();
-    extern __shared__ __align__(16) float smem[];
-    float* XS2 = smem;
+    extern __shared__ __align__(128) float smem[];
+    float* XR = smem;                                  // [32 rows][kXRP] raw x of the block being staged (TMA only)
+    float* XS2 = smem + (TMA ? kRB * kXRP : 0);
     float* HS = XS2 + kPairs * kXP2;
     float* MS = HS + kHRows * kHP;  // per virtual row: m = (1-c) + c*q
     __shared__ ImgParams sp;
+    __shared__ __align__(8) uint64_t tma_bar;
+    uint32_t tma_phase = 0;
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&tma_bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
 
     const int tid = threadIdx.x;
     const Sched sc = make_sched(B, H, W);
@@ -87,6 +104,18 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
         // item (k) of a thread: row pair rp (2 rows) x float4 column c4; fixed across blocks
         float4 pre[kStage2][2], prei[kStage2][2];
         auto stage = [&](int n) {
+            if (TMA) {
+                if (tid < 32) {
+                    const int nrows = min(kRB, u.nU - n * kRB);
+                    if (tid == 0) mbar_arrive_expect_tx(&tma_bar, (uint32_t)nrows * kXP * 4u);
+                    __syncwarp();
+                    if (tid < nrows) {
+                        const int row = min(max(reflect(u.r0 - kRadius + n * kRB + tid, H), 0), H - 1);
+                        tma_load_3d(XR + tid * kXRP, &xmap, u.c0 - kRadius, row, u.plane, &tma_bar);
+                    }
+                }
+                return;
+            }
 #pragma unroll
             for (int k = 0; k < kStage2; ++k) {
                 const int f = tid + k * kThreads;
@@ -119,6 +148,10 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
 
         for (int n = 0; n < u.nB; ++n) {
             __syncthreads();  // MS ready (n == 0); ring slots of block n no longer read by the previous V pass
+            if (TMA) {
+                mbar_wait(&tma_bar, tma_phase);
+                tma_phase ^= 1u;
+            }
 #pragma unroll
             for (int k = 0; k < kStage2; ++k) {
                 const int f = tid + k * kThreads;
@@ -130,7 +163,7 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const float m = MS[min(v0 + e, u.nU - 1)];
-                        const float4 in = pre[k][e];
+                        const float4 in = TMA ? *reinterpret_cast<const float4*>(XR + (2 * rp + e) * kXRP + 4 * c4) : pre[k][e];
                         const float4 ic = HAS_ICA ? prei[k][e] : make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
                         o[e][0] = chain_x3<HAS_ICA, FAST>(ck, in.x, ic.x) * m;
                         o[e][1] = chain_x3<HAS_ICA, FAST>(ck, in.y, ic.y) * m;
@@ -163,8 +196,9 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
                     }
                 }
             }
-            if (n + 1 < u.nB) stage(n + 1);
+            if (!TMA && n + 1 < u.nB) stage(n + 1);
             __syncthreads();
+            if (TMA && n + 1 < u.nB) stage(n + 1);  // the staging tile has been consumed by everyone
             {   // horizontal pass: thread = row pair x 8 columns; lanes 0..15 -> row pairs
                 const int rp = tid & 15, cg = tid >> 4;
                 const int v0 = n * kRB + 2 * rp;
@@ -234,13 +268,29 @@ recovery_fwd_kernel(const float* __restrict__ x, const float* __restrict__ A, co
 }
 
 constexpr size_t kFwdSmem = (size_t)(kPairs * kXP2 + kHRows * kHP + kMaxU) * sizeof(float);
+constexpr size_t kFwdSmemTma = kFwdSmem + (size_t)kRB * kXRP * sizeof(float);
+
+template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA>
+static int launch_fwd4(const CUtensorMap& xmap, const float* x, const float* A, const float* IcA, const float* feat, float* y, int B,
+                       int H, int W, const Sched& sc, cudaStream_t st) {
+    constexpr size_t smem = TMA ? kFwdSmemTma : kFwdSmem;
+    DD_ENSURE_SMEM((recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>), smem, "recovery kernel");
+    launch_pdl(recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>, dim3(sc.G), dim3(kThreads), smem, st, xmap, x, A, IcA, feat, y, B, H, W);
+    return DD_OK;
+}
 
 template <bool HAS_ICA, bool FAST, bool ALIGNED>
 static int launch_fwd3(const float* x, const float* A, const float* IcA, const float* feat, float* y, int B, int H,
                        int W, cudaStream_t st) {
     const Sched sc = make_sched(B, H, W);
-    DD_ENSURE_SMEM((recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED>), kFwdSmem, "recovery kernel");
-    launch_pdl(recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED>, dim3(sc.G), dim3(kThreads), kFwdSmem, st, x, A, IcA, feat, y, B, H, W);
+    CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));
+    // TMA staging: 16-byte aligned rows (ALIGNED), the default IcA (no second tile to stage) and an image at least one
+    // row box wide; otherwise the register-prefetch path
+    const bool tma = ALIGNED && !HAS_ICA && W >= kXP && make_tensor_map_3d(&xmap, x, B * 3, H, W, kXP, 1);
+    if (int e = tma ? launch_fwd4<HAS_ICA, FAST, ALIGNED, ALIGNED && !HAS_ICA>(xmap, x, A, IcA, feat, y, B, H, W, sc, st)
+                    : launch_fwd4<HAS_ICA, FAST, ALIGNED, false>(xmap, x, A, IcA, feat, y, B, H, W, sc, st))
+        return e;
     count_launch();
     return check_launch("dd_recovery_fwd");
 }
