@@ -31,12 +31,14 @@ constexpr int kHRows = kHRing + 24;     // HS rows: 64-row ring + the first 24 r
 constexpr int kStage2 = (16 * kXW4 + kThreads - 1) / kThreads;  // (row pair, float4 column) items per thread per block (3)
 constexpr int kXRP = 160;               // pitch (floats) of the TMA staging rows: 640 B, a multiple of the 128 B TMA alignment
 
-// TMA: the raw x rows of every row-block arrive by cp.async.bulk.tensor, one 156-column row box per (reflected) image row,
-// issued by the lanes of warp 0 one block ahead into a staging tile and counted on an mbarrier: no register prefetch, no
-// per-thread address arithmetic, and the stage phase never waits for DRAM.
+// TMA: the raw x rows of every row-block arrive by cp.async.bulk.tensor -- two 16-row x 160-column boxes for a block inside the
+// image, one row box per (reflected) image row for the blocks at its top and bottom -- issued by warp 0 one block ahead into a
+// staging tile and counted on an mbarrier: no register prefetch, no per-thread address arithmetic, and the stage phase never
+// waits for DRAM.
 template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2)
-recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ x, const float* __restrict__ A,
+recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap xmap16,
+                    const float* __restrict__ x, const float* __restrict__ A,
                     const float* __restrict__ IcA, const float* __restrict__ feat, float* __restrict__ y, int B, int H, int W) {
     pdl_begin();
     extern __shared__ __align__(128) float smem[];
@@ -107,10 +109,13 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __res
             if (TMA) {
                 if (tid < 32) {
                     const int nrows = min(kRB, u.nU - n * kRB);
-                    if (tid == 0) mbar_arrive_expect_tx(&tma_bar, (uint32_t)nrows * kXP * 4u);
+                    const int first = u.r0 - kRadius + n * kRB;  // image row of the block's first virtual row
+                    if (tid == 0) mbar_arrive_expect_tx(&tma_bar, (uint32_t)nrows * kXRP * 4u);
                     __syncwarp();
-                    if (tid < nrows) {
-                        const int row = min(max(reflect(u.r0 - kRadius + n * kRB + tid, H), 0), H - 1);
+                    if (nrows == kRB && first >= 0 && first + kRB <= H) {  // interior block: two 16-row boxes
+                        if (tid < 2) tma_load_3d(XR + tid * 16 * kXRP, &xmap16, u.c0 - kRadius, first + 16 * tid, u.plane, &tma_bar);
+                    } else if (tid < nrows) {                              // border block: one row box per reflected row
+                        const int row = min(max(reflect(first + tid, H), 0), H - 1);
                         tma_load_3d(XR + tid * kXRP, &xmap, u.c0 - kRadius, row, u.plane, &tma_bar);
                     }
                 }
@@ -271,11 +276,11 @@ constexpr size_t kFwdSmem = (size_t)(kPairs * kXP2 + kHRows * kHP + kMaxU) * siz
 constexpr size_t kFwdSmemTma = kFwdSmem + (size_t)kRB * kXRP * sizeof(float);
 
 template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA>
-static int launch_fwd4(const CUtensorMap& xmap, const float* x, const float* A, const float* IcA, const float* feat, float* y, int B,
+static int launch_fwd4(const CUtensorMap& xmap, const CUtensorMap& xmap16, const float* x, const float* A, const float* IcA, const float* feat, float* y, int B,
                        int H, int W, const Sched& sc, cudaStream_t st) {
     constexpr size_t smem = TMA ? kFwdSmemTma : kFwdSmem;
     DD_ENSURE_SMEM((recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>), smem, "recovery kernel");
-    launch_pdl(recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>, dim3(sc.G), dim3(kThreads), smem, st, xmap, x, A, IcA, feat, y, B, H, W);
+    launch_pdl(recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>, dim3(sc.G), dim3(kThreads), smem, st, xmap, xmap16, x, A, IcA, feat, y, B, H, W);
     return DD_OK;
 }
 
@@ -283,13 +288,15 @@ template <bool HAS_ICA, bool FAST, bool ALIGNED>
 static int launch_fwd3(const float* x, const float* A, const float* IcA, const float* feat, float* y, int B, int H,
                        int W, cudaStream_t st) {
     const Sched sc = make_sched(B, H, W);
-    CUtensorMap xmap;
+    CUtensorMap xmap, xmap16;
     memset(&xmap, 0, sizeof(xmap));
+    memset(&xmap16, 0, sizeof(xmap16));
     // TMA staging: 16-byte aligned rows (ALIGNED), the default IcA (no second tile to stage) and an image at least one
     // row box wide; otherwise the register-prefetch path
-    const bool tma = ALIGNED && !HAS_ICA && W >= kXP && make_tensor_map_3d(&xmap, x, B * 3, H, W, kXP, 1);
-    if (int e = tma ? launch_fwd4<HAS_ICA, FAST, ALIGNED, ALIGNED && !HAS_ICA>(xmap, x, A, IcA, feat, y, B, H, W, sc, st)
-                    : launch_fwd4<HAS_ICA, FAST, ALIGNED, false>(xmap, x, A, IcA, feat, y, B, H, W, sc, st))
+    const bool tma = ALIGNED && !HAS_ICA && W >= kXRP && H >= 16 && make_tensor_map_3d(&xmap, x, B * 3, H, W, kXRP, 1) &&
+                     make_tensor_map_3d(&xmap16, x, B * 3, H, W, kXRP, 16);
+    if (int e = tma ? launch_fwd4<HAS_ICA, FAST, ALIGNED, ALIGNED && !HAS_ICA>(xmap, xmap16, x, A, IcA, feat, y, B, H, W, sc, st)
+                    : launch_fwd4<HAS_ICA, FAST, ALIGNED, false>(xmap, xmap16, x, A, IcA, feat, y, B, H, W, sc, st))
         return e;
     count_launch();
     return check_launch("dd_recovery_fwd");
