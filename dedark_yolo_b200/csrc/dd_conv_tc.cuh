@@ -808,7 +808,7 @@ struct ReduceJob {
 struct ReduceJobs {
     ReduceJob j[5];
 };
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 2)  // 2 CTAs per SM: this kernel is a latency chain, occupancy is its throughput
 wgrad_reduce_kernel(const ReduceJobs jobs, const PushCtx px) {
     pdl_begin();
     __shared__ float s_part[32][33];
