@@ -17,6 +17,7 @@
 //      the row sum S = sum_w g4 x3 (the rgb2lum quirk couples every pixel of a row to columns 0..2) by warp shuffle.
 // Per (CTA, plane-strip) partial sums and per-row S go to the workspace; a fixed-order finalize kernel (one CTA per
 // image, no float atomics) adds them up, applies the column 0..2 fix-up and the regressor Jacobians.
+#include <cooperative_groups.h>
 #include <cstring>
 
 #include "dd_async.cuh"
@@ -26,7 +27,8 @@ namespace dd {
 
 constexpr int kXRingB = 80;   // XS ring depth of the backward kernel: 32 (H pass) + 12 (lagging centre rows) + 32 in flight
 constexpr int kBP = kStripW;  // BT pitch (floats)
-constexpr int kFinThreads = 1024;  // finalize: one CTA per image, ~2 rows of the column 0..2 fix-up per thread
+constexpr int kFinThreads = 512;   // finalize: a cluster of kFinCluster CTAs per image, ~1 row of the column 0..2 fix-up per thread
+constexpr int kFinCluster = 4;
 constexpr int kPW4 = (kRB * kStripW / 4) / kThreads;  // float4 per thread in the pointwise phase (4)
 
 __constant__ float c_tap[13] = {DD_K0, DD_K1, DD_K2, DD_K3, DD_K4, DD_K5, DD_K6,
@@ -376,8 +378,10 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
     if (cur_ps >= 0) flush();
 }
 
-// One CTA per image: fixed-order sum of the (CTA, plane-strip) partials, the row-coupled fix-up of columns 0..2
-// (d lum / d x3[:, :, :, 0..2]) and the regressor Jacobians -> dfeat[b, 0..14].
+// One CLUSTER of 4 CTAs per image (the kernel is a chain of latencies on ~2000 rows, one CTA per image left 132 SMs idle):
+// fixed-order sum of the (CTA, plane-strip) partials, the row-coupled fix-up of columns 0..2 (d lum / d x3[:, :, :, 0..2]),
+// each CTA on a quarter of the rows; the four partial results meet through distributed shared memory in rank order and
+// CTA 0 applies the regressor Jacobians -> dfeat[b, 0..14].
 template <bool HAS_ICA, bool FAST>
 __global__ void __launch_bounds__(kFinThreads)
 recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restrict__ A,
@@ -385,23 +389,26 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
                              const float* __restrict__ part, const float* __restrict__ Spart,
                              float* __restrict__ dfeat, float* __restrict__ dx, int B, int H, int W) {
     pdl_begin();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ ImgParams sp;
-    __shared__ double s_red[32][7];
-    const int tid = threadIdx.x, b = blockIdx.x;
+    __shared__ double s_red[kFinThreads / 32][7];
+    const int tid = threadIdx.x, b = blockIdx.x / kFinCluster, crank = (int)cluster.block_rank();
     const Sched sc = make_sched(B, H, W);
+    const int rows_per = (3 * H + kFinCluster - 1) / kFinCluster, row_lo = crank * rows_per, row_hi = min(3 * H, row_lo + rows_per);
     if (tid < 32) regress_warp(feat + b * kFeat, sp);
     double dp = 0, dc = 0, dg = 0, dw = 0, ds[3] = {0, 0, 0};
     const float kappa[3] = {kLumR, kLumG, kLumB};
 
     // rows of the column 0..2 fix-up, two per thread and pass: every load is issued before anything that needs the
     // regressed parameters (this kernel is a chain of dependent latencies, not of arithmetic)
-    for (int i0 = 0; i0 < 3 * H; i0 += 2 * kFinThreads) {
+    for (int i0 = row_lo; i0 < max(row_hi, row_lo + 1); i0 += 2 * kFinThreads) {
         float S[2], x0[2][3], ica[2][3];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = i0 + e * kFinThreads + tid;
             S[e] = 0.f;
-            if (i < 3 * H) {
+            if (i < row_hi) {
                 const int ch = i / H, row = i - ch * H, plane = 3 * b + ch;
                 for (int st = 0; st < sc.strips; ++st) S[e] += Spart[((size_t)plane * H + row) * sc.strips + st];
                 const size_t off = ((size_t)plane * H + row) * W;
@@ -412,12 +419,12 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
                 }
             }
         }
-        if (i0 == 0) __syncthreads();  // sp
+        if (i0 == row_lo) __syncthreads();  // sp
         const float pg = sp.gamma, pc = sp.c;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = i0 + e * kFinThreads + tid;
-            if (i >= 3 * H) continue;
+            if (i >= row_hi) continue;
             const int ch = i / H, row = i - ch * H, plane = 3 * b + ch;
             const float a = A ? __ldg(A + b * 3 + ch) : kDefaultA;
             const ChainK ck = make_chain(sp, ch, a);
@@ -451,7 +458,7 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
     }
 
     // partial sums: plane-strip ps of this image was processed by CTAs c_of(first block) .. c_of(last block)
-    for (int i = tid; i < 3 * sc.strips; i += kFinThreads) {
+    for (int i = crank * kFinThreads + tid; i < 3 * sc.strips; i += kFinCluster * kFinThreads) {
         const int ps = 3 * b * sc.strips + i;
         const int ch = i / sc.strips;
         const long long x0b = (long long)ps * sc.nRB, x1b = x0b + sc.nRB - 1;
@@ -480,10 +487,18 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
             s_red[0][tid] = r;
         }
         __syncthreads();
-        dp = s_red[0][0]; dc = s_red[0][1]; dg = s_red[0][2]; dw = s_red[0][3];
-        ds[0] = s_red[0][4]; ds[1] = s_red[0][5]; ds[2] = s_red[0][6];
     }
-    if (tid == 0) {
+    cluster.sync();
+    if (crank == 0 && tid == 0) {  // the four quarters in rank order (deterministic)
+        double v[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int r = 0; r < kFinCluster; ++r) {
+            const double* q = cluster.map_shared_rank(&s_red[0][0], r);
+            for (int k = 0; k < 7; ++k) v[k] += q[k];
+        }
+        dp = v[0]; dc = v[1]; dg = v[2]; dw = v[3];
+        ds[0] = v[4]; ds[1] = v[5]; ds[2] = v[6];
+    }
+    if (crank == 0 && tid == 0) {
         float* o = dfeat + b * kFeat;
         for (int i = 0; i < kFeat; ++i) o[i] = 0.f;
         const float* t = sp.t;
@@ -500,6 +515,7 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
         o[kSlotContrast] = (float)(dc * (1.0 - (double)t[kSlotContrast] * t[kSlotContrast]));
         o[kSlotUsm] = (float)(dp * 2.5 * (1.0 - (double)t[kSlotUsm] * t[kSlotUsm]));
     }
+    cluster.sync();  // keep the peers' shared memory alive until CTA 0 has read it
 }
 
 constexpr size_t kBwdSmem = (size_t)(kXRingB * kXP + kHRing * kHP + kRB * kBP + 2 * kMaxU) * sizeof(float);
@@ -526,7 +542,8 @@ static int launch_bwd3(const float* x, const float* A, const float* IcA, const f
     if (int e = tma ? launch_bwd4<HAS_ICA, FAST, ALIGNED, ALIGNED>(gmap, x, A, IcA, feat, g, part, Spart, dx, B, H, W, sc, st)
                     : launch_bwd4<HAS_ICA, FAST, ALIGNED, false>(gmap, x, A, IcA, feat, g, part, Spart, dx, B, H, W, sc, st))
         return e;
-    launch_pdl(recovery_bwd_finalize_kernel<HAS_ICA, FAST>, dim3(B), dim3(kFinThreads), 0, st, x, A, IcA, feat, (const float*)part, (const float*)Spart, dfeat, dx, B, H, W);
+    launch_pdl_cluster(recovery_bwd_finalize_kernel<HAS_ICA, FAST>, dim3(B * kFinCluster), dim3(kFinThreads), 0, st, kFinCluster, x, A, IcA, feat,
+                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W);
     count_launch(2);
     return check_launch("dd_recovery_bwd");
 }
