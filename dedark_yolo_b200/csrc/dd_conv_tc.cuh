@@ -878,6 +878,22 @@ allreduce_exchange_kernel(const PushCtx px, const GradPtrs gp) {
         return seg;
     };
     const uint2* slots = exchange_slot(px.buf[px.rank], e & 1u, 0);
+    // wait gently for the peers first: one thread per CTA watches one word that every rank pushes from its LAST producing
+    // kernel (the slice reduction) and backs off between polls; without this an early rank hammers its L2 with 75 k polling
+    // threads exactly while the late ranks' stores are arriving.  The per-element tag checks below stay (stores of
+    // different CTAs are not ordered), but then they almost always pass at the first load.
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < px.world; ++r) {
+            const uint2* src = slots + (size_t)r * kGradPad + grad_off_conv_w(0);
+            unsigned int t = 0, spin = 0;
+            do {
+                asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(t) : "l"(&src->y) : "memory");
+                if (t != tag) __nanosleep(200);
+                if (++spin > (1u << 26)) __trap();
+            } while (t != tag);
+        }
+    }
+    __syncthreads();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNumGrads; i += gridDim.x * blockDim.x) {
         float acc = 0.f;
         for (int r = 0; r < px.world; ++r) {
