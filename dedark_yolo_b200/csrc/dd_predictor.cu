@@ -496,7 +496,9 @@ static int predictor_bwd_impl(const float* r, const dd_predictor_tensors* w, con
             gp.p[2 * l + 1] = g->conv_b[l];
         }
         gp.p[10] = g->fc1_w; gp.p[11] = g->fc1_b; gp.p[12] = g->fc2_w; gp.p[13] = g->fc2_b;
-        launch_pdl(tc::allreduce_exchange_kernel, dim3(sm_count()), dim3(512), 0, st, px, gp);
+        // 64 CTAs, not one per SM: the kernel waits for other ranks; leaving SMs free keeps a second rank on the SAME device
+        // (the single-GPU test, MPS-style sharing) schedulable whatever the register footprints are
+        launch_pdl(tc::allreduce_exchange_kernel, dim3(64), dim3(512), 0, st, px, gp);
         count_launch();
     }
     if (dr) launch_conv_dgrad<3, 16, 256, 3>(d[0], w->conv_w[0], nullptr, dr, B, st);
