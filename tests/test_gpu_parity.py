@@ -388,3 +388,34 @@ def test_fused_gradient_exchange_two_virtual_ranks(ops):
         for i, key in enumerate(O.STATE_KEYS):
             assert torch.equal(outs[0][i], outs[1][i]), f"step {step}: ranks disagree on {key}"
             assert torch.equal(outs[0][i], expect[i]), f"step {step}: {key} is not the sum of the per-rank gradients"
+
+
+# ---- BASELINE configs[3]: synthesis + recovery inference at 1280x1280, batch 32, bit-exact darkening ------------------------
+@pytest.mark.parametrize("p", [7.5, 15.0])
+def test_config4_synthesis_and_inference_1280_batch32(dd, p):
+    """uint8 batch 32x3x1280x1280, darkening compared bit for bit with the reference's own
+    expression evaluated by torch on the same GPU, then module inference with size-independent checks (finite,
+    batch-permutation equivariance bit for bit, one image against the fp64 oracle)."""
+    B, H, W = 32, 1280, 1280
+    gen = torch.Generator(device="cuda").manual_seed(2024)
+    u8 = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=gen, device="cuda")
+    batch = dd.preprocess_batch({"img": u8}, "cuda", dark_param=p)
+    clean_ref = u8.float() / 255                                  # train.py:72 on this GPU
+    assert torch.equal(batch["clean_img"].view(torch.int32), clean_ref.view(torch.int32))
+    dark_ref = torch.pow(clean_ref, p)                            # train.py:103
+    assert torch.equal(batch["img"].view(torch.int32), dark_ref.view(torch.int32)), "darkening is not bit-exact"
+    rec_ref = torch.nn.functional.mse_loss(dark_ref.double(), clean_ref.double())
+    assert abs(float(batch["recovery_loss_batch"]) - float(rec_ref)) <= 1e-6 * float(rec_ref)
+    del clean_ref, dark_ref
+    m = make_module(dd, 4.0).eval()
+    with torch.no_grad():
+        y = m(batch["img"])
+        assert y.shape == (B, 3, H, W) and y.dtype == torch.float32 and bool(torch.isfinite(y).all())
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).cuda()
+        y_p = m(batch["img"][perm].contiguous())
+        assert torch.equal(y_p, y[perm])
+    if p == 7.5:  # one image against the fp64 oracle (the CPU side of this costs a few seconds)
+        b = 17
+        weights = O.cast_weights({k: v.detach().cpu() for k, v in m.state_dict().items()}, torch.float64)
+        y64 = O.recovery_forward(batch["img"][b:b + 1].cpu().double(), weights, dense_blur=False)
+        report(f"config4 fwd 1280x1280 img {b}", y[b:b + 1], y64, FWD_TOL)
