@@ -306,9 +306,10 @@ def run_ours(args):
     for i in range(args.steps):
         src, g = cleans[i % RING], gs[i % RING]
         ev[i][0].record()
-        pipe.synth(src, st)
+        pipe.synth(src, st)  # synthesis + recovery loss (fp32 source: the resize stays a separate pass, see pipeline.py)
         ev[i][1].record()
-        _lib.check(_lib.lib.dd_resize256(_p(pipe.dark), _p(pipe.r), B, H, W, st))
+        if not pipe.fused_resize:
+            _lib.check(_lib.lib.dd_resize256(_p(pipe.dark), _p(pipe.r), B, H, W, st))
         _lib.check(_lib.lib.dd_predictor_fwd(_p(pipe.r), C.byref(pipe._w), _p(pipe.acts), _p(pipe.feat), B, st))
         ev[i][2].record()
         _lib.check(_lib.lib.dd_recovery_fwd(_p(pipe.dark), None, None, _p(pipe.feat), _p(pipe.y), B, H, W, st))

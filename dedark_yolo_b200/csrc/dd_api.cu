@@ -44,7 +44,7 @@ unsigned long long dd_launch_count(void) { return dd::g_launches.load(std::memor
 size_t dd_workspace_bytes(int kind, int B, int H, int W) {
     if (B <= 0) return 0;
     switch (kind) {
-        case DD_WS_SYNTH: return dd::synth_ws_bytes();
+        case DD_WS_SYNTH: return dd::synth_ws_bytes(B);
         case DD_WS_PREDICTOR_ACTS: return dd::predictor_acts_bytes(B);
         case DD_WS_PREDICTOR_BWD: return dd::predictor_bwd_ws_bytes(B);
         case DD_WS_RECOVERY_BWD: return (H > 0 && W > 0) ? dd::recovery_bwd_ws_bytes(B, H, W) : 0;

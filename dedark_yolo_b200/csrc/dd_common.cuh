@@ -190,6 +190,14 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
     return r;
 }
 
+// the four-tap lerp of the 256x256 resize with a fixed operation order (explicit FMAs), so that every kernel that evaluates it
+// (resize256_kernel, the fused synthesis + resize pass) produces the same bits
+__device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v11, float lx, float ly) {
+    const float hx = 1.f - lx, hy = 1.f - ly;
+    const float top = __fmaf_rn(lx, v01, __fmul_rn(hx, v00)), bot = __fmaf_rn(lx, v11, __fmul_rn(hx, v10));
+    return __fmaf_rn(ly, bot, __fmul_rn(hy, top));
+}
+
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : kLeaky * v; }
 __device__ __forceinline__ float leaky_grad(float act, float g) { return act > 0.f ? g : kLeaky * g; }
 

@@ -6,7 +6,17 @@ namespace dd {
 
 // ---- synthesis -----------------------------------------------------------------------------------
 constexpr int kSynthMaxBlocks = 148 * 8;  // one double partial per CTA
-inline size_t synth_ws_bytes() { return sizeof(double) * kSynthMaxBlocks; }
+// (the fused synthesis + resize pass keeps one partial per (plane, band of 2 output rows): B*3*128 doubles)
+inline size_t synth_ws_bytes(int B = 0) {
+    const size_t fused = (size_t)(B > 0 ? B : 0) * 3 * 128;
+    return sizeof(double) * (fused > (size_t)kSynthMaxBlocks ? fused : (size_t)kSynthMaxBlocks);
+}
+// shared memory of the fused synthesis + resize pass: the source rows behind two output rows (+1 row of the next band)
+constexpr size_t kSynthResizeMaxSmem = 200 * 1024;
+inline size_t synth_resize_smem_bytes(int H, int W) {
+    const int rows = (int)(2.5 * H / 256.0) + 3;  // band 0 also owns the rows above the first tap row (half a step)
+    return (size_t)rows * W * sizeof(float);
+}
 
 // ---- predictor (common.py:52-78): channels 3->16->32->32->32->32, spatial 256->128->64->32->16->8 --
 constexpr int kPredLayers = 5;

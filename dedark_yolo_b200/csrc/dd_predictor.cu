@@ -47,8 +47,7 @@ resize256_kernel(const float* __restrict__ x, float* __restrict__ r, int B, int 
     const float* p = x + (size_t)plane * H * W;
     const float v00 = __ldg(p + (size_t)y0 * W + x0), v01 = __ldg(p + (size_t)y0 * W + x1);
     const float v10 = __ldg(p + (size_t)y1 * W + x0), v11 = __ldg(p + (size_t)y1 * W + x1);
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    r[((size_t)plane * DD_RESIZE + i) * DD_RESIZE + j] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+    r[((size_t)plane * DD_RESIZE + i) * DD_RESIZE + j] = bilerp(v00, v01, v10, v11, lx, ly);
 }
 
 // adjoint as a gather (deterministic): every source pixel sums the output pixels that sampled it

@@ -75,6 +75,38 @@ def synth_forward(src: torch.Tensor, p: float, lut: Optional[torch.Tensor] = Non
     return clean, dark, dark_u8, rec
 
 
+def synth_resize_supported(H: int, W: int) -> bool:
+    return bool(lib.dd_synth_resize_supported(int(H), int(W)))
+
+
+def synth_resize_forward(src: torch.Tensor, p: float, lut: Optional[torch.Tensor] = None,
+                         clean_lut: Optional[torch.Tensor] = None, want_clean: bool = True, want_rec: bool = True):
+    """Synthesis fused with the module's 256x256 bilinear resize (train.py:72,103,108 + llie.py:43) in one pass:
+    ``src`` uint8 or float32 ``[B,3,H,W]`` -> ``(clean, dark, r, rec)`` with ``r = resize256(dark)`` bit for bit, without
+    reading the dark batch back from HBM.  Needs ``synth_resize_supported(H, W)``."""
+    _need_cuda(src, lut, clean_lut)
+    if src.dtype not in (torch.uint8, torch.float32) or src.dim() != 4 or src.shape[1] != 3:
+        raise TypeError(f"synth_resize_forward: uint8 or float32 [B,3,H,W] expected, got {src.dtype} {tuple(src.shape)}")
+    src = src.contiguous()
+    B, _, H, W = src.shape
+    is_u8 = src.dtype == torch.uint8
+    dev = src.device
+    with torch.cuda.device(dev):
+        clean = torch.empty(src.shape, dtype=torch.float32, device=dev) if (is_u8 and want_clean) else None
+        dark = torch.empty(src.shape, dtype=torch.float32, device=dev)
+        r = torch.empty(B, 3, RESIZE, RESIZE, dtype=torch.float32, device=dev)
+        rec = torch.empty((), dtype=torch.float32, device=dev) if want_rec else None
+        ws_bytes = _lib.workspace_bytes(_lib.WS_SYNTH, B)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if want_rec else None
+        lut = None if lut is None else _f32c(lut)
+        clean_lut = None if clean_lut is None else _f32c(clean_lut)
+        check(lib.dd_synth_resize_fwd(_ptr(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, float(p), _ptr(lut), _ptr(clean_lut), _ptr(clean),
+                                      _ptr(dark), _ptr(r), _ptr(rec), B, H, W, _ptr(ws), ws_bytes if want_rec else 0, _stream(dev)))
+    if not is_u8 and want_clean:
+        clean = src
+    return clean, dark, r, rec
+
+
 def reference_cpu_tables(p: float, device):
     """The reference's CPU bits for uint8-sourced data: ``clean = k / 255`` (true division) and
     ``dark = torch.pow(clean, p)`` evaluated by torch on the host for k = 0..255 (train.py:72,79 run on CPU).

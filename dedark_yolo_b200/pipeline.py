@@ -1,6 +1,6 @@
 """Device-resident training step of the hot path with every buffer pre-allocated.
 
-    synthesis (+recovery loss)  ->  resize  ->  predictor fwd  ->  fused filters fwd
+    synthesis (+recovery loss, + the 256x256 resize in the same pass)  ->  predictor fwd  ->  fused filters fwd
                                 ->  fused filters bwd (cotangent g)  ->  predictor bwd
                                 ->  [NCCL all-reduce(sum) of the flat predictor gradient when world_size > 1]
 
@@ -62,17 +62,27 @@ class RecoveryPipeline:
         # exchange: a dist.GradExchange (or any object with a ``px`` descriptor).  With it the predictor backward itself
         # exchanges and sums the gradients over peer memory (dd_predictor_bwd_allreduce) and no NCCL call is made.
         self.exchange = exchange
+        # uint8 batches: synthesis and the module's 256x256 resize in ONE pass when the size allows it (W % 4 == 0, band fits in
+        # shared memory) -- that pass is HBM bound and the fusion saves the re-read of the dark batch (e2e +7 %).  fp32 sources stay
+        # on two passes: their synthesis is issue bound on the exact powf and the fused kernel measured 8 us slower than the pair.
+        self.fused_resize = src_dtype == torch.uint8 and bool(lib.dd_synth_resize_supported(H, W))
         self.graphs = {}
 
     # -- individual stages (each is one C-ABI call) -------------------------------------------------------
     def synth(self, src, st):
         is_u8 = src.dtype == torch.uint8
+        if self.fused_resize:  # also produces self.r: forward() then skips dd_resize256
+            check(lib.dd_synth_resize_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None,
+                                          _p(self.clean) if is_u8 else None, _p(self.dark), _p(self.r), _p(self.rec), self.B, self.H,
+                                          self.W, _p(self._ws_syn), self._ws_syn.numel(), st))
+            return
         check(lib.dd_synth_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None, _p(self.clean) if is_u8 else None,
                                _p(self.dark), None, _p(self.rec), src.numel(), _p(self._ws_syn), self._ws_syn.numel(), st))
 
     def forward(self, st, A=None, IcA=None):
         B, H, W = self.B, self.H, self.W
-        check(lib.dd_resize256(_p(self.dark), _p(self.r), B, H, W, st))
+        if not self.fused_resize:
+            check(lib.dd_resize256(_p(self.dark), _p(self.r), B, H, W, st))
         check(lib.dd_predictor_fwd(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.feat), B, st))
         check(lib.dd_recovery_fwd(_p(self.dark), _p(A), _p(IcA), _p(self.feat), _p(self.y), B, H, W, st))
 

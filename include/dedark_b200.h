@@ -39,7 +39,7 @@ extern "C" {
 #define DD_RESIZE 256         /* llie.py:43       */
 
 /* workspace kinds for dd_workspace_bytes */
-#define DD_WS_SYNTH 0          /* dd_synth_fwd partial sums                                        */
+#define DD_WS_SYNTH 0          /* dd_synth_fwd / dd_synth_resize_fwd partial sums (depends on B)   */
 #define DD_WS_PREDICTOR_ACTS 1 /* activations + prepared tensor-core weights kept from dd_predictor_fwd for dd_predictor_bwd */
 #define DD_WS_PREDICTOR_BWD 2  /* scratch of dd_predictor_bwd                                      */
 #define DD_WS_RECOVERY_BWD 3   /* partial sums of dd_recovery_bwd                                  */
@@ -73,6 +73,15 @@ size_t dd_workspace_bytes(int kind, int B, int H, int W);
 int dd_synth_fwd(const void* src, int src_dtype, float p, const float* lut256,
                  const float* clean_lut256, float* clean_out, float* dark_out, uint8_t* dark_u8, float* rec_out, long long n, void* ws,
                  size_t ws_bytes, void* stream);
+
+/* ---- a1 + a2 + a4 in one pass: synthesis fused with the 256x256 bilinear resize the module applies to the darkened
+ * batch (train.py:72,103,108 + llie.py:43).  Same outputs as dd_synth_fwd followed by dd_resize256 (r bit-identical), but
+ * the dark batch is not read back from HBM for the resize.  Needs W % 4 == 0 and a band of source rows that fits in shared
+ * memory: dd_synth_resize_supported(H, W) == 1; ws: DD_WS_SYNTH bytes for this B. */
+int dd_synth_resize_supported(int H, int W);
+int dd_synth_resize_fwd(const void* src, int src_dtype, float p, const float* lut256, const float* clean_lut256,
+                        float* clean_out, float* dark_out, float* r_out, float* rec_out, int B, int H, int W, void* ws,
+                        size_t ws_bytes, void* stream);
 
 /* ---- a4: bilinear resize to 256x256 (llie.py:43; align_corners=False, no antialias) ----------- */
 int dd_resize256(const float* x, float* r, int B, int H, int W, void* stream);

@@ -419,3 +419,25 @@ def test_config4_synthesis_and_inference_1280_batch32(dd, p):
         weights = O.cast_weights({k: v.detach().cpu() for k, v in m.state_dict().items()}, torch.float64)
         y64 = O.recovery_forward(batch["img"][b:b + 1].cpu().double(), weights, dense_blur=False)
         report(f"config4 fwd 1280x1280 img {b}", y[b:b + 1], y64, FWD_TOL)
+
+
+# ---- a1 + a2 + a4 in one pass ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,dtype", [((2, 3, 640, 640), torch.float32), ((3, 3, 640, 640), torch.uint8), ((1, 3, 1280, 1280), torch.uint8),
+                                         ((2, 3, 96, 80), torch.float32), ((2, 3, 300, 516), torch.uint8), ((1, 3, 2048, 1024), torch.float32),
+                                         ((2, 3, 13, 16), torch.uint8)])
+def test_synth_resize_fused_equals_separate_passes(ops, shape, dtype):
+    """dd_synth_resize_fwd == dd_synth_fwd followed by dd_resize256: clean, dark and r bit for bit, rec within 1e-6 of the fp64
+    value (the partial sums are grouped differently); covers down- and up-sampling, scales below and above 2, non-square images."""
+    gen = torch.Generator().manual_seed(11)
+    src = (torch.randint(0, 256, shape, dtype=torch.uint8, generator=gen) if dtype == torch.uint8 else torch.rand(shape, generator=gen)).cuda()
+    assert ops.synth_resize_supported(shape[2], shape[3])
+    clean_a, dark_a, _, rec_a = ops.synth_forward(src, 7.5)
+    r_a = ops.resize256(dark_a)
+    clean_b, dark_b, r_b, rec_b = ops.synth_resize_forward(src, 7.5)
+    assert torch.equal(dark_a, dark_b) and torch.equal(r_a, r_b)
+    if dtype == torch.uint8:
+        assert torch.equal(clean_a, clean_b)
+    clean64 = (clean_b if dtype == torch.uint8 else src).double()
+    rec64 = float(torch.nn.functional.mse_loss(dark_b.double(), clean64))
+    assert abs(float(rec_b) - rec64) <= 1e-6 * rec64 and abs(float(rec_a) - rec64) <= 1e-6 * rec64
+    assert not ops.synth_resize_supported(640, 641)  # W % 4 != 0 stays on the two-pass path
