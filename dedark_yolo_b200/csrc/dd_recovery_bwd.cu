@@ -73,21 +73,34 @@ struct BwdAcc {
 template <bool HAS_ICA, bool FAST>
 __device__ __forceinline__ float px_bwd(float x0, float ica, float g5, float bt, float m, float q1, const ChainK& ck,
                                         float pp, BwdAcc& acc, float& srow) {
-    float inv, icaw = 0.f;
-    bool pass_tx = true;
-    const float xa = x0 - ck.a;
-    float x1;
-    if (HAS_ICA) {
-        const float tx = fmaf(-ck.w, ica, 1.f);
-        pass_tx = tx >= kTxMin;
-        const float txc = fmaxf(tx, kTxMin);
-        inv = __fdiv_rn(1.f, txc);
-        x1 = __fdiv_rn(xa, txc) + ck.a;
-        icaw = ica * inv * inv;
-    } else {
-        inv = ck.inv;
-        x1 = fmaf(xa, inv, ck.a);
+    if (!HAS_ICA) {
+        // default IcA: DeDark + WB are one FMA (the forward's own expression), and the two sums that need x1 and x0 - a are
+        // taken in terms of x2:  with h2 = g2 / gamma,  acc.s = sum h2 x2,  acc.w = sum h2;  the finalize kernel turns them
+        // into  ds = gamma acc.s / s  and  dw = gamma (acc.s - s a acc.w) / inv  (x1 = x2 / s, x0 - a = (x1 - a) / inv):
+        // 4 instructions per pixel less than carrying x1 and x0 - a through the chain.
+        const float x2 = fmaf(x0, ck.k1, ck.k0);
+        const float x2c = fmaxf(x2, kGammaClamp);
+        float l2;
+        const float x3 = gamma_pow<FAST>(x2c, ck.gamma, &l2);
+        const float g4 = fmaf(g5, 1.f + pp, -pp * bt);
+        acc.p = fmaf(x3 * m, g5 - bt, acc.p);
+        const float u3 = g4 * x3;
+        srow += u3;
+        acc.c = fmaf(u3, q1, acc.c);
+        const float g3x3 = u3 * m;
+        acc.g = fmaf(g3x3, l2, acc.g);  // log2: * ln 2 applied in finalize
+        const float h2 = x2 >= kGammaClamp ? g3x3 * rcp_fast(x2c) : 0.f;
+        acc.s = fmaf(h2, x2, acc.s);
+        acc.w += h2;
+        return h2 * (ck.gamma * ck.k1);  // dL/dx0 = g2 s inv = h2 gamma k1
     }
+    const float xa = x0 - ck.a;
+    const float tx = fmaf(-ck.w, ica, 1.f);
+    const bool pass_tx = tx >= kTxMin;
+    const float txc = fmaxf(tx, kTxMin);
+    const float inv = __fdiv_rn(1.f, txc);
+    const float x1 = __fdiv_rn(xa, txc) + ck.a;
+    const float icaw = ica * inv * inv;
     const float x2 = x1 * ck.s;
     const float x2c = fmaxf(x2, kGammaClamp);
     float l2;
@@ -103,11 +116,7 @@ __device__ __forceinline__ float px_bwd(float x0, float ica, float g5, float bt,
     acc.s = fmaf(g2, x1, acc.s);
     const float g1 = g2 * ck.s;
     // d x1 / d w = (x0 - a) * ica / txc^2   (tx = 1 - w ica, only where tx >= 0.01)
-    if (HAS_ICA) {
-        if (pass_tx) acc.w = fmaf(g1 * xa, icaw, acc.w);
-    } else {
-        acc.w = fmaf(g1, xa, acc.w);  // * ica / txc^2 applied in finalize
-    }
+    if (pass_tx) acc.w = fmaf(g1 * xa, icaw, acc.w);
     return g1 * inv;
 }
 
@@ -467,9 +476,17 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
         // default-IcA constants folded out of the kernel's acc.w
         const float txc = fmaxf(1.f - sp.w * kDefaultIcA, kTxMin);
         const float wk = HAS_ICA ? 1.f : ((1.f - sp.w * kDefaultIcA >= kTxMin) ? kDefaultIcA / (txc * txc) : 0.f);
+        const ChainK ckp = make_chain(sp, ch, A ? __ldg(A + b * 3 + ch) : kDefaultA);
         for (int c = c_first; c <= c_last; ++c) {
             const float* q = part + (size_t)(c + ps) * kBwdSums;
-            dp += q[0]; dc += q[1]; dg += (double)q[2] * 0.69314718055994530942; ds[ch] += q[3]; dw += (double)q[4] * wk;
+            dp += q[0]; dc += q[1]; dg += (double)q[2] * 0.69314718055994530942;
+            if (HAS_ICA) {
+                ds[ch] += q[3];
+                dw += (double)q[4];
+            } else {  // q[3] = sum h2 x2, q[4] = sum h2 (see px_bwd)
+                ds[ch] += (double)ckp.gamma * (double)q[3] / (double)ckp.s;
+                dw += (double)ckp.gamma * ((double)q[3] - (double)ckp.s * (double)ckp.a * (double)q[4]) / (double)ckp.inv * (double)wk;
+            }
         }
     }
     {   // the seven block sums in one pass: lanes (shuffles), then warps in index order (deterministic)
