@@ -83,6 +83,38 @@ def test_synth_f32_bit_exact_vs_torch_cuda(ops, p):
     assert abs(float(rec) - float(ref_rec)) <= 1e-6 * float(ref_rec)
 
 
+@pytest.mark.parametrize("p", [15.0, 5.0, 7.5, 10.0, 1.5, 2.2, 0.45, 4.999999, 1e-3, 977.0, 2.0 ** -20, 2.0 ** 20])
+def test_synth_f32_every_float_in_unit_interval_bit_exact(ops, p):
+    """The fp32 synthesis evaluates the main path of powf inline (dd_synth.cu: powf_unit).  EVERY bit pattern from +0 to 2.0
+    -- all of [0, 1], the denormals and the (1, 2) values that take the library call -- must give torch.pow's bits."""
+    chunk = 1 << 26
+    for k in range(16):
+        bits = torch.arange(k * chunk, (k + 1) * chunk, dtype=torch.int32, device="cuda")
+        x = bits.view(torch.float32)
+        _, dark, _, _ = ops.synth_forward(x, p)
+        ref = torch.pow(x, p)
+        same = dark.view(torch.int32) == ref.view(torch.int32)
+        if not bool(same.all()):
+            bad = (~same).nonzero()[:4].flatten().tolist()
+            raise AssertionError(f"p={p}: {int((~same).sum())} mismatches in chunk {k}, e.g. " +
+                                 ", ".join(f"x={float(x[i])!r} got {float(dark[i])!r} ref {float(ref[i])!r}" for i in bad))
+
+
+@pytest.mark.parametrize("p", [15.0, 2.5, 3.0, 0.5, -1.0, -2.0, -0.5, 0.0, -3.3, float("inf")])
+def test_synth_f32_out_of_domain_inputs_follow_torch_pow(ops, p):
+    """Negative, > 1, denormal, infinite and NaN inputs (never produced by an image, but legal) and non-positive or special
+    exponents take the library path: same bits as torch.pow, NaN for NaN."""
+    gen = torch.Generator().manual_seed(7)
+    x = torch.cat([torch.randn(4096, generator=gen) * 3, torch.rand(4096, generator=gen),
+                   torch.tensor([0.0, -0.0, 1.0, -1.0, float("inf"), -float("inf"), float("nan"), 1e-40, -1e-40, 1e-38, 2.0, 0.5]),
+                   torch.zeros(4)]).cuda()
+    _, dark, _, _ = ops.synth_forward(x, p)
+    ref = torch.pow(x, p)
+    nan = torch.isnan(ref)
+    assert torch.equal(torch.isnan(dark), nan)
+    assert torch.equal(dark.view(torch.int32)[~nan], ref.view(torch.int32)[~nan])
+
+
 def test_synth_host_lut_reproduces_reference_cpu_bits(ops):
     s = load_golden("synth.npz")
     u8 = torch.from_numpy(s["u8"]).cuda()
