@@ -250,8 +250,35 @@ def run_ours(args):
     gs = [torch.randn(B, 3, H, W, generator=gen, device=dev) for _ in range(RING)]
 
     use_graph = not args.no_graph
+    overlap = not args.no_overlap
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed_run(step_fn, first):
+        """W warm-up + K timed calls of step_fn(n), n counting on from `first`; returns ms for the K steps (max over ranks)."""
+        n = first
+        for _ in range(max(args.warmup, 3)):
+            step_fn(n)
+            n += 1
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step_fn(n)
+            n += 1
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1), dev), sampler.stop(), n
+
+    # (1) plain steps: synthesis -> ... -> predictor backward back to back on one stream
     launches_per_step = None
-    if use_graph:
+    seq_graph = use_graph
+    if seq_graph:
         try:
             for i in range(RING):
                 n0 = dd.launch_count()
@@ -259,37 +286,38 @@ def run_ours(args):
                 launches_per_step = (dd.launch_count() - n0) // 2  # warm-up + captured pass
         except Exception as e:  # pragma: no cover
             print(f"[bench] CUDA graph capture failed ({e!r}); falling back to eager launches", file=sys.stderr)
-            use_graph = False
+            seq_graph = use_graph = False
             pipe.graphs.clear()
     if launches_per_step is None:
         n0 = dd.launch_count()
         pipe.step(cleans[0], gs[0])
         launches_per_step = dd.launch_count() - n0
 
-    def one_step(i):
-        if use_graph:
-            pipe.replay(i % RING)
+    def plain_step(n):
+        if seq_graph:
+            pipe.replay(n % RING)
         else:
-            pipe.step(cleans[i % RING], gs[i % RING])
+            pipe.step(cleans[n % RING], gs[n % RING])
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    ms_plain, clocks, _ = timed_run(plain_step, 0)
 
-    for i in range(max(args.warmup, 3)):
-        one_step(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        one_step(i)
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
+    # (2) software-pipelined steps (the headline): step n consumes the batch synthesised during step n-1 and synthesises batch
+    # n+1 on a side stream under its own predictor backward.  One synthesis and one of everything else per step, as in (1).
+    ms_total = ms_plain
+    if overlap:
+        if use_graph:
+            for i in range(RING):  # RING is even: step n uses graph n % RING and buffer set n % 2
+                pipe.capture_overlapped(("ovl", i), cleans[(i + 1) % RING], gs[i], slot=i % 2)
+        pipe._cur = 0
+        pipe.prime(cleans[0])
+
+        def overlapped_step(n):
+            if use_graph:
+                pipe.replay_overlapped(("ovl", n % RING))
+            else:
+                pipe.step_overlapped(cleans[(n + 1) % RING], gs[n % RING])
+
+        ms_total, clocks, _ = timed_run(overlapped_step, 0)
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
 
@@ -413,19 +441,35 @@ def run_ours(args):
         pf2.submit(host_u8[k])
     slots = [pf2.get(), pf2.get()]
     torch.cuda.synchronize(dev)
-    for k in range(2):
-        pipe8.capture(("u8", k), slots[k], gs[k])
     res_dev = torch.empty(2, dtype=torch.float32, device=dev)
-    pf2.submit(host_u8[0])
+    if overlap:
+        # step i: forward/backward of batch i (synthesised during step i-1) + synthesis of batch i+1 from staging slot (i+1) % 2,
+        # whose H2D was submitted at the start of step i-1; the H2D of batch i+2 is submitted now.
+        for k in range(2):
+            pipe8.capture_overlapped(("u8", k), slots[(k + 1) % 2], gs[k], slot=k)
+        pipe8._cur = 0
+        pf2.submit(host_u8[0])
+        pipe8.prime(pf2.get())  # staging slot 0
+        pf2.submit(host_u8[1])  # -> staging slot 1
+    else:
+        for k in range(2):
+            pipe8.capture(("u8", k), slots[k], gs[k])
+        pf2.submit(host_u8[0])
 
     def e2e_step_pipeline(i):
         src = pf2.get()
-        assert src.data_ptr() == slots[i % 2].data_ptr()
-        pf2.submit(host_u8[(i + 1) % 2])
-        pipe8.graphs[("u8", i % 2)].replay()
+        if overlap:
+            assert src.data_ptr() == slots[(i + 1) % 2].data_ptr()
+            pf2.submit(host_u8[i % 2])
+            _, rec, _ = pipe8.replay_overlapped(("u8", i % 2))
+        else:
+            assert src.data_ptr() == slots[i % 2].data_ptr()
+            pf2.submit(host_u8[(i + 1) % 2])
+            pipe8.graphs[("u8", i % 2)].replay()
+            rec = pipe8.rec
         if world > 1 and exchange is None:
             dist.all_reduce(pipe8.flat_grad)
-        res_dev[0] = pipe8.rec
+        res_dev[0] = rec
         res_dev[1] = pipe8.flat_grad.norm()
         host_out.copy_(res_dev, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
@@ -451,8 +495,9 @@ def run_ours(args):
     h2d_gbs = 5 * host_u8[0].numel() / (h2d0.elapsed_time(h2d1) * 1e-3) / 1e9
     e2e = {"value": world * B * e2e_steps / e2e_pipe_s, "unit": UNIT, "h2d_bytes_per_step": B * 3 * H * W,
            "d2h_bytes_per_step": 8, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_pipe_s / e2e_steps,
-           "api": "HostBatchPrefetcher(uint8 pinned host batch; H2D of step i+1 overlaps step i) -> RecoveryPipeline (the C-ABI calls "
-                  "of one step, captured in a CUDA graph per staging slot) -> D2H(recovery loss, grad norm) + stream sync, every step",
+           "api": "HostBatchPrefetcher(uint8 pinned host batch; H2D runs ahead of the step that reads it) -> RecoveryPipeline (the C-ABI "
+                  "calls of one step, captured in a CUDA graph per staging slot" + ("; software-pipelined as config.pipelining" if overlap else "")
+                  + ") -> D2H(recovery loss, grad norm) + stream sync, every step",
            "module_api": {"value": world * B * e2e_steps / e2e_s, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                           "api": "HostBatchPrefetcher -> preprocess_batch -> lowlight_recovery(nn.Module) fwd -> autograd bwd -> "
                                  "D2H(recovery loss, grad norm) + stream sync every step (eager; bound by ~0.7 ms of Python/autograd "
@@ -474,6 +519,10 @@ def run_ours(args):
                             + (", all-reduce of 164943 grads)" if world > 1 else ")"),
                 "gradient_exchange": exchange_how,
                 "global_batch": world * B, "parallelism": f"dp{world}", "launch": "cuda_graph" if use_graph else "eager",
+                "pipelining": ("step n = predictor fwd, filters fwd, filters bwd, predictor bwd of batch n + synthesis/resize of batch n+1 on a "
+                               "side stream under that predictor bwd (weight-independent data preparation); one synthesis per step")
+                              if overlap else "none: the stages of a batch run back to back on one stream",
+                "without_pipelining": {"ms_per_step": ms_plain / args.steps, "value": world * B * args.steps / (ms_plain * 1e-3)},
                 "l2": f"inputs rotate over a ring of {RING} (clean, g) sets = {RING * 2 * B * 3 * H * W * 4 / 1e6:.0f} MB + "
                       f"{2 * B * 3 * H * W * 4 / 1e6:.0f} MB of outputs per step (L2 = 126 MB); no explicit flush",
                 "e2e_input": "uint8 batch (train.py:72) in pinned host memory",
@@ -497,6 +546,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="do not overlap the synthesis of batch n+1 with the predictor backward of batch n")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 20:  # defaults are sized for the GPU arm

@@ -56,7 +56,7 @@ class PeerExchange(C.Structure):
 def _load():
     if not os.path.isfile(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m dedark_yolo_b200.build` (needs nvcc). "
+            f"{LIB_PATH} is missing: build it with `python dedark_yolo_b200/build.py` (needs nvcc). "
             "dedark_yolo_b200 has no CPU or PyTorch fallback.")
     lib = C.CDLL(LIB_PATH)
     vp, i, f, ll, sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t

@@ -1,6 +1,6 @@
 """Builds ``lib/libdedark_b200.so`` in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m dedark_yolo_b200.build [--force]
+    python dedark_yolo_b200/build.py [--force] [-v]   (run as a script: importing the package needs the built library)
 
 The library links the CUDA runtime statically (nvcc 12.9 is newer than torch's bundled 12.8 runtime;
 both sit on the same driver context, and streams are passed explicitly), so it has no dependency on

@@ -75,6 +75,16 @@ int check_launch(const char* what);  // cudaGetLastError -> DD_OK / DD_ERR_CUDA
         }                                                                                                   \
     } while (0)
 
+inline int sm_count() {  // SMs of the current device (all GPUs of a node are the same part)
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
 // ---- programmatic dependent launch ---------------------------------------------------------------
 // Every kernel of the library is launched with the programmatic-stream-serialization attribute and starts with
 // pdl_begin(): the next kernel in the stream may be scheduled as soon as all CTAs of this one have started (its CTAs
@@ -96,7 +106,8 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static const bool no_pdl = [] { const char* v = getenv("DEDARK_NOPDL"); return v && v[0] == '1'; }();  // debugging aid
+    cfg.numAttrs = no_pdl ? 0 : 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
     // DEDARK_SYNC=1 (debugging aid): synchronise after every launch and name the first one that fails
     static const bool dbg = [] { const char* v = getenv("DEDARK_SYNC"); return v && v[0] == '1'; }();

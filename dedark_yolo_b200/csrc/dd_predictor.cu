@@ -309,7 +309,6 @@ conv1_fwd_prep_kernel(const __grid_constant__ CUtensorMap rmap, const float* __r
     }
 }
 
-static int sm_count();
 static int launch_conv1_prep(const float* in, const float* w, const float* b, float* out, const tc::PrepJobs& jobs, int B, cudaStream_t st) {
     constexpr size_t smem = conv1_fwd_smem();
     DD_ENSURE_SMEM(conv1_fwd_prep_kernel, smem, "conv1_fwd_prep_kernel");
@@ -326,15 +325,6 @@ static int launch_conv1_prep(const float* in, const float* w, const float* b, fl
 }
 
 // ---- conv2..conv5: tensor-core kernels (dd_conv_tc.cuh) --------------------------------------------
-static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
-    return n;
-}
 template <int CIN, int COUT, int HIN>
 static int launch_tc_fwd(const float* in, const float* wprep, const float* bias, float* out, int B, cudaStream_t st) {
     constexpr int HO = HIN / 2;

@@ -5,7 +5,12 @@
                                 ->  [NCCL all-reduce(sum) of the flat predictor gradient when world_size > 1]
 
 This is what ``bench.py`` times: no allocation, no host sync, all launches on the current stream, so a step
-can also be captured into a CUDA graph (``capture``).  It shares the parameter tensors of a
+can also be captured into a CUDA graph (``capture``).
+
+Software-pipelined mode (``prime`` / ``step_overlapped``): the synthesis (+resize) of batch i+1 does not depend on the
+weights, so it is issued on a side stream as soon as the fused filter backward of batch i has been enqueued and runs in
+the shadow of the predictor backward -- eight small-grid, latency-bound launches that leave most SMs idle.  dark / r /
+rec are double-buffered for it; every step still executes exactly one synthesis and one of everything else.  It shares the parameter tensors of a
 ``lowlight_recovery`` module; gradients land in one flat fp32 buffer (164 943 floats) whose 14 views are laid
 out in state-dict order -- the buffer the single all-reduce runs on.
 """
@@ -44,15 +49,13 @@ class RecoveryPipeline:
         for q in self.params:
             self.grads.append(self.flat_grad[off:off + q.numel()].view(q.shape))
             off += q.numel()
-        self.clean = torch.empty(B, 3, H, W, **f32) if src_dtype == torch.uint8 else None
-        self.dark = torch.empty(B, 3, H, W, **f32)
-        self.rec = torch.zeros((), **f32)
-        self.r = torch.empty(B, 3, 256, 256, **f32)
+        self._slots = [self._new_slot()]  # [1] is added by enable_overlap()
+        self._cur = 0
+        self._side = None
         self.acts = torch.empty(_lib.workspace_bytes(_lib.WS_PREDICTOR_ACTS, B) // 4, **f32)
         self.feat = torch.empty(B, 15, **f32)
         self.y = torch.empty(B, 3, H, W, **f32)
         self.dfeat = torch.empty(B, 15, **f32)
-        self._ws_syn = torch.empty(_lib.workspace_bytes(_lib.WS_SYNTH, B), dtype=torch.uint8, device=dev)
         self._ws_pb = torch.empty(_lib.workspace_bytes(_lib.WS_PREDICTOR_BWD, B), dtype=torch.uint8, device=dev)
         self._ws_rb = torch.empty(_lib.workspace_bytes(_lib.WS_RECOVERY_BWD, B, H, W), dtype=torch.uint8, device=dev)
         self._w = PredictorTensors.from_tensors(self.params)
@@ -68,34 +71,68 @@ class RecoveryPipeline:
         self.fused_resize = src_dtype == torch.uint8 and bool(lib.dd_synth_resize_supported(H, W))
         self.graphs = {}
 
-    # -- individual stages (each is one C-ABI call) -------------------------------------------------------
-    def synth(self, src, st):
-        is_u8 = src.dtype == torch.uint8
-        if self.fused_resize:  # also produces self.r: forward() then skips dd_resize256
-            check(lib.dd_synth_resize_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None,
-                                          _p(self.clean) if is_u8 else None, _p(self.dark), _p(self.r), _p(self.rec), self.B, self.H,
-                                          self.W, _p(self._ws_syn), self._ws_syn.numel(), st))
-            return
-        check(lib.dd_synth_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None, _p(self.clean) if is_u8 else None,
-                               _p(self.dark), None, _p(self.rec), src.numel(), _p(self._ws_syn), self._ws_syn.numel(), st))
+    # -- per-batch buffers: what the synthesis writes and the rest of the step reads ---------------------
+    class _Slot:
+        __slots__ = ("clean", "dark", "rec", "r", "ws_syn")
 
-    def forward(self, st, A=None, IcA=None):
+    def _new_slot(self):
+        f32 = dict(dtype=torch.float32, device=self.dev)
         B, H, W = self.B, self.H, self.W
+        s = self._Slot()
+        s.clean = torch.empty(B, 3, H, W, **f32) if self.src_dtype == torch.uint8 else None
+        s.dark = torch.empty(B, 3, H, W, **f32)
+        s.rec = torch.zeros((), **f32)
+        s.r = torch.empty(B, 3, 256, 256, **f32)
+        s.ws_syn = torch.empty(_lib.workspace_bytes(_lib.WS_SYNTH, B), dtype=torch.uint8, device=self.dev)
+        return s
+
+    # the buffers of the batch the next forward/backward works on
+    clean = property(lambda self: self._slots[self._cur].clean)
+    dark = property(lambda self: self._slots[self._cur].dark)
+    rec = property(lambda self: self._slots[self._cur].rec)
+    r = property(lambda self: self._slots[self._cur].r)
+
+    # -- individual stages (each is one C-ABI call) -------------------------------------------------------
+    def synth(self, src, st, slot=None):
+        s = self._slots[self._cur if slot is None else slot]
+        is_u8 = src.dtype == torch.uint8
+        if self.fused_resize:  # also produces r: forward() then skips dd_resize256
+            check(lib.dd_synth_resize_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None,
+                                          _p(s.clean) if is_u8 else None, _p(s.dark), _p(s.r), _p(s.rec), self.B, self.H,
+                                          self.W, _p(s.ws_syn), s.ws_syn.numel(), st))
+            return
+        check(lib.dd_synth_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None, _p(s.clean) if is_u8 else None,
+                               _p(s.dark), None, _p(s.rec), src.numel(), _p(s.ws_syn), s.ws_syn.numel(), st))
+
+    def resize(self, st, slot=None):
+        s = self._slots[self._cur if slot is None else slot]
         if not self.fused_resize:
-            check(lib.dd_resize256(_p(self.dark), _p(self.r), B, H, W, st))
+            check(lib.dd_resize256(_p(s.dark), _p(s.r), self.B, self.H, self.W, st))
+
+    def forward(self, st, A=None, IcA=None, resize=True):
+        B, H, W = self.B, self.H, self.W
+        if resize:
+            self.resize(st)
         check(lib.dd_predictor_fwd(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.feat), B, st))
         check(lib.dd_recovery_fwd(_p(self.dark), _p(A), _p(IcA), _p(self.feat), _p(self.y), B, H, W, st))
 
-    def backward(self, g, st, A=None, IcA=None):
+    def backward_filters(self, g, st, A=None, IcA=None):
         B, H, W = self.B, self.H, self.W
         check(lib.dd_recovery_bwd(_p(self.dark), _p(A), _p(IcA), _p(self.feat), _p(g), _p(self.dfeat), None, B, H, W,
                                   _p(self._ws_rb), self._ws_rb.numel(), st))
+
+    def backward_predictor(self, st):
+        B = self.B
         if self.exchange is not None:
             check(lib.dd_predictor_bwd_allreduce(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.dfeat), C.byref(self._g), B,
                                                  _p(self._ws_pb), self._ws_pb.numel(), C.byref(self.exchange.px), st))
         else:
             check(lib.dd_predictor_bwd(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.dfeat), C.byref(self._g), None, B,
                                        _p(self._ws_pb), self._ws_pb.numel(), st))
+
+    def backward(self, g, st, A=None, IcA=None):
+        self.backward_filters(g, st, A, IcA)
+        self.backward_predictor(st)
 
     def step(self, src: torch.Tensor, g: torch.Tensor):
         """One full pass: ``src`` is the clean batch (uint8 or fp32 [B,3,H,W]), ``g`` the cotangent dL/dy."""
@@ -108,6 +145,80 @@ class RecoveryPipeline:
             if self.allreduce and self.exchange is None:
                 torch.distributed.all_reduce(self.flat_grad, group=self.pg)
         return self.y, self.rec, self.flat_grad
+
+    # -- software-pipelined steps ---------------------------------------------------------------------
+    def enable_overlap(self):
+        """Allocate the second set of per-batch buffers and the side stream of ``step_overlapped``."""
+        if len(self._slots) == 1:
+            self._slots.append(self._new_slot())
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+
+    def prime(self, src: torch.Tensor):
+        """Synthesise the first batch (current stream); the next ``step_overlapped`` consumes it."""
+        self.enable_overlap()
+        with torch.cuda.device(self.dev):
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            self.synth(src, st)
+            self.resize(st)
+
+    def step_overlapped(self, src_next: Optional[torch.Tensor], g: torch.Tensor):
+        """Forward + backward of the batch synthesised by the previous call (or ``prime``), with the synthesis (+resize) of
+        ``src_next`` overlapped with the predictor backward on a side stream.  Returns ``(y, rec, flat_grad)`` of the batch
+        consumed; ``rec`` is that batch's recovery loss.  ``src_next=None`` ends the sequence (nothing is synthesised)."""
+        assert self._side is not None, "call prime() first"
+        assert g.shape == (self.B, 3, self.H, self.W) and g.dtype == torch.float32
+        with torch.cuda.device(self.dev):
+            main = torch.cuda.current_stream(self.dev)
+            st = main.cuda_stream
+            cur = self._cur
+            rec = self._slots[cur].rec
+            self.forward(st, resize=False)
+            self.backward_filters(g, st)
+            if src_next is not None:
+                assert src_next.shape == (self.B, 3, self.H, self.W)
+                self._ev_fork.record(main)
+                self._side.wait_event(self._ev_fork)
+                sst = self._side.cuda_stream
+                self.synth(src_next, sst, slot=cur ^ 1)
+                self.resize(sst, slot=cur ^ 1)
+                self._ev_join.record(self._side)
+            self.backward_predictor(st)
+            if src_next is not None:
+                main.wait_event(self._ev_join)
+            if self.allreduce and self.exchange is None:
+                torch.distributed.all_reduce(self.flat_grad, group=self.pg)
+            self._cur = cur ^ 1
+        return self.y, rec, self.flat_grad
+
+    def capture_overlapped(self, key, src_next: torch.Tensor, g: torch.Tensor, slot: int):
+        """Capture ``step_overlapped(src_next, g)`` for the step that consumes buffer set ``slot`` (steps alternate 0, 1, 0, ...;
+        the collective stays outside the graph).  ``replay_overlapped(key)`` must be called in that alternation."""
+        self.enable_overlap()
+        ar, self.allreduce = self.allreduce, False
+        try:
+            self._cur = slot
+            self.step_overlapped(src_next, g)  # warm-up outside capture
+            torch.cuda.synchronize(self.dev)
+            self._cur = slot
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.step_overlapped(src_next, g)
+            self.graphs[key] = (graph, slot)
+        finally:
+            self.allreduce = ar
+        return graph
+
+    def replay_overlapped(self, key):
+        graph, slot = self.graphs[key]
+        assert slot == self._cur, "overlapped graphs must be replayed in the order they alternate buffer sets"
+        rec = self._slots[slot].rec
+        graph.replay()
+        if self.allreduce and self.exchange is None:
+            torch.distributed.all_reduce(self.flat_grad, group=self.pg)
+        self._cur = slot ^ 1
+        return self.y, rec, self.flat_grad
 
     # -- CUDA graphs ------------------------------------------------------------------------------------
     def capture(self, key, src: torch.Tensor, g: torch.Tensor):

@@ -1,0 +1,27 @@
+"""GPU timeline (CUPTI via torch.profiler) of one software-pipelined step: which kernels of the two streams overlap."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+from torch.profiler import profile, ProfilerActivity
+import dedark_yolo_b200 as dd
+
+dev = torch.device("cuda", 0)
+B, H, W = 16, 640, 640
+m = dd.lowlight_recovery(3).to(dev).train()
+pipe = dd.RecoveryPipeline(m, B, H, W, dark_param=15.0)
+gen = torch.Generator(device=dev).manual_seed(1)
+cleans = [torch.rand(B, 3, H, W, generator=gen, device=dev) for _ in range(4)]
+gs = [torch.randn(B, 3, H, W, generator=gen, device=dev) for _ in range(4)]
+pipe.prime(cleans[0])
+for i in range(6):
+    pipe.step_overlapped(cleans[(i + 1) % 4], gs[i % 4])
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for i in range(6, 9):
+        pipe.step_overlapped(cleans[(i + 1) % 4], gs[i % 4])
+    torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+t0 = evs[0].time_range.start
+for e in evs:
+    print(f"{e.time_range.start - t0:9.1f} +{e.time_range.end - e.time_range.start:7.1f} us  stream? {getattr(e, 'device_resource_id', '?')!s:4}  {e.name[:70]}")

@@ -310,6 +310,44 @@ def test_full_size_properties(dd, ops, B, H, W):
     report(f"bwd linearity {H}x{W}", d3, 2.0 * d1, 1e-5)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.uint8])
+def test_pipeline_overlapped_steps_equal_plain_steps(dd, dtype):
+    """Software-pipelined mode (synthesis of batch i+1 on a side stream under the predictor backward of batch i): the same bits
+    as the plain step for every batch of a sequence, eagerly and replayed from CUDA graphs."""
+    gen = torch.Generator().manual_seed(99)
+    B, H, W, n = 2, 160, 200, 6
+    if dtype == torch.uint8:
+        srcs = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=gen).cuda() for _ in range(n)]
+    else:
+        srcs = [torch.rand(B, 3, H, W, generator=gen).cuda() for _ in range(n)]
+    gs = [torch.randn(B, 3, H, W, generator=gen).cuda() for _ in range(n)]
+    m = make_module(dd, 4.0).train()
+    plain = dd.RecoveryPipeline(m, B, H, W, dark_param=5.0, src_dtype=dtype)
+    want = [tuple(t.clone() for t in plain.step(srcs[i], gs[i])) for i in range(n)]
+
+    pipe = dd.RecoveryPipeline(m, B, H, W, dark_param=5.0, src_dtype=dtype)
+    pipe.prime(srcs[0])
+    for i in range(n):
+        y, rec, flat = pipe.step_overlapped(srcs[i + 1] if i + 1 < n else None, gs[i])
+        torch.cuda.synchronize()
+        assert torch.equal(y, want[i][0]) and torch.equal(rec, want[i][1]) and torch.equal(flat, want[i][2]), f"eager step {i}"
+
+    # graphs: step i consumes buffer set i % 2 and synthesises batch i + 1; inputs are read from fixed staging tensors
+    stage_src = [torch.empty_like(srcs[0]) for _ in range(2)]
+    stage_g = [torch.empty_like(gs[0]) for _ in range(2)]
+    for k in range(2):
+        pipe.capture_overlapped(k, stage_src[(k + 1) % 2], stage_g[k], slot=k)
+    pipe._cur = 0
+    stage_src[0].copy_(srcs[0])
+    pipe.prime(stage_src[0])
+    for i in range(n):
+        stage_src[(i + 1) % 2].copy_(srcs[(i + 1) % n])
+        stage_g[i % 2].copy_(gs[i])
+        y, rec, flat = pipe.replay_overlapped(i % 2)
+        torch.cuda.synchronize()
+        assert torch.equal(y, want[i][0]) and torch.equal(rec, want[i][1]) and torch.equal(flat, want[i][2]), f"graph step {i}"
+
+
 def test_pipeline_step_matches_module(dd):
     gen = torch.Generator().manual_seed(77)
     B, H, W = 4, 160, 200
