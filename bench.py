@@ -442,11 +442,20 @@ def run_ours(args):
     slots = [pf2.get(), pf2.get()]
     torch.cuda.synchronize(dev)
     res_dev = torch.empty(2, dtype=torch.float32, device=dev)
+    # the read-back of the step's result (recovery loss, gradient norm -> pinned host memory) is part of the captured graph when
+    # no collective library call has to run between the step and it (1 GPU, or the peer-memory exchange inside the backward)
+    readback_in_graph = overlap and (world == 1 or exchange is not None)
+
+    def readback(y, rec, flat):
+        res_dev[0].copy_(rec)
+        torch.linalg.vector_norm(flat, out=res_dev[1])
+        host_out.copy_(res_dev, non_blocking=True)
+
     if overlap:
         # step i: forward/backward of batch i (synthesised during step i-1) + synthesis of batch i+1 from staging slot (i+1) % 2,
-        # whose H2D was submitted at the start of step i-1; the H2D of batch i+2 is submitted now.
+        # whose H2D was submitted during step i-1; the H2D of batch i+2 is submitted right after this step's graph launch.
         for k in range(2):
-            pipe8.capture_overlapped(("u8", k), slots[(k + 1) % 2], gs[k], slot=k)
+            pipe8.capture_overlapped(("u8", k), slots[(k + 1) % 2], gs[k], slot=k, epilogue=readback if readback_in_graph else None)
         pipe8._cur = 0
         pf2.submit(host_u8[0])
         pipe8.prime(pf2.get())  # staging slot 0
@@ -456,23 +465,26 @@ def run_ours(args):
             pipe8.capture(("u8", k), slots[k], gs[k])
         pf2.submit(host_u8[0])
 
+    if overlap:
+        pf2.get()  # orders the stream behind the H2D of batch 1 (staging slot 1), which step 0 synthesises
+
     def e2e_step_pipeline(i):
-        src = pf2.get()
         if overlap:
-            assert src.data_ptr() == slots[(i + 1) % 2].data_ptr()
-            pf2.submit(host_u8[i % 2])
-            _, rec, _ = pipe8.replay_overlapped(("u8", i % 2))
+            out = pipe8.replay_overlapped(("u8", i % 2))
+            pf2.submit(host_u8[i % 2])  # H2D of batch i+2 -> staging slot i % 2 (read last by the synthesis inside step i-1)
+            nxt = pf2.get()             # orders the stream -- the next step's graph -- behind that copy; no host wait
+            assert nxt.data_ptr() == slots[i % 2].data_ptr()
         else:
+            src = pf2.get()
             assert src.data_ptr() == slots[i % 2].data_ptr()
             pf2.submit(host_u8[(i + 1) % 2])
             pipe8.graphs[("u8", i % 2)].replay()
-            rec = pipe8.rec
+            out = (pipe8.y, pipe8.rec, pipe8.flat_grad)
         if world > 1 and exchange is None:
             dist.all_reduce(pipe8.flat_grad)
-        res_dev[0] = rec
-        res_dev[1] = pipe8.flat_grad.norm()
-        host_out.copy_(res_dev, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        if not readback_in_graph:
+            readback(*out)
+        torch.cuda.current_stream(dev).synchronize()  # the step's result is on the host
 
     for i in range(4):
         e2e_step_pipeline(i)
@@ -497,7 +509,8 @@ def run_ours(args):
            "d2h_bytes_per_step": 8, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_pipe_s / e2e_steps,
            "api": "HostBatchPrefetcher(uint8 pinned host batch; H2D runs ahead of the step that reads it) -> RecoveryPipeline (the C-ABI "
                   "calls of one step, captured in a CUDA graph per staging slot" + ("; software-pipelined as config.pipelining" if overlap else "")
-                  + ") -> D2H(recovery loss, grad norm) + stream sync, every step",
+                  + ") -> D2H(recovery loss, grad norm)" + (" as the last nodes of that graph" if readback_in_graph else "")
+                  + " + stream sync, every step",
            "module_api": {"value": world * B * e2e_steps / e2e_s, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                           "api": "HostBatchPrefetcher -> preprocess_batch -> lowlight_recovery(nn.Module) fwd -> autograd bwd -> "
                                  "D2H(recovery loss, grad norm) + stream sync every step (eager; bound by ~0.7 ms of Python/autograd "

@@ -192,19 +192,25 @@ class RecoveryPipeline:
             self._cur = cur ^ 1
         return self.y, rec, self.flat_grad
 
-    def capture_overlapped(self, key, src_next: torch.Tensor, g: torch.Tensor, slot: int):
+    def capture_overlapped(self, key, src_next: torch.Tensor, g: torch.Tensor, slot: int, epilogue=None):
         """Capture ``step_overlapped(src_next, g)`` for the step that consumes buffer set ``slot`` (steps alternate 0, 1, 0, ...;
-        the collective stays outside the graph).  ``replay_overlapped(key)`` must be called in that alternation."""
+        the collective stays outside the graph).  ``replay_overlapped(key)`` must be called in that alternation.
+        ``epilogue(y, rec, flat_grad)``: optional work captured behind the step in the same graph (reading the step's results
+        back to pinned host memory, say) -- only meaningful when no collective has to run between the two."""
         self.enable_overlap()
         ar, self.allreduce = self.allreduce, False
         try:
             self._cur = slot
-            self.step_overlapped(src_next, g)  # warm-up outside capture
+            out = self.step_overlapped(src_next, g)  # warm-up outside capture
+            if epilogue is not None:
+                epilogue(*out)
             torch.cuda.synchronize(self.dev)
             self._cur = slot
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self.step_overlapped(src_next, g)
+                out = self.step_overlapped(src_next, g)
+                if epilogue is not None:
+                    epilogue(*out)
             self.graphs[key] = (graph, slot)
         finally:
             self.allreduce = ar
