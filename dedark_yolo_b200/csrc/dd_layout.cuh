@@ -11,10 +11,12 @@ inline size_t synth_ws_bytes(int B = 0) {
     const size_t fused = (size_t)(B > 0 ? B : 0) * 3 * 128;
     return sizeof(double) * (fused > (size_t)kSynthMaxBlocks ? fused : (size_t)kSynthMaxBlocks);
 }
-// shared memory of the fused synthesis + resize pass: the source rows behind two output rows (+1 row of the next band)
+// shared memory of the fused synthesis + resize pass: the source rows behind the `rpb` output rows of a band (+1 row of the next)
 constexpr size_t kSynthResizeMaxSmem = 200 * 1024;
-inline size_t synth_resize_smem_bytes(int H, int W) {
-    const int rows = (int)(2.5 * H / 256.0) + 3;  // band 0 also owns the rows above the first tap row (half a step)
+constexpr size_t kSynthResizeTableBytes = 256 * 32 * sizeof(float);  // uint8 sources: the dark table, one copy per bank
+constexpr int kResizeRowsPerBandF32 = 2, kResizeRowsPerBandU8 = 4;  // partials: at most B*3*128 (synth_ws_bytes)
+inline size_t synth_resize_smem_bytes(int H, int W, int rpb) {
+    const int rows = (int)((rpb + 0.5) * H / 256.0) + 3;  // band 0 also owns the rows above the first tap row (half a step)
     return (size_t)rows * W * sizeof(float);
 }
 

@@ -33,12 +33,15 @@ def _p(t):
 class RecoveryPipeline:
     def __init__(self, module: lowlight_recovery, B: int, H: int, W: int, dark_param: float = 15.0,
                  src_dtype: torch.dtype = torch.float32, device=None, process_group=None, allreduce: bool = False,
-                 exchange=None):
+                 exchange=None, keep_clean: bool = False):
         dev = torch.device(device if device is not None else next(module.parameters()).device)
         if dev.type != "cuda":
             raise RuntimeError("RecoveryPipeline needs a CUDA device (no CPU fallback)")
         self.dev, self.B, self.H, self.W, self.p = dev, B, H, W, float(dark_param)
         self.src_dtype = src_dtype
+        # uint8 sources: the fp32 clean image (train.py:72, ``batch["clean_img"]``) is only an operand of the recovery loss, which
+        # the synthesis pass has already reduced -- it is materialised (one more full-size write) only on request
+        self.keep_clean = keep_clean
         self.params = [q.detach() for q in module.extractor.ordered_parameters()]
         for q in self.params:
             assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous()
@@ -79,7 +82,7 @@ class RecoveryPipeline:
         f32 = dict(dtype=torch.float32, device=self.dev)
         B, H, W = self.B, self.H, self.W
         s = self._Slot()
-        s.clean = torch.empty(B, 3, H, W, **f32) if self.src_dtype == torch.uint8 else None
+        s.clean = torch.empty(B, 3, H, W, **f32) if (self.src_dtype == torch.uint8 and self.keep_clean) else None
         s.dark = torch.empty(B, 3, H, W, **f32)
         s.rec = torch.zeros((), **f32)
         s.r = torch.empty(B, 3, 256, 256, **f32)
@@ -98,10 +101,10 @@ class RecoveryPipeline:
         is_u8 = src.dtype == torch.uint8
         if self.fused_resize:  # also produces r: forward() then skips dd_resize256
             check(lib.dd_synth_resize_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None,
-                                          _p(s.clean) if is_u8 else None, _p(s.dark), _p(s.r), _p(s.rec), self.B, self.H,
+                                          _p(s.clean), _p(s.dark), _p(s.r), _p(s.rec), self.B, self.H,
                                           self.W, _p(s.ws_syn), s.ws_syn.numel(), st))
             return
-        check(lib.dd_synth_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None, _p(s.clean) if is_u8 else None,
+        check(lib.dd_synth_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None, _p(s.clean),
                                _p(s.dark), None, _p(s.rec), src.numel(), _p(s.ws_syn), s.ws_syn.numel(), st))
 
     def resize(self, st, slot=None):

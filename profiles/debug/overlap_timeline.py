@@ -8,9 +8,14 @@ import dedark_yolo_b200 as dd
 dev = torch.device("cuda", 0)
 B, H, W = 16, 640, 640
 m = dd.lowlight_recovery(3).to(dev).train()
-pipe = dd.RecoveryPipeline(m, B, H, W, dark_param=15.0)
+U8 = os.environ.get("SRC", "f32") == "u8"
+pipe = dd.RecoveryPipeline(m, B, H, W, dark_param=15.0, src_dtype=torch.uint8 if U8 else torch.float32)
 gen = torch.Generator(device=dev).manual_seed(1)
-cleans = [torch.rand(B, 3, H, W, generator=gen, device=dev) for _ in range(4)]
+if U8:
+    cleans = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, device=dev) for _ in range(4)]
+else:
+    cleans = [torch.rand(B, 3, H, W, generator=gen, device=dev) for _ in range(4)]
+PLAIN = os.environ.get("PLAIN") == "1"
 gs = [torch.randn(B, 3, H, W, generator=gen, device=dev) for _ in range(4)]
 pipe.prime(cleans[0])
 for i in range(6):
@@ -18,7 +23,10 @@ for i in range(6):
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for i in range(6, 9):
-        pipe.step_overlapped(cleans[(i + 1) % 4], gs[i % 4])
+        if PLAIN:
+            pipe.step(cleans[i % 4], gs[i % 4])
+        else:
+            pipe.step_overlapped(cleans[(i + 1) % 4], gs[i % 4])
     torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
