@@ -13,7 +13,7 @@ inline size_t synth_ws_bytes(int B = 0) {
 }
 // shared memory of the fused synthesis + resize pass: the source rows behind the `rpb` output rows of a band (+1 row of the next)
 constexpr size_t kSynthResizeMaxSmem = 200 * 1024;
-constexpr size_t kSynthResizeTableBytes = 256 * 16 * sizeof(float);  // uint8 sources: the dark table, 16 bank-interleaved copies
+constexpr size_t kSynthResizeTableBytes = 256 * 16 * 2 * sizeof(float);  // uint8 sources: {dark, dark - clean}, 16 bank-interleaved copies
 constexpr int kResizeRowsPerBandF32 = 2, kResizeRowsPerBandU8 = 4;  // partials: at most B*3*128 (synth_ws_bytes)
 inline size_t synth_resize_smem_bytes(int H, int W, int rpb) {
     const int rows = (int)((rpb + 0.5) * H / 256.0) + 3;  // band 0 also owns the rows above the first tap row (half a step)

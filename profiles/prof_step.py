@@ -16,9 +16,11 @@ B, H, W = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (16, 640, 64
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 m = dd.lowlight_recovery(3).to(dev).train()
-pipe = dd.RecoveryPipeline(m, B, H, W, dark_param=15.0)
+U8 = os.environ.get("PROF_SRC", "f32") == "u8"  # the e2e path: uint8 batch, synthesis fused with the resize
+pipe = dd.RecoveryPipeline(m, B, H, W, dark_param=15.0, src_dtype=torch.uint8 if U8 else torch.float32)
 gen = torch.Generator(device=dev).manual_seed(1234)
-clean = torch.rand(B, 3, H, W, generator=gen, device=dev)
+clean = (torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, device=dev) if U8
+         else torch.rand(B, 3, H, W, generator=gen, device=dev))
 g = torch.randn(B, 3, H, W, generator=gen, device=dev)
 n0 = dd.launch_count()
 for _ in range(steps):
