@@ -145,7 +145,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
     float* MSm = BT + kRB * kBP;        // per virtual row: m = (1-c) + c*q
     float* MSq = MSm + kMaxU;           // per virtual row: q - 1
     __shared__ ImgParams sp;
-    __shared__ float s_red[32];
+    __shared__ float s_red[(kThreads / 32) * kBwdSums];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const Sched sc = make_sched(B, H, W);
@@ -153,14 +153,21 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
 
     BwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f};
     int cur_ps = -1;
-    auto flush = [&]() {  // per (CTA, plane-strip) partial sums -> slot (cta + ps)
+    auto flush = [&]() {  // per (CTA, plane-strip) partial sums -> slot (cta + ps); the five sums share two barriers
         float* out = part + (size_t)(blockIdx.x + cur_ps) * kBwdSums;
-        float s;
-        s = block_sum<float>(acc.p, s_red); if (tid == 0) out[0] = s;
-        s = block_sum<float>(acc.c, s_red); if (tid == 0) out[1] = s;
-        s = block_sum<float>(acc.g, s_red); if (tid == 0) out[2] = s;
-        s = block_sum<float>(acc.s, s_red); if (tid == 0) out[3] = s;
-        s = block_sum<float>(acc.w, s_red); if (tid == 0) out[4] = s;
+        const float v[kBwdSums] = {warp_sum(acc.p), warp_sum(acc.c), warp_sum(acc.g), warp_sum(acc.s), warp_sum(acc.w)};
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < kBwdSums; ++j) s_red[(tid >> 5) * kBwdSums + j] = v[j];
+        }
+        __syncthreads();
+        if (tid < kBwdSums) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) s += s_red[w * kBwdSums + tid];  // fixed order
+            out[tid] = s;
+        }
+        __syncthreads();
         acc.p = acc.c = acc.g = acc.s = acc.w = 0.f;
     };
 

@@ -75,34 +75,6 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         const float* ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
         float* yp = y + (size_t)u.plane * H * W;
 
-        {   // per-row contrast scalars of the segment: all loads first (<= 3 rows per thread), then the arithmetic
-            constexpr int kPer = (kMaxU + kThreads - 1) / kThreads;
-            float x0r[kPer][3], icr[kPer][3];
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) {
-                const int v = tid + k * kThreads;
-                if (v < u.nU) {
-                    const int row = reflect(u.r0 - kRadius + v, H);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        x0r[k][c] = __ldg(xp + (size_t)row * W + c);
-                        icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) {
-                const int v = tid + k * kThreads;
-                if (v < u.nU) {
-                    float x3[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) x3[c] = chain_x3<HAS_ICA, FAST>(ck, x0r[k][c], icr[k][c]);
-                    const RowLum rl = row_lum<true>(x3[0], x3[1], x3[2]);
-                    MS[v] = (1.f - pc) + pc * rl.q;
-                }
-            }
-        }
-
         // item (k) of a thread: row pair rp (2 rows) x float4 column c4; fixed across blocks
         float4 pre[kStage2][2], prei[kStage2][2];
         auto stage = [&](int n) {
@@ -149,7 +121,36 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                 }
             }
         };
-        stage(0);
+        if (TMA) stage(0);  // the first block's rows fly while the per-row scalars below are computed
+        {   // per-row contrast scalars of the segment: all loads first (<= 3 rows per thread), then the arithmetic
+            constexpr int kPer = (kMaxU + kThreads - 1) / kThreads;
+            float x0r[kPer][3], icr[kPer][3];
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int v = tid + k * kThreads;
+                if (v < u.nU) {
+                    const int row = reflect(u.r0 - kRadius + v, H);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        x0r[k][c] = __ldg(xp + (size_t)row * W + c);
+                        icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int v = tid + k * kThreads;
+                if (v < u.nU) {
+                    float x3[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) x3[c] = chain_x3<HAS_ICA, FAST>(ck, x0r[k][c], icr[k][c]);
+                    const RowLum rl = row_lum<true>(x3[0], x3[1], x3[2]);
+                    MS[v] = (1.f - pc) + pc * rl.q;
+                }
+            }
+        }
+
+        if (!TMA) stage(0);
 
         for (int n = 0; n < u.nB; ++n) {
             __syncthreads();  // MS ready (n == 0); ring slots of block n no longer read by the previous V pass
