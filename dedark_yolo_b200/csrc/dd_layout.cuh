@@ -6,7 +6,7 @@ namespace dd {
 
 // ---- synthesis -----------------------------------------------------------------------------------
 constexpr int kSynthMaxBlocks = 148 * 8;  // one double partial per CTA
-// (the fused synthesis + resize pass keeps one partial per (plane, band of 2 output rows): B*3*128 doubles)
+// (the fused synthesis + resize pass keeps one partial per CTA: at most B*3*128 for fp32 sources, one band of 2 output rows each)
 inline size_t synth_ws_bytes(int B = 0) {
     const size_t fused = (size_t)(B > 0 ? B : 0) * 3 * 128;
     return sizeof(double) * (fused > (size_t)kSynthMaxBlocks ? fused : (size_t)kSynthMaxBlocks);
