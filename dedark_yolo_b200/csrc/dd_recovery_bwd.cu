@@ -261,133 +261,143 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
             }
         }
 
-        for (int n = 0; n < u.nB; ++n) {
-            if (TMA) {
-                mbar_wait(&tma_bar, tma_phase);
-                tma_phase ^= 1u;
-            } else {
-                cp_async_wait_all();
-            }
-            __syncthreads();  // g block n visible; previous pointwise phase done with BT / XS centre rows / MS
-            if (n + 1 < u.nB) stage(n + 1);
-
-            {   // horizontal adjoint pass
-                const int rr = tid & 31, cg = tid >> 5;
-                const int v = n * kRB + rr;
-                const float* xrow = XS + (v % kXRingB) * kXP;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    const int cb = 64 * half + 8 * cg;
-                    float o[8];
-                    hpass8(xrow + cb, o);
-                    const int j0 = u.c0 + cb;  // global column of o[0]
-                    if (j0 <= kRadius || j0 + 7 >= W - 1 - kRadius) {  // reflect fold-back (image borders only)
-                        float tmp[8];
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) tmp[t] = o[t];
-                        hfold8(tmp, xrow, j0, u.c0, W);
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) o[t] = tmp[t];
-                    }
-                    float4* dst = reinterpret_cast<float4*>(HS + (v & (kHRing - 1)) * kHP + cb);
-                    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        // Two barriers per row-block: the pointwise phase of block n-1 shares an interval with the horizontal pass of block n (both
+        // only read the g ring; the pointwise phase reads BT, the horizontal pass writes the H ring), the vertical pass of block n
+        // (reads the H ring, writes BT) has the other.  One extra iteration drains the last pointwise phase.
+        float4 x0p[kPW4];
+        for (int n = 0; n <= u.nB; ++n) {
+            const bool have = n < u.nB;
+            if (have) {
+                if (TMA) {
+                    mbar_wait(&tma_bar, tma_phase);
+                    tma_phase ^= 1u;
+                } else {
+                    cp_async_wait_all();
                 }
             }
-            __syncthreads();
-            // prefetch x0 for this block's output rows (issued after the H pass to keep its register footprint down; consumed after the V pass)
-            float4 x0p[kPW4];
-#pragma unroll
-            for (int k = 0; k < kPW4; ++k) {
-                const int f = tid + k * kThreads;
-                const int rr = f >> 5, c4 = f & 31;
-                const int o = n * kRB - kRadius + rr;
-                const int gc = u.c0 + 4 * c4;
-                x0p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (o >= kRadius && o < kRadius + u.seg_len && gc < W) {
-                    const float* rp = xp + (size_t)(u.r0 + o - kRadius) * W + gc;
-                    if (ALIGNED) {
-                        x0p[k] = __ldg(reinterpret_cast<const float4*>(rp));
-                    } else {
-                        x0p[k].x = __ldg(rp);
-                        if (gc + 1 < W) x0p[k].y = __ldg(rp + 1);
-                        if (gc + 2 < W) x0p[k].z = __ldg(rp + 2);
-                        if (gc + 3 < W) x0p[k].w = __ldg(rp + 3);
-                    }
-                }
-            }
-
-            {   // vertical adjoint pass -> BT
-                const int col2 = 2 * (tid & 63), rg = tid >> 6;
-                const int o_first = n * kRB - kRadius + 8 * rg;
-                if (o_first >= kRadius && o_first < kRadius + u.seg_len) {
-                    u64 bt2[8];
-                    vpass8x2(HS, (o_first - kRadius) & (kHRing - 1), col2, bt2);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const int o = o_first + r;
-                        const int jr = u.r0 + o - kRadius;  // image row
-                        if (jr <= kRadius || jr >= H - 1 - kRadius) {  // reflect fold-back (top / bottom rows only)
-                            const float2 bt = vfold(upk(bt2[r]), HS, col2, jr, u.r0, H);
-                            bt2[r] = pk(bt.x, bt.y);
+            __syncthreads();  // g block n visible; BT of block n-1 complete; the H ring rows block n overwrites are no longer read
+            if (n > 0) {
+                // pointwise phase: warp <-> output row, lane <-> float4
+    #pragma unroll
+                for (int k = 0; k < kPW4; ++k) {
+                    const int f = tid + k * kThreads;
+                    const int rr = f >> 5, c4 = f & 31;
+                    const int o = (n - 1) * kRB - kRadius + rr;
+                    const bool row_ok = o >= kRadius && o < kRadius + u.seg_len;  // warp-uniform
+                    if (!row_ok) continue;
+                    const int jr = u.r0 + o - kRadius;
+                    const int gc = u.c0 + 4 * c4;
+                    float srow = 0.f;
+                    if (gc < W) {
+                        const float4 g5 = *reinterpret_cast<const float4*>(XS + (o % kXRingB) * kXP + 4 * c4 + kRadius);
+                        const float4 bt = *reinterpret_cast<const float4*>(BT + rr * kBP + 4 * c4);
+                        const float m = MSm[o], q1 = MSq[o];
+                        const float4 x0 = x0p[k];
+                        const size_t off = (size_t)jr * W + gc;
+                        float4 ic = make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
+                        if (HAS_ICA) {
+                            ic.x = __ldg(ip + off);
+                            if (gc + 1 < W) ic.y = __ldg(ip + off + 1);
+                            if (gc + 2 < W) ic.z = __ldg(ip + off + 2);
+                            if (gc + 3 < W) ic.w = __ldg(ip + off + 3);
                         }
-                        *reinterpret_cast<u64*>(BT + (8 * rg + r) * kBP + col2) = bt2[r];
-                    }
-                }
-            }
-            __syncthreads();
-            // pointwise phase: warp <-> output row, lane <-> float4
-#pragma unroll
-            for (int k = 0; k < kPW4; ++k) {
-                const int f = tid + k * kThreads;
-                const int rr = f >> 5, c4 = f & 31;
-                const int o = n * kRB - kRadius + rr;
-                const bool row_ok = o >= kRadius && o < kRadius + u.seg_len;  // warp-uniform
-                if (!row_ok) continue;
-                const int jr = u.r0 + o - kRadius;
-                const int gc = u.c0 + 4 * c4;
-                float srow = 0.f;
-                if (gc < W) {
-                    const float4 g5 = *reinterpret_cast<const float4*>(XS + (o % kXRingB) * kXP + 4 * c4 + kRadius);
-                    const float4 bt = *reinterpret_cast<const float4*>(BT + rr * kBP + 4 * c4);
-                    const float m = MSm[o], q1 = MSq[o];
-                    const float4 x0 = x0p[k];
-                    const size_t off = (size_t)jr * W + gc;
-                    float4 ic = make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
-                    if (HAS_ICA) {
-                        ic.x = __ldg(ip + off);
-                        if (gc + 1 < W) ic.y = __ldg(ip + off + 1);
-                        if (gc + 2 < W) ic.z = __ldg(ip + off + 2);
-                        if (gc + 3 < W) ic.w = __ldg(ip + off + 3);
-                    }
-                    // columns beyond W - 1 (only when W % 4 != 0): g5 and bt are zero-padded there, but bt is not
-                    // (it is a blur of real data), so mask their cotangents explicitly
-                    float4 d;
-                    d.x = px_bwd<HAS_ICA, FAST>(x0.x, ic.x, g5.x, bt.x, m, q1, ck, pp, acc, srow);
-                    if (ALIGNED) {  // W % 4 == 0: a float4 that starts inside the image ends inside it
-                        d.y = px_bwd<HAS_ICA, FAST>(x0.y, ic.y, g5.y, bt.y, m, q1, ck, pp, acc, srow);
-                        d.z = px_bwd<HAS_ICA, FAST>(x0.z, ic.z, g5.z, bt.z, m, q1, ck, pp, acc, srow);
-                        d.w = px_bwd<HAS_ICA, FAST>(x0.w, ic.w, g5.w, bt.w, m, q1, ck, pp, acc, srow);
-                    } else {
-                        const float l1 = gc + 1 < W ? 1.f : 0.f, l2 = gc + 2 < W ? 1.f : 0.f, l3 = gc + 3 < W ? 1.f : 0.f;
-                        d.y = px_bwd<HAS_ICA, FAST>(x0.y, ic.y, g5.y * l1, bt.y * l1, m, q1, ck, pp, acc, srow);
-                        d.z = px_bwd<HAS_ICA, FAST>(x0.z, ic.z, g5.z * l2, bt.z * l2, m, q1, ck, pp, acc, srow);
-                        d.w = px_bwd<HAS_ICA, FAST>(x0.w, ic.w, g5.w * l3, bt.w * l3, m, q1, ck, pp, acc, srow);
-                    }
-                    if (dx) {
-                        float* dp = dx + (size_t)u.plane * H * W + off;
-                        if (ALIGNED) {
-                            *reinterpret_cast<float4*>(dp) = d;
+                        // columns beyond W - 1 (only when W % 4 != 0): g5 and bt are zero-padded there, but bt is not
+                        // (it is a blur of real data), so mask their cotangents explicitly
+                        float4 d;
+                        d.x = px_bwd<HAS_ICA, FAST>(x0.x, ic.x, g5.x, bt.x, m, q1, ck, pp, acc, srow);
+                        if (ALIGNED) {  // W % 4 == 0: a float4 that starts inside the image ends inside it
+                            d.y = px_bwd<HAS_ICA, FAST>(x0.y, ic.y, g5.y, bt.y, m, q1, ck, pp, acc, srow);
+                            d.z = px_bwd<HAS_ICA, FAST>(x0.z, ic.z, g5.z, bt.z, m, q1, ck, pp, acc, srow);
+                            d.w = px_bwd<HAS_ICA, FAST>(x0.w, ic.w, g5.w, bt.w, m, q1, ck, pp, acc, srow);
                         } else {
-                            dp[0] = d.x;
-                            if (gc + 1 < W) dp[1] = d.y;
-                            if (gc + 2 < W) dp[2] = d.z;
-                            if (gc + 3 < W) dp[3] = d.w;
+                            const float l1 = gc + 1 < W ? 1.f : 0.f, l2 = gc + 2 < W ? 1.f : 0.f, l3 = gc + 3 < W ? 1.f : 0.f;
+                            d.y = px_bwd<HAS_ICA, FAST>(x0.y, ic.y, g5.y * l1, bt.y * l1, m, q1, ck, pp, acc, srow);
+                            d.z = px_bwd<HAS_ICA, FAST>(x0.z, ic.z, g5.z * l2, bt.z * l2, m, q1, ck, pp, acc, srow);
+                            d.w = px_bwd<HAS_ICA, FAST>(x0.w, ic.w, g5.w * l3, bt.w * l3, m, q1, ck, pp, acc, srow);
+                        }
+                        if (dx) {
+                            float* dp = dx + (size_t)u.plane * H * W + off;
+                            if (ALIGNED) {
+                                *reinterpret_cast<float4*>(dp) = d;
+                            } else {
+                                dp[0] = d.x;
+                                if (gc + 1 < W) dp[1] = d.y;
+                                if (gc + 2 < W) dp[2] = d.z;
+                                if (gc + 3 < W) dp[3] = d.w;
+                            }
+                        }
+                    }
+                    srow = warp_sum(srow);
+                    if (lane == 0) Spart[((size_t)u.plane * H + jr) * sc.strips + u.strip] = srow;
+                }
+            }
+            if (have) {
+                {   // horizontal adjoint pass
+                    const int rr = tid & 31, cg = tid >> 5;
+                    const int v = n * kRB + rr;
+                    const float* xrow = XS + (v % kXRingB) * kXP;
+    #pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        const int cb = 64 * half + 8 * cg;
+                        float o[8];
+                        hpass8(xrow + cb, o);
+                        const int j0 = u.c0 + cb;  // global column of o[0]
+                        if (j0 <= kRadius || j0 + 7 >= W - 1 - kRadius) {  // reflect fold-back (image borders only)
+                            float tmp[8];
+    #pragma unroll
+                            for (int t = 0; t < 8; ++t) tmp[t] = o[t];
+                            hfold8(tmp, xrow, j0, u.c0, W);
+    #pragma unroll
+                            for (int t = 0; t < 8; ++t) o[t] = tmp[t];
+                        }
+                        float4* dst = reinterpret_cast<float4*>(HS + (v & (kHRing - 1)) * kHP + cb);
+                        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+            }
+            __syncthreads();  // H ring rows of block n visible; BT, the g centre rows and x0p of block n-1 consumed
+            if (have) {
+                if (n + 1 < u.nB) stage(n + 1);
+                // prefetch x0 for this block's output rows (issued after the H pass to keep its register footprint down; consumed after the V pass)
+    #pragma unroll
+                for (int k = 0; k < kPW4; ++k) {
+                    const int f = tid + k * kThreads;
+                    const int rr = f >> 5, c4 = f & 31;
+                    const int o = n * kRB - kRadius + rr;
+                    const int gc = u.c0 + 4 * c4;
+                    x0p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (o >= kRadius && o < kRadius + u.seg_len && gc < W) {
+                        const float* rp = xp + (size_t)(u.r0 + o - kRadius) * W + gc;
+                        if (ALIGNED) {
+                            x0p[k] = __ldg(reinterpret_cast<const float4*>(rp));
+                        } else {
+                            x0p[k].x = __ldg(rp);
+                            if (gc + 1 < W) x0p[k].y = __ldg(rp + 1);
+                            if (gc + 2 < W) x0p[k].z = __ldg(rp + 2);
+                            if (gc + 3 < W) x0p[k].w = __ldg(rp + 3);
                         }
                     }
                 }
-                srow = warp_sum(srow);
-                if (lane == 0) Spart[((size_t)u.plane * H + jr) * sc.strips + u.strip] = srow;
+
+                {   // vertical adjoint pass -> BT
+                    const int col2 = 2 * (tid & 63), rg = tid >> 6;
+                    const int o_first = n * kRB - kRadius + 8 * rg;
+                    if (o_first >= kRadius && o_first < kRadius + u.seg_len) {
+                        u64 bt2[8];
+                        vpass8x2(HS, (o_first - kRadius) & (kHRing - 1), col2, bt2);
+    #pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const int o = o_first + r;
+                            const int jr = u.r0 + o - kRadius;  // image row
+                            if (jr <= kRadius || jr >= H - 1 - kRadius) {  // reflect fold-back (top / bottom rows only)
+                                const float2 bt = vfold(upk(bt2[r]), HS, col2, jr, u.r0, H);
+                                bt2[r] = pk(bt.x, bt.y);
+                            }
+                            *reinterpret_cast<u64*>(BT + (8 * rg + r) * kBP + col2) = bt2[r];
+                        }
+                    }
+                }
             }
         }
     }
