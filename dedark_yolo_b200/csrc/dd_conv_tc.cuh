@@ -808,10 +808,11 @@ struct ReduceJob {
 struct ReduceJobs {
     ReduceJob j[5];
 };
+constexpr int kReduceOut = 64;  // outputs per CTA: two per lane (one 64-bit load per slice), half the CTAs of a 32-output version
 __global__ void __launch_bounds__(1024, 2)  // 2 CTAs per SM: this kernel is a latency chain, occupancy is its throughput
 wgrad_reduce_kernel(const ReduceJobs jobs, const PushCtx px) {
     pdl_begin();
-    __shared__ float s_part[32][33];
+    __shared__ float s_part[32][kReduceOut + 1];
     const unsigned int tag = push_tag(px);
     int ji = 0;
 #pragma unroll
@@ -819,24 +820,35 @@ wgrad_reduce_kernel(const ReduceJobs jobs, const PushCtx px) {
         if ((int)blockIdx.x >= jobs.j[k].block0) ji = k;
     const ReduceJob jb = jobs.j[ji];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int i = ((int)blockIdx.x - jb.block0) * 32 + lane;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (i < jb.n) {
-        int s = wid;
-        for (; s + 96 < jb.nslices; s += 128) {
-            a0 += __ldg(jb.partial + (size_t)s * jb.stride + i);
-            a1 += __ldg(jb.partial + (size_t)(s + 32) * jb.stride + i);
-            a2 += __ldg(jb.partial + (size_t)(s + 64) * jb.stride + i);
-            a3 += __ldg(jb.partial + (size_t)(s + 96) * jb.stride + i);
+    const int base = ((int)blockIdx.x - jb.block0) * kReduceOut;
+    {   // warp `wid` sums slices wid, wid + 32, ... for outputs base + 2*lane, base + 2*lane + 1 (n and stride are even)
+        const int i = base + 2 * lane;
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        if (i < jb.n) {
+            const float* p0 = jb.partial + i;
+            int s = wid;
+            for (; s + 96 < jb.nslices; s += 128) {
+                const float2 v0 = __ldg(reinterpret_cast<const float2*>(p0 + (size_t)s * jb.stride));
+                const float2 v1 = __ldg(reinterpret_cast<const float2*>(p0 + (size_t)(s + 32) * jb.stride));
+                const float2 v2 = __ldg(reinterpret_cast<const float2*>(p0 + (size_t)(s + 64) * jb.stride));
+                const float2 v3 = __ldg(reinterpret_cast<const float2*>(p0 + (size_t)(s + 96) * jb.stride));
+                a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
+                a2.x += v2.x; a2.y += v2.y; a3.x += v3.x; a3.y += v3.y;
+            }
+            for (; s < jb.nslices; s += 32) {
+                const float2 v0 = __ldg(reinterpret_cast<const float2*>(p0 + (size_t)s * jb.stride));
+                a0.x += v0.x; a0.y += v0.y;
+            }
         }
-        for (; s < jb.nslices; s += 32) a0 += __ldg(jb.partial + (size_t)s * jb.stride + i);
+        s_part[wid][2 * lane] = (a0.x + a1.x) + (a2.x + a3.x);
+        s_part[wid][2 * lane + 1] = (a0.y + a1.y) + (a2.y + a3.y);
     }
-    s_part[wid][lane] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    if (wid == 0 && i < jb.n) {
+    const int i = base + wid * 32 + lane;  // warps 0 and 1 finish 32 outputs each
+    if (wid < kReduceOut / 32 && i < jb.n) {
         float r = 0.f;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) r += s_part[k][lane];
+        for (int k = 0; k < 32; ++k) r += s_part[k][wid * 32 + lane];
         int off;  // canonical flat offset of this output
         if (jb.cin == 0) {
             if (i < jb.nw) { jb.dw[i] = r; off = jb.off_w + i; } else { jb.db[i - jb.nw] = r; off = jb.off_b + i - jb.nw; }

@@ -473,7 +473,7 @@ static int predictor_bwd_impl(const float* r, const dd_predictor_tensors* w, con
             const int n = l == 0 ? 432 + 16 : (9 * pred_cin(l) + 1) * 32;
             jobs.j[l] = tc::ReduceJob{pl[l], g->conv_w[l], g->conv_b[l], nsl[l], n, l == 0 ? n : pred_wgrad_rp(l) * 32,
                                       l == 0 ? 0 : pred_cin(l), 432, block0, grad_off_conv_w(l), grad_off_conv_b(l)};
-            block0 += (n + 31) / 32;
+            block0 += (n + tc::kReduceOut - 1) / tc::kReduceOut;
         }
         launch_pdl(tc::wgrad_reduce_kernel, dim3(block0), dim3(1024), 0, st, jobs, px);
     }
