@@ -808,7 +808,7 @@ struct ReduceJob {
 struct ReduceJobs {
     ReduceJob j[5];
 };
-constexpr int kReduceOut = 64;  // outputs per CTA: two per lane (one 64-bit load per slice), half the CTAs of a 32-output version
+constexpr int kReduceOut = 128;  // outputs per CTA: four per lane (one 128-bit load per slice): 257 CTAs, one wave
 __global__ void __launch_bounds__(1024, 2)  // 2 CTAs per SM: this kernel is a latency chain, occupancy is its throughput
 wgrad_reduce_kernel(const ReduceJobs jobs, const PushCtx px) {
     pdl_begin();
@@ -821,30 +821,29 @@ wgrad_reduce_kernel(const ReduceJobs jobs, const PushCtx px) {
     const ReduceJob jb = jobs.j[ji];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int base = ((int)blockIdx.x - jb.block0) * kReduceOut;
-    {   // warp `wid` sums slices wid, wid + 32, ... for outputs base + 2*lane, base + 2*lane + 1 (n and stride are even)
-        const int i = base + 2 * lane;
-        float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    {   // warp `wid` sums slices wid, wid + 32, ... for outputs base + 4*lane .. + 3 (n and stride are multiples of 4)
+        const int i = base + 4 * lane;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        auto add = [](float4& a, const float4 v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
         if (i < jb.n) {
             const float* p0 = jb.partial + i;
             int s = wid;
             for (; s + 96 < jb.nslices; s += 128) {
-                const float2 v0 = __ldg(reinterpret_cast<const float2*>(p0 + (size_t)s * jb.stride));
-                const float2 v1 = __ldg(reinterpret_cast<const float2*>(p0 + (size_t)(s + 32) * jb.stride));
-                const float2 v2 = __ldg(reinterpret_cast<const float2*>(p0 + (size_t)(s + 64) * jb.stride));
-                const float2 v3 = __ldg(reinterpret_cast<const float2*>(p0 + (size_t)(s + 96) * jb.stride));
-                a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
-                a2.x += v2.x; a2.y += v2.y; a3.x += v3.x; a3.y += v3.y;
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(p0 + (size_t)s * jb.stride));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(p0 + (size_t)(s + 32) * jb.stride));
+                const float4 v2 = __ldg(reinterpret_cast<const float4*>(p0 + (size_t)(s + 64) * jb.stride));
+                const float4 v3 = __ldg(reinterpret_cast<const float4*>(p0 + (size_t)(s + 96) * jb.stride));
+                add(a0, v0); add(a1, v1); add(a2, v2); add(a3, v3);
             }
-            for (; s < jb.nslices; s += 32) {
-                const float2 v0 = __ldg(reinterpret_cast<const float2*>(p0 + (size_t)s * jb.stride));
-                a0.x += v0.x; a0.y += v0.y;
-            }
+            for (; s < jb.nslices; s += 32) add(a0, __ldg(reinterpret_cast<const float4*>(p0 + (size_t)s * jb.stride)));
         }
-        s_part[wid][2 * lane] = (a0.x + a1.x) + (a2.x + a3.x);
-        s_part[wid][2 * lane + 1] = (a0.y + a1.y) + (a2.y + a3.y);
+        s_part[wid][4 * lane] = (a0.x + a1.x) + (a2.x + a3.x);
+        s_part[wid][4 * lane + 1] = (a0.y + a1.y) + (a2.y + a3.y);
+        s_part[wid][4 * lane + 2] = (a0.z + a1.z) + (a2.z + a3.z);
+        s_part[wid][4 * lane + 3] = (a0.w + a1.w) + (a2.w + a3.w);
     }
     __syncthreads();
-    const int i = base + wid * 32 + lane;  // warps 0 and 1 finish 32 outputs each
+    const int i = base + wid * 32 + lane;  // warps 0..3 finish 32 outputs each
     if (wid < kReduceOut / 32 && i < jb.n) {
         float r = 0.f;
 #pragma unroll
