@@ -22,8 +22,11 @@ Timed numbers
               (`module_api`) the drop-in `lowlight_recovery` nn.Module with autograd, which is bound by Python host work.
   roofline    for the dominant kernel (largest stage time): algorithmic bytes per launch
               / its mean duration, measured with CUDA events around each stage over a second eager pass of K steps.
-  cpu_baseline  the oracle's fp32 port (same op mix as the reference's PyTorch CPU path) on the host cores, on a
-              bounded sample.
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, a byte-for-byte copy of its ultralytics package made by
+              baseline/install_reference.py) on the host cores, on a bounded sample; `--impl reference` runs the same
+              on the full 16-image batch per step.
+  reference_gpu_eager  the same unmodified reference, PyTorch eager on this GPU, TF32 off and on (SURVEY.md section 0.1:
+              "the bar is PyTorch eager on the same B200").
 L2 hygiene: inputs rotate over a ring of sets much larger than the 126 MB L2 (see config.l2).
 """
 from __future__ import annotations
@@ -135,77 +138,148 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle's fp32 port (dense 25x25 conv like the reference) on the host cores
+# Reference arms.  The UNMODIFIED reference (baseline/_ref: a byte-for-byte copy of the reference's ultralytics package,
+# baseline/install_reference.py) is driven through its own public API -- torch.pow / F.mse_loss as in
+# models/yolo/detect/train.py:103,108 and lowlight_recovery.forward (nn/modules/llie.py:17-53) + autograd.  When the copy
+# is absent the oracle's fp32 port (same op mix) stands in and the line says kind = "port".
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_step(clean, g, weights, O, torch):
-    dark = O.synth_darken(clean, DARK_PARAM)
-    rec = O.recovery_mse(dark, clean)
-    y = O.recovery_forward(dark, weights, dense_blur=True)
-    (y * g).sum().backward()
-    return float(rec)
+WORKLOAD = ("configs[1]: lowlight_recovery fwd+bwd + recovery_loss, batch 16x3x640x640 fp32 synthetic per GPU "
+            "(synthesis clean**15 + mse, resize, predictor fwd, filter chain fwd, filter chain bwd, predictor bwd; "
+            "N > 1: + sum over ranks of the 164943 predictor gradients)")
+
+
+def shared_config(world: int):
+    """The part of `config` both arms print identically (the workload, not how an arm executes it)."""
+    return {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
+            "inputs": "clean = U[0,1) fp32 [16,3,640,640], cotangent g = N(0,1); module weights torch.manual_seed(0)",
+            "l2": "GPU arm: inputs rotate over a ring of 4 (clean, g) sets = 629 MB + 157 MB of outputs per step (L2 = 126 MB), "
+                  "no explicit flush; CPU arm: one 16-image set (157 MB, far beyond the host caches)"}
+
+
+def reference_step_fn(torch, device):
+    """Returns (step(clean, g) -> rec, kind).  One call = synthesis + recovery loss + module forward + backward."""
+    import torch.nn.functional as F
+    from baseline import reference_runtime as R
+    if R.available():
+        ns = R.load_modules()
+        torch.manual_seed(0)
+        m = ns.lowlight_recovery(3).to(device).train()
+
+        def step(clean, g):
+            for q in m.parameters():
+                q.grad = None
+            dark = torch.pow(clean, DARK_PARAM)          # train.py:103
+            rec = F.mse_loss(dark, clean)                # train.py:108
+            y = m(dark)                                  # llie.py:17-53
+            y.backward(g)
+            return rec
+        return step, "reference"
+    from oracle import lowlight_oracle as O
+    weights = {k: v.to(device) for k, v in O.cast_weights(O.init_weights(0), torch.float32, requires_grad=True).items()}
+
+    def step(clean, g):
+        for v in weights.values():
+            v.grad = None
+        dark = O.synth_darken(clean, DARK_PARAM)
+        rec = O.recovery_mse(dark, clean)
+        y = O.recovery_forward(dark, weights, dense_blur=True)
+        y.backward(g)
+        return rec
+    return step, "port"
+
+
+def cpu_inputs(torch, n):
+    gen = torch.Generator().manual_seed(1234)
+    return torch.rand(n, 3, H, W, generator=gen), torch.randn(n, 3, H, W, generator=gen)
 
 
 def cpu_baseline(sample_images: int, reps: int):
+    """The reference on the host cores, bounded: `reps` steps of `sample_images` images after one warm-up."""
     import torch
-    from oracle import lowlight_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    weights = O.cast_weights(O.init_weights(0), torch.float32, requires_grad=True)
-    gen = torch.Generator().manual_seed(1234)
-    clean = torch.rand(sample_images, 3, H, W, generator=gen)
-    g = torch.randn(sample_images, 3, H, W, generator=gen)
+    step, kind = reference_step_fn(torch, torch.device("cpu"))
+    clean, g = cpu_inputs(torch, sample_images)
     times = []
     for i in range(reps + 1):
-        for v in weights.values():
-            v.grad = None
         t0 = time.perf_counter()
-        cpu_step(clean, g, weights, O, torch)
+        step(clean, g)
         if i > 0 or reps == 0:
             times.append(time.perf_counter() - t0)
     t = statistics.median(times)
     return {
-        "value": sample_images / t, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"{sample_images} image(s) of the 16x3x640x640 workload per step (synthesis + fwd + bwd, fp32, "
-                  f"torch CPU, dense 25x25 blur as in the reference), median of {len(times)} after 1 warm-up",
+        "value": sample_images / t, "unit": UNIT, "cores": cores, "kind": kind,
+        "sample": f"{sample_images} image(s) of the 16x3x640x640 workload per step (pow + mse + lowlight_recovery fwd + bwd, fp32, "
+                  f"torch CPU, {cores} threads), median of {len(times)} after 1 warm-up",
     }, t
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python and cannot travel to
-    the GPU box) on all host cores.  Each step is a bounded sample (2 images) of the workload."""
+    """--impl reference: the unmodified reference on all host cores.  A timed step is the FULL configs[1] batch (16 images,
+    ~10-30 s on the box's cores); the W warm-up steps run on a 2-image sample (they only page the code and the allocator in),
+    so that the default driver invocation (--steps 20 --warmup 5) ends within minutes.  DEDARK_REF_SAMPLE=n overrides the
+    images per timed step.  Rank 0 only under torchrun."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from oracle import lowlight_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = 2
-    weights = O.cast_weights(O.init_weights(0), torch.float32, requires_grad=True)
-    gen = torch.Generator().manual_seed(1234)
-    clean = torch.rand(sample, 3, H, W, generator=gen)
-    g = torch.randn(sample, 3, H, W, generator=gen)
+    step, kind = reference_step_fn(torch, torch.device("cpu"))
+    sample = int(os.environ.get("DEDARK_REF_SAMPLE", B_PER_GPU))
+    clean, g = cpu_inputs(torch, B_PER_GPU)
     for _ in range(args.warmup):
-        cpu_step(clean, g, weights, O, torch)
+        step(clean[:2], g[:2])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        for v in weights.values():
-            v.grad = None
-        cpu_step(clean, g, weights, O, torch)
+        step(clean[:sample], g[:sample])
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
+    what = "full 16-image batch" if sample == B_PER_GPU else f"{sample}-image sample of the 16-image batch"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{sample}-image sample per step of configs[1] (16x3x640x640 fp32: synthesis + recovery "
-                               "loss + lowlight_recovery fwd + bwd), reference algorithm on host CPU"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} images per step x {args.steps} steps"},
+        "config": shared_config(max(1, args.gpus)),
+        "execution": f"{'unmodified reference (baseline/_ref)' if kind == 'reference' else 'oracle port'} on the host CPU, "
+                     f"{cores} torch threads, one process; {what} per timed step",
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{what} per step x {args.steps} steps (warm-up steps on 2 images)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def reference_gpu_eager(torch, dev, clean, g, steps=10):
+    """SURVEY.md section 0.1 / 8(d) timing (ii): the unmodified reference module, PyTorch eager, on THIS GPU -- the bar a
+    PyTorch user starts from.  TF32 off (parity-comparable) and on (cuDNN's default, ~1e-3 accurate).  CUDA events."""
+    from baseline import reference_runtime as R
+    if not R.available():
+        return {"unavailable": "baseline/_ref missing (run baseline/install_reference.py in the build container)"}
+    step, _ = reference_step_fn(torch, dev)
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, flag in (("tf32_off", False), ("tf32_on", True)):
+            torch.backends.cudnn.allow_tf32 = flag
+            torch.backends.cuda.matmul.allow_tf32 = flag
+            for _ in range(3):
+                step(clean, g)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step(clean, g)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": ms, "value": clean.shape[0] / (ms * 1e-3), "unit": UNIT}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    out["what"] = ("unmodified reference (baseline/_ref): torch.pow + F.mse_loss + lowlight_recovery fwd + autograd bwd, PyTorch "
+                   f"{torch.__version__} eager on this GPU, same 16x3x640x640 batch, CUDA events over {steps} steps after 3 warm-ups")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -353,6 +427,10 @@ def run_ours(args):
                 for k, s in enumerate(stages)}
     peak, peak_src = load_peaks()
     alg = {"filters_fwd": BYTES_FWD * B, "filters_bwd": BYTES_BWD * B, "synth": BYTES_SYNTH * B}
+    # whole-step fraction: the quantity the north star targets (22 806 528 B per image fwd+bwd at
+    # 640^2 = x + y + resize taps + g + x; + 9 830 400 B when the fp32 synthesis pass is counted) over the timed step
+    step_bytes = (BYTES_FWD + BYTES_RESIZE_TAPS + BYTES_BWD) * B
+    step_s = ms_per_step * 1e-3
     dominant = max(("filters_fwd", "filters_bwd"), key=lambda s: stage_us[s])
     achieved = alg[dominant] / (stage_us[dominant] * 1e-6) / 1e9
     roofline = {
@@ -364,6 +442,9 @@ def run_ours(args):
         "all_stages_us": stage_us,
         "frac_by_stage": {s: alg[s] / (stage_us[s] * 1e-6) / 1e9 / peak for s in alg},
         "frac_vs_nominal_8TBs": achieved / 8000.0,
+        "step_frac": step_bytes / step_s / 1e9 / peak,
+        "step_frac_with_synthesis_bytes": (step_bytes + BYTES_SYNTH * B) / step_s / 1e9 / peak,
+        "step_algorithmic_bytes": step_bytes, "step_target_frac": 0.70,
     }
 
     # ---- e2e: user-facing API, uint8 batch in pinned host memory, H2D + D2H inside the timed region
@@ -380,7 +461,7 @@ def run_ours(args):
             p.grad = None
         src = prefetch.get()                      # H2D of this step's batch (issued while the previous step ran)
         prefetch.submit(host_u8[(i + 1) % 2])     # next step's H2D overlaps this step's kernels
-        batch = dd.preprocess_batch({"img": src}, dev, dark_param=DARK_PARAM)
+        batch = dd.preprocess_batch({"img": src}, dev, dark_param=DARK_PARAM, dedark_FLAG=False)
         y = module(batch["img"])
         y.backward(gs[i % RING])
         flat = torch.cat([p.grad.reshape(-1) for p in params])
@@ -412,7 +493,7 @@ def run_ours(args):
             p.grad = None
         src = prefetch.get()
         prefetch.submit(host_u8[(i + 1) % 2])
-        batch = dd.preprocess_batch({"img": src}, dev, dark_param=DARK_PARAM)
+        batch = dd.preprocess_batch({"img": src}, dev, dark_param=DARK_PARAM, dedark_FLAG=False)
         y = module(batch["img"])
         y.backward(gs[i % RING])
         flat = torch.cat([p.grad.reshape(-1) for p in params])
@@ -519,25 +600,27 @@ def run_ours(args):
            "h2d_gbs_measured": h2d_gbs, "h2d_ms_per_step_alone": B * 3 * H * W / (h2d_gbs * 1e9) * 1e3}
 
     if rank == 0:
-        cpu = None
+        cpu, ref_gpu = None, None
         if not args.skip_cpu and world == 1:
             cpu, _ = cpu_baseline(sample_images=2, reps=3)
+            del pipe8, pf2, prefetch
+            torch.cuda.empty_cache()
+            try:
+                ref_gpu = reference_gpu_eager(torch, dev, cleans[0], gs[0])
+            except Exception as e:  # pragma: no cover
+                ref_gpu = {"unavailable": repr(e)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {
-                "workload": "configs[1]: lowlight_recovery fwd+bwd + recovery_loss, batch 16x3x640x640 fp32 synthetic per GPU "
-                            "(synthesis clean**15 + mse, resize, predictor fwd, fused filters fwd, fused filters bwd, predictor bwd"
-                            + (", all-reduce of 164943 grads)" if world > 1 else ")"),
+            "config": shared_config(world),
+            "execution": {
                 "gradient_exchange": exchange_how,
-                "global_batch": world * B, "parallelism": f"dp{world}", "launch": "cuda_graph" if use_graph else "eager",
+                "launch": "cuda_graph" if use_graph else "eager",
                 "pipelining": ("step n = predictor fwd, filters fwd, filters bwd, predictor bwd of batch n + synthesis/resize of batch n+1 on a "
                                "side stream under that predictor bwd (weight-independent data preparation); one synthesis per step")
                               if overlap else "none: the stages of a batch run back to back on one stream",
                 "without_pipelining": {"ms_per_step": ms_plain / args.steps, "value": world * B * args.steps / (ms_plain * 1e-3)},
-                "l2": f"inputs rotate over a ring of {RING} (clean, g) sets = {RING * 2 * B * 3 * H * W * 4 / 1e6:.0f} MB + "
-                      f"{2 * B * 3 * H * W * 4 / 1e6:.0f} MB of outputs per step (L2 = 126 MB); no explicit flush",
                 "e2e_input": "uint8 batch (train.py:72) in pinned host memory",
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
@@ -545,6 +628,8 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if ref_gpu is not None:
+            line["reference_gpu_eager"] = ref_gpu
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

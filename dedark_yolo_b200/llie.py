@@ -20,6 +20,8 @@ Behaviour kept from the reference:
 """
 from __future__ import annotations
 
+import copy
+
 import torch
 import torch.nn as nn
 
@@ -41,10 +43,21 @@ class ConvBlock(nn.Module):
         )
 
 
-class ExtractParameters2(nn.Module):
-    """Parameter holder for the predictor CNN (common.py:52-66): 3->16->32->32->32->32, fc 2048->64->15."""
+def ordered_parameters(extractor: nn.Module):
+    """The 14 tensors of a predictor in state-dict order (the order of ``dd_predictor_tensors``).  Works on this package's
+    ``ExtractParameters2`` and on the reference's (a checkpoint written while installed holds reference children)."""
+    out = []
+    for blk in extractor.conv_layers:
+        out += [blk.conv_block[0].weight, blk.conv_block[0].bias]
+    return out + [extractor.fc1.weight, extractor.fc1.bias, extractor.fc2.weight, extractor.fc2.bias]
 
-    def __init__(self):
+
+class ExtractParameters2(nn.Module):
+    """Parameter holder for the predictor CNN (common.py:52-66): 3->16->32->32->32->32, fc 2048->64->15.
+    ``cfg`` is accepted for signature parity with the reference (common.py:53) and ignored: the filter configuration is
+    frozen into the kernels (filter_cfg.py:17-44)."""
+
+    def __init__(self, cfg=None):
         super().__init__()
         self.output_dim = 15
         self.channels = 16
@@ -55,11 +68,7 @@ class ExtractParameters2(nn.Module):
         self.fc2 = nn.Linear(64, self.output_dim)
 
     def ordered_parameters(self):
-        """The 14 tensors in state-dict order (the order of ``dd_predictor_tensors``)."""
-        out = []
-        for blk in self.conv_layers:
-            out += [blk.conv_block[0].weight, blk.conv_block[0].bias]
-        return out + [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias]
+        return ordered_parameters(self)
 
     def forward(self, r):
         """[B,3,256,256] -> [B,15] through the CUDA predictor (inference helper; no autograd)."""
@@ -90,19 +99,49 @@ class lowlight_recovery(nn.Module):
         self.extractor = ExtractParameters2()
         self.filters = nn.ModuleList(_FilterSlot(n) for n in FILTER_ORDER)
 
-    def _compute_device(self, x):
-        if x.is_cuda:
-            return x.device
-        if not torch.cuda.is_available():
-            raise RuntimeError(
-                "lowlight_recovery (dedark_yolo_b200): no CUDA device available -- this build has no CPU fallback")
-        p = next(self.parameters())
-        return p.device if p.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    def _tensors(self):
+        """The 14 parameters in state-dict order through plain dict look-ups (no nn.Module.__getattr__: 2 us instead of 30)."""
+        ex = self._modules["extractor"]._modules
+        out = []
+        for blk in ex["conv_layers"]._modules.values():
+            c = blk._modules["conv_block"]._modules["0"]._parameters
+            out.append(c["weight"])
+            out.append(c["bias"])
+        f1, f2 = ex["fc1"]._parameters, ex["fc2"]._parameters
+        out += [f1["weight"], f1["bias"], f2["weight"], f2["bias"]]
+        return out
 
     def forward(self, x, dedark_A=None, IcA=None):
         from . import ops
         ops.check_image_shape(x)
-        if x.is_cuda and any(p.device != x.device for p in self.parameters()):
-            self.to(x.device)  # llie.py:28: the module follows its input (a no-op traversal is skipped: 0.2 ms of host time)
-        dev = self._compute_device(x)
-        return ops.RecoveryFunction.apply(dev, x, dedark_A, IcA, *self.extractor.ordered_parameters())
+        params = self._tensors()
+        pdev = params[-1].device
+        if x.is_cuda:
+            if pdev != x.device:
+                self.to(x.device)  # llie.py:28: the module follows its input (the no-op traversal is skipped: 0.2 ms of host time)
+                params = self._tensors()
+            dev = x.device
+        else:
+            if not torch.cuda.is_available():
+                raise RuntimeError(
+                    "lowlight_recovery (dedark_yolo_b200): no CUDA device available -- this build has no CPU fallback")
+            dev = pdev if pdev.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        return ops.RecoveryFunction.apply(self, dev, x, dedark_A, IcA, *params)
+
+    # -- copies and checkpoints ----------------------------------------------------------------------------------------------
+    def __deepcopy__(self, memo):
+        """Plain deep copy (ModelEMA, torch_utils.py:353; save_model, trainer.py:413): never goes through ``__reduce_ex__``."""
+        new = type(self).__new__(type(self))
+        memo[id(self)] = new
+        new.__dict__.update(copy.deepcopy(self.__dict__, memo))
+        return new
+
+    def __reduce_ex__(self, protocol):
+        """While ``integrate.install()`` is active the module pickles itself as a genuine reference module under the
+        reference's qualified class name (see integrate.py, "Checkpoints"): ultralytics checkpoints hold whole objects
+        (trainer.py:408-433), and one written with the drop-in must load in a vanilla Dedark-YOLO process."""
+        from . import integrate
+        if integrate.installed() and type(self) is lowlight_recovery:
+            import copyreg
+            return copyreg.__newobj__, (type(self),), integrate.export_reference_module(self).__dict__
+        return super().__reduce_ex__(protocol)

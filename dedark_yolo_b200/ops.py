@@ -7,6 +7,7 @@ no CPU path).
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Sequence
 
 import torch
@@ -209,37 +210,156 @@ def check_image_shape(x: torch.Tensor) -> None:
         raise RuntimeError(f"reflect padding of 12 needs H, W > 12, got {H} x {W} (filtersB.py:167)")
 
 
+# ---- the module's autograd node ---------------------------------------------------------------------------------------
+_SIZES = (432, 16, 4608, 32, 9216, 32, 9216, 32, 9216, 32, 131072, 64, 960, 15)   # the 14 tensors, state-dict order
+_SHAPES = ((16, 3, 3, 3), (16,), (32, 16, 3, 3), (32,), (32, 32, 3, 3), (32,), (32, 32, 3, 3), (32,), (32, 32, 3, 3), (32,),
+           (64, 2048), (64,), (15, 64), (15,))
+_OFFS = tuple(sum(_SIZES[:k]) for k in range(15))
+_MAX_PLANS = 4
+
+
+class _Plan:
+    """Buffers of one (device, B, H, W) call shape of one module instance, reused from call to call so that a forward +
+    backward costs a handful of C-ABI calls and two allocations (y and the flat gradient) of host work.  ``version``
+    counts the forwards that have written the activation buffers: a backward whose forward is no longer the latest one
+    (two forwards before a backward) recomputes resize + predictor forward first -- correctness never depends on the cache."""
+    __slots__ = ("r", "acts", "feat", "dfeat", "ws_pb", "ws_rb", "version", "wkey", "w", "tick")
+
+    def __init__(self, dev, B, H, W):
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.r = torch.empty(B, 3, RESIZE, RESIZE, **f32)
+        self.acts = torch.empty(_lib.workspace_bytes(_lib.WS_PREDICTOR_ACTS, B) // 4, **f32)
+        self.feat = torch.empty(B, NUM_FEATURES, **f32)
+        self.dfeat = torch.empty(B, NUM_FEATURES, **f32)
+        self.ws_pb = self.ws_rb = None   # allocated by the first backward (inference never needs them)
+        self.version = 0
+        self.wkey, self.w = None, None
+        self.tick = 0
+
+
+_PLANS = weakref.WeakKeyDictionary()   # module instance -> {(device index, B, H, W): _Plan}
+_TICK = [0]
+
+
+def _plan_for(owner, dev, B, H, W) -> _Plan:
+    plans = _PLANS.get(owner)
+    if plans is None:
+        plans = _PLANS[owner] = {}
+    key = (dev.index, B, H, W)
+    pl = plans.get(key)
+    if pl is None:
+        if len(plans) >= _MAX_PLANS:   # drop the least recently used shape (validation batches, ragged last batches)
+            del plans[min(plans, key=lambda k: plans[k].tick)]
+        with torch.cuda.device(dev):
+            pl = plans[key] = _Plan(dev, B, H, W)
+    _TICK[0] += 1
+    pl.tick = _TICK[0]
+    return pl
+
+
+def _weights_struct(pl: _Plan, pd):
+    key = tuple(t.data_ptr() for t in pd)
+    if pl.wkey != key:
+        pl.wkey, pl.w = key, PredictorTensors.from_tensors(pd)
+    return pl.w
+
+
+def _grad_struct(base_ptr: int) -> PredictorTensors:
+    g = PredictorTensors()
+    for i in range(5):
+        g.conv_w[i] = base_ptr + 4 * _OFFS[2 * i]
+        g.conv_b[i] = base_ptr + 4 * _OFFS[2 * i + 1]
+    g.fc1_w, g.fc1_b, g.fc2_w, g.fc2_b = (base_ptr + 4 * _OFFS[k] for k in (10, 11, 12, 13))
+    return g
+
+
+def _ready(t: torch.Tensor, dev) -> bool:
+    return t.device == dev and t.dtype == torch.float32 and t.is_contiguous()
+
+
 class RecoveryFunction(torch.autograd.Function):
     """lowlight_recovery.forward as one autograd node: resize -> predictor -> fused filter chain.
 
     Inputs may live on the CPU (DetectionModel.__init__ probes the model with CPU zeros, nn/tasks.py:290-291):
     they are staged through ``device`` and the result is returned on x's device.  The work itself always runs on
-    the GPU through the C-ABI."""
+    the GPU through the C-ABI.  ``owner`` (the module instance) keys the buffer cache, see ``_Plan``."""
 
     @staticmethod
-    def forward(ctx, device, x, A, IcA, *params):
+    def forward(ctx, owner, device, x, A, IcA, *params):
+        # the reference propagates gradients into dedark_A / IcA through DeDarkFilter (filtersB.py:211-214); no caller of the
+        # module asks for them (they are data, train.py:95-96) and the fused backward does not produce them: refuse loudly
+        # rather than return a silent None
+        if (A is not None and A.requires_grad) or (IcA is not None and IcA.requires_grad):
+            raise NotImplementedError("lowlight_recovery (dedark_yolo_b200): gradients w.r.t. dedark_A / IcA are not implemented; "
+                                      "detach them (the reference trainer passes constants)")
         out_dev = x.device
-        xd = _f32c(x.to(device))
-        Ad = None if A is None else _f32c(A.to(device)).reshape(xd.shape[0], 3)
-        Id = None if IcA is None else _f32c(IcA.to(device)).expand(xd.shape[0], 1, xd.shape[2], xd.shape[3]).contiguous()
-        pd = [_f32c(p.to(device)) for p in params]
-        r = resize256(xd)
-        feat, acts = predictor_forward(r, pd)
-        y = filters_forward(xd, feat, Ad, Id)
-        ctx.save_for_backward(xd, Ad, Id, r, acts, feat, *pd)
+        xd = x.detach() if _ready(x, device) else _f32c(x.to(device))
+        B, _, H, W = xd.shape
+        Ad = None if A is None else _f32c(A.to(device)).reshape(B, 3)
+        Id = None if IcA is None else _f32c(IcA.to(device)).expand(B, 1, H, W).contiguous()
+        pd = [q.detach() if _ready(q, device) else _f32c(q.to(device)) for q in params]
+        pl = _plan_for(owner, device, B, H, W)
+        prev = torch.cuda.current_device()
+        if prev != device.index:  # kernels launch on the current device: switch for the duration of the call only
+            torch.cuda.set_device(device)
+        try:
+            st = _stream(device)
+            w = _weights_struct(pl, pd)
+            y = torch.empty_like(xd)
+            check(lib.dd_resize256(_ptr(xd), _ptr(pl.r), B, H, W, st))
+            check(lib.dd_predictor_fwd(_ptr(pl.r), C.byref(w), _ptr(pl.acts), _ptr(pl.feat), B, st))
+            check(lib.dd_recovery_fwd(_ptr(xd), _ptr(Ad), _ptr(Id), _ptr(pl.feat), _ptr(y), B, H, W, st))
+        finally:
+            if prev != device.index:
+                torch.cuda.set_device(prev)
+        pl.version += 1
+        ctx.plan, ctx.version, ctx.st_dev = pl, pl.version, device
+        ctx.save_for_backward(xd, Ad, Id, *pd)
         ctx.out_dev = out_dev
-        ctx.param_devs = [(p.device, p.dtype) for p in params]
-        return y.to(out_dev)
+        ctx.param_meta = None if all(q.device == device and q.dtype == torch.float32 for q in params) \
+            else [(q.device, q.dtype) for q in params]
+        return y if out_dev == device else y.to(out_dev)
 
     @staticmethod
     def backward(ctx, g):
-        xd, Ad, Id, r, acts, feat, *pd = ctx.saved_tensors
-        need_dx = ctx.needs_input_grad[1]
-        gd = _f32c(g.to(xd.device))
-        dfeat, dx = filters_backward(xd, feat, gd, Ad, Id, need_dx)
-        grads, dr = predictor_backward(r, pd, acts, dfeat, need_dr=need_dx)
+        xd, Ad, Id, *pd = ctx.saved_tensors
+        pl, dev = ctx.plan, ctx.st_dev
+        B, _, H, W = xd.shape
+        need_dx = ctx.needs_input_grad[2]
+        gd = g if _ready(g, dev) else _f32c(g.to(dev))
+        prev = torch.cuda.current_device()
+        if prev != dev.index:
+            torch.cuda.set_device(dev)
+        try:
+            return RecoveryFunction._backward(ctx, pl, dev, xd, Ad, Id, pd, gd, need_dx, B, H, W)
+        finally:
+            if prev != dev.index:
+                torch.cuda.set_device(prev)
+
+    @staticmethod
+    def _backward(ctx, pl, dev, xd, Ad, Id, pd, gd, need_dx, B, H, W):
+        st = _stream(dev)
+        w = _weights_struct(pl, pd)
+        if pl.version != ctx.version:  # another forward of this shape ran in between: its activations replaced ours
+            check(lib.dd_resize256(_ptr(xd), _ptr(pl.r), B, H, W, st))
+            check(lib.dd_predictor_fwd(_ptr(pl.r), C.byref(w), _ptr(pl.acts), _ptr(pl.feat), B, st))
+            pl.version += 1
+            ctx.version = pl.version
+        if pl.ws_pb is None:
+            pl.ws_pb = torch.empty(_lib.workspace_bytes(_lib.WS_PREDICTOR_BWD, B), dtype=torch.uint8, device=dev)
+            pl.ws_rb = torch.empty(_lib.workspace_bytes(_lib.WS_RECOVERY_BWD, B, H, W), dtype=torch.uint8, device=dev)
+        flat = torch.empty(_OFFS[14], dtype=torch.float32, device=dev)
+        dx = torch.empty_like(xd) if need_dx else None
+        dr = torch.empty_like(pl.r) if need_dx else None
+        check(lib.dd_recovery_bwd(_ptr(xd), _ptr(Ad), _ptr(Id), _ptr(pl.feat), _ptr(gd), _ptr(pl.dfeat), _ptr(dx), B, H, W,
+                                  _ptr(pl.ws_rb), pl.ws_rb.numel(), st))
+        gs = _grad_struct(flat.data_ptr())
+        check(lib.dd_predictor_bwd(_ptr(pl.r), C.byref(w), _ptr(pl.acts), _ptr(pl.dfeat), C.byref(gs), _ptr(dr), B, _ptr(pl.ws_pb),
+                                   pl.ws_pb.numel(), st))
         if need_dx:
-            resize256_backward_(dr, dx)
+            check(lib.dd_resize256_bwd(_ptr(dr), _ptr(dx), B, H, W, st))
             dx = dx.to(ctx.out_dev)
-        grads = [gr.to(device=d, dtype=t) for gr, (d, t) in zip(grads, ctx.param_devs)]
-        return (None, dx, None, None, *grads)
+        grads = [t.view(sh) for t, sh in zip(flat.split(_SIZES), _SHAPES)]
+        if ctx.param_meta is not None:
+            grads = [gr.to(device=d, dtype=t) for gr, (d, t) in zip(grads, ctx.param_meta)]
+        return (None, None, dx, None, None, *grads)

@@ -23,7 +23,7 @@ import torch
 
 from . import _lib
 from ._lib import PredictorTensors, check, lib
-from .llie import lowlight_recovery
+from .llie import lowlight_recovery, ordered_parameters
 
 
 def _p(t):
@@ -42,7 +42,7 @@ class RecoveryPipeline:
         # uint8 sources: the fp32 clean image (train.py:72, ``batch["clean_img"]``) is only an operand of the recovery loss, which
         # the synthesis pass has already reduced -- it is materialised (one more full-size write) only on request
         self.keep_clean = keep_clean
-        self.params = [q.detach() for q in module.extractor.ordered_parameters()]
+        self.params = [q.detach() for q in ordered_parameters(module.extractor)]
         for q in self.params:
             assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous()
         f32 = dict(dtype=torch.float32, device=dev)

@@ -21,6 +21,9 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("DEDARK_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "ultralytics")):
+    # the byte-for-byte copy made by baseline/install_reference.py (git-ignored; it travels to the GPU box)
+    REFERENCE_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 _MODULES_DIR = os.path.join(REFERENCE_ROOT, "ultralytics", "nn", "modules")
 _PKG = "_dedark_reference_modules"
 

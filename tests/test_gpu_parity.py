@@ -136,14 +136,17 @@ def test_synth_host_lut_reproduces_reference_cpu_bits(ops):
 def test_preprocess_batch_and_offline_darkener(dd):
     s = load_golden("synth.npz")
     u8 = torch.from_numpy(s["u8"])
-    batch = dd.preprocess_batch({"img": u8.clone()}, "cuda", dark_param=15.0)
+    batch = dd.preprocess_batch({"img": u8.clone()}, "cuda", dark_param=15.0, dedark_FLAG=False)
     assert set(batch) >= {"img", "clean_img", "recovery_loss_batch"}
     assert torch.equal(batch["clean_img"], u8.cuda().float() / 255)  # the reference's bits when it runs on CUDA
     assert torch.equal(batch["img"], torch.pow(u8.cuda().float() / 255, 15.0))
     assert batch["recovery_loss_batch"].ndim == 0 and not batch["recovery_loss_batch"].requires_grad
     assert abs(float(batch["recovery_loss_batch"]) - float(s["mse_15.0"])) <= 2e-6 * float(s["mse_15.0"])
-    b2 = dd.preprocess_batch({"img": u8.clone()}, "cuda", dark_param=15.0, dedark_FLAG=True)
+    b2 = dd.preprocess_batch({"img": u8.clone()}, "cuda", dark_param=15.0)  # defaults = cfg/default.yaml:32-34 (dedark branch)
     assert b2["img"] is b2["clean_img"] and float(b2["recovery_loss_batch"]) == 0.0
+    assert torch.equal(b2["img"], batch["img"]) and b2["dedark_A"] is None and b2["IcA"] is None
+    with pytest.raises(TypeError):
+        dd.preprocess_batch({"img": torch.rand(1, 3, 16, 16)}, "cuda")  # train.py:72 would divide a [0,1] image by 255
     b3 = dd.preprocess_batch({"img": u8.clone()}, "cuda", lowlight_FLAG=False)
     assert torch.equal(b3["img"], u8.cuda().float() / 255) and float(b3["recovery_loss_batch"]) == 0.0
     lut, _ = ops_tables(7.5)
@@ -388,13 +391,35 @@ def test_host_batch_prefetcher_overlapped_copies_are_exact(dd):
         src = pf.get()
         if i + 1 < 5:
             pf.submit(host[i + 1])
-        batch = dd.preprocess_batch({"img": src}, "cuda", dark_param=5.0)
+        batch = dd.preprocess_batch({"img": src}, "cuda", dark_param=5.0, dedark_FLAG=False)
         outs.append(batch["clean_img"].clone())
     torch.cuda.synchronize()
     for i in range(5):
         assert torch.equal(outs[i], host[i].cuda().float() / 255), f"batch {i}"  # the reference's expression on this GPU
     with pytest.raises(RuntimeError):
         pf.get()  # nothing outstanding
+
+
+def test_host_batch_prefetcher_never_overwrites_the_batch_in_use(dd):
+    """get(); submit(); submit() with two slots must not copy into the buffer the consumer still reads."""
+    gen = torch.Generator().manual_seed(8)
+    host = [torch.randint(0, 256, (4, 3, 256, 256), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(3)]
+    pf = dd.HostBatchPrefetcher("cuda", depth=2)
+    pf.submit(host[0])
+    cur = pf.get()
+    pf.submit(host[1])
+    with pytest.raises(RuntimeError):
+        pf.submit(host[2])           # slot 0 is held by the consumer, slot 1 is outstanding
+    torch.cuda.synchronize()
+    assert torch.equal(cur.cpu(), host[0])
+    pf.release()                     # explicit end of use: the slot may be refilled now
+    pf.submit(host[2])
+    assert torch.equal(pf.get().cpu(), host[1]) and torch.equal(pf.get().cpu(), host[2])
+    # three slots: two copies may run ahead of the batch in use
+    pf3 = dd.HostBatchPrefetcher("cuda", depth=3)
+    pf3.submit(host[0]); a = pf3.get(); pf3.submit(host[1]); pf3.submit(host[2])
+    torch.cuda.synchronize()
+    assert torch.equal(a.cpu(), host[0])
 
 
 def test_predictor_is_bit_reproducible(ops):
@@ -469,7 +494,7 @@ def test_config4_synthesis_and_inference_1280_batch32(dd, p):
     B, H, W = 32, 1280, 1280
     gen = torch.Generator(device="cuda").manual_seed(2024)
     u8 = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=gen, device="cuda")
-    batch = dd.preprocess_batch({"img": u8}, "cuda", dark_param=p)
+    batch = dd.preprocess_batch({"img": u8}, "cuda", dark_param=p, dedark_FLAG=False)
     clean_ref = u8.float() / 255                                  # train.py:72 on this GPU
     assert torch.equal(batch["clean_img"].view(torch.int32), clean_ref.view(torch.int32))
     dark_ref = torch.pow(clean_ref, p)                            # train.py:103
