@@ -17,7 +17,7 @@ SRC_U8, SRC_F32 = 0, 1
 EXPORTS = (
     "dd_version", "dd_last_error", "dd_launch_count", "dd_workspace_bytes", "dd_synth_fwd", "dd_resize256",
     "dd_resize256_bwd", "dd_predictor_fwd", "dd_predictor_bwd", "dd_recovery_fwd", "dd_recovery_bwd",
-    "dd_synth_resize_fwd", "dd_synth_resize_supported", "dd_predictor_bwd_allreduce", "dd_exchange_bytes",
+    "dd_synth_resize_fwd", "dd_synth_resize_supported", "dd_predictor_bwd_allreduce", "dd_debug_blur_tc", "dd_exchange_bytes",
 )
 MAX_PEERS = 8
 
@@ -76,6 +76,7 @@ def _load():
     lib.dd_synth_resize_supported.argtypes = [i, i]
     lib.dd_predictor_bwd_allreduce.argtypes = [vp, C.POINTER(PredictorTensors), vp, vp, C.POINTER(PredictorTensors), i, vp, sz,
                                                C.POINTER(PeerExchange), vp]
+    lib.dd_debug_blur_tc.argtypes = [vp, vp, i, i, i, i, vp]
     lib.dd_exchange_bytes.restype = sz
     lib.dd_exchange_bytes.argtypes = []
     for name in EXPORTS[4:-1]:

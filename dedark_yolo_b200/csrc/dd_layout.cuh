@@ -122,9 +122,10 @@ __host__ __device__ inline long long sched_begin(const Sched& s, int c) { return
 // backward workspace: [G + nPS][kBwdSums] floats of partial sums -- slot (c + ps) belongs to the pair (CTA c,
 // plane-strip ps), which is injective because CTA ranges are ordered -- then [B*3][H][strips] floats of
 // per-row partial sums S (the row-coupled contrast term).
+// (the tensor-core variant keeps four row sums per (row, strip), one per 32-column quarter; the workspace covers both)
 inline size_t recovery_bwd_ws_bytes(int B, int H, int W) {
     const Sched s = make_sched(B, H, W);
-    return ((size_t)(s.G + s.nPS) * kBwdSums + (size_t)B * 3 * H * s.strips) * sizeof(float);
+    return ((size_t)(s.G + s.nPS) * kBwdSums + (size_t)B * 3 * H * s.strips * 4) * sizeof(float);
 }
 
 }  // namespace dd

@@ -320,6 +320,13 @@ inline int set_smem(K kernel, size_t bytes) {
     return DD_OK;
 }
 
+// DEDARK_BLUR=cc selects the CUDA-core (FFMA2) blur kernels; default: the tensor-core kernels (dd_blur_tc.cuh) whenever the
+// rows are 16-byte aligned (W % 4 == 0).  Read on every call so that tests can compare the two paths in one process.
+inline bool blur_on_tensor_cores() {
+    const char* e = getenv("DEDARK_BLUR");
+    return !(e && e[0] == 'c' && e[1] == 'c');
+}
+
 inline bool precise_mode() {  // DEDARK_PRECISE=1: powf/log2f instead of the MUFU pow (debugging aid, read once)
     static const bool v = [] { const char* e = getenv("DEDARK_PRECISE"); return e && e[0] == '1'; }();
     return v;

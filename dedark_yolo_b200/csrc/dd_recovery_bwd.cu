@@ -120,6 +120,10 @@ __device__ __forceinline__ float px_bwd(float x0, float ica, float g5, float bt,
     return g1 * inv;
 }
 
+}  // namespace dd
+#include "dd_recovery_tc_bwd.cuh"  // the tensor-core variant (uses px_bwd / BwdAcc above)
+namespace dd {
+
 // TMA: the g halo tile of every row-block arrives as two 16-row x 156-column boxes (cp.async.bulk.tensor through a tensor
 // map of the [planes][H][W] cotangent; everything outside the image is zero-filled by the copy engine), issued by one
 // thread and counted on an mbarrier: no per-thread address arithmetic, no staging instructions at all.
@@ -413,14 +417,14 @@ __global__ void __launch_bounds__(kFinThreads)
 recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restrict__ A,
                              const float* __restrict__ IcA, const float* __restrict__ feat,
                              const float* __restrict__ part, const float* __restrict__ Spart,
-                             float* __restrict__ dfeat, float* __restrict__ dx, int B, int H, int W) {
+                             float* __restrict__ dfeat, float* __restrict__ dx, int B, int H, int W, int ctas, int nsp) {
     pdl_begin();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ ImgParams sp;
     __shared__ double s_red[kFinThreads / 32][7];
     const int tid = threadIdx.x, b = blockIdx.x / kFinCluster, crank = (int)cluster.block_rank();
-    const Sched sc = make_sched(B, H, W);
+    const Sched sc = make_sched(B, H, W, ctas);  // the work list of the kernel that produced the partials (ctas CTAs, nsp row sums per row)
     const int rows_per = (3 * H + kFinCluster - 1) / kFinCluster, row_lo = crank * rows_per, row_hi = min(3 * H, row_lo + rows_per);
     if (tid < 32) regress_warp(feat + b * kFeat, sp);
     double dp = 0, dc = 0, dg = 0, dw = 0, ds[3] = {0, 0, 0};
@@ -436,7 +440,7 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
             S[e] = 0.f;
             if (i < row_hi) {
                 const int ch = i / H, row = i - ch * H, plane = 3 * b + ch;
-                for (int st = 0; st < sc.strips; ++st) S[e] += Spart[((size_t)plane * H + row) * sc.strips + st];
+                for (int st = 0; st < nsp; ++st) S[e] += Spart[((size_t)plane * H + row) * nsp + st];
                 const size_t off = ((size_t)plane * H + row) * W;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -563,9 +567,29 @@ static int launch_bwd4(const CUtensorMap& gmap, const float* x, const float* A, 
     return DD_OK;
 }
 
+// tensor-core variant: 148 persistent CTAs, 3xTF32 (fp32 gates).  Same workspace, same finalize kernel.
+template <bool HAS_ICA, bool FAST>
+static int launch_bwd_tc(const float* x, const float* A, const float* IcA, const float* feat, const float* g, float* dfeat,
+                         float* dx, int B, int H, int W, float* ws, cudaStream_t st) {
+    constexpr int R = 48;
+    constexpr bool X3 = true;
+    const Sched sc = make_sched(B, H, W, btc::kSchedCtasTC);
+    float* part = ws;
+    float* Spart = part + (size_t)(sc.G + sc.nPS) * kBwdSums;
+    auto kern = btc::recovery_bwd_tc_kernel<R, X3, HAS_ICA, FAST>;
+    constexpr size_t smem = btc::Lay<R, X3>::SMEM;
+    DD_ENSURE_SMEM(kern, smem, "recovery_bwd_tc_kernel");
+    launch_pdl(kern, dim3(sc.G), dim3(btc::kThreadsTC), smem, st, x, A, IcA, feat, g, part, Spart, dx, B, H, W);
+    launch_pdl_cluster(recovery_bwd_finalize_kernel<HAS_ICA, FAST>, dim3(B * kFinCluster), dim3(kFinThreads), 0, st, kFinCluster, x, A, IcA, feat,
+                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W, sc.G, sc.strips * btc::kSpartPerStrip);
+    count_launch(2);
+    return check_launch("dd_recovery_bwd (tensor-core blur)");
+}
+
 template <bool HAS_ICA, bool FAST, bool ALIGNED>
 static int launch_bwd3(const float* x, const float* A, const float* IcA, const float* feat, const float* g, float* dfeat,
                        float* dx, int B, int H, int W, float* ws, cudaStream_t st) {
+    if (ALIGNED && blur_on_tensor_cores()) return launch_bwd_tc<HAS_ICA, FAST>(x, A, IcA, feat, g, dfeat, dx, B, H, W, ws, st);
     const Sched sc = make_sched(B, H, W);
     float* part = ws;
     float* Spart = part + (size_t)(sc.G + sc.nPS) * kBwdSums;
@@ -577,7 +601,7 @@ static int launch_bwd3(const float* x, const float* A, const float* IcA, const f
                     : launch_bwd4<HAS_ICA, FAST, ALIGNED, false>(gmap, x, A, IcA, feat, g, part, Spart, dx, B, H, W, sc, st))
         return e;
     launch_pdl_cluster(recovery_bwd_finalize_kernel<HAS_ICA, FAST>, dim3(B * kFinCluster), dim3(kFinThreads), 0, st, kFinCluster, x, A, IcA, feat,
-                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W);
+                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W, sc.G, sc.strips);
     count_launch(2);
     return check_launch("dd_recovery_bwd");
 }

@@ -22,6 +22,7 @@
 
 #include "dd_async.cuh"
 #include "dd_recovery.cuh"
+#include "dd_recovery_tc_fwd.cuh"
 
 namespace dd {
 
@@ -285,9 +286,31 @@ static int launch_fwd4(const CUtensorMap& xmap, const CUtensorMap& xmap16, const
     return DD_OK;
 }
 
+// tensor-core variant: 148 persistent CTAs, 3xTF32 (fp32 gate 1e-5)
+template <bool HAS_ICA, bool FAST, bool DBG>
+static int launch_fwd_tc(const float* x, const float* A, const float* IcA, const float* feat, float* y, int B, int H, int W,
+                         bool x3, cudaStream_t st) {
+    constexpr int R = 48;
+    const Sched sc = make_sched(B, H, W, btc::kSchedCtasTC);
+    if (x3) {
+        auto kern = btc::recovery_fwd_tc_kernel<R, true, HAS_ICA, FAST, DBG>;
+        constexpr size_t smem = btc::Lay<R, true>::SMEM;
+        DD_ENSURE_SMEM(kern, smem, "recovery_fwd_tc_kernel");
+        launch_pdl(kern, dim3(sc.G), dim3(btc::kThreadsTC), smem, st, x, A, IcA, feat, y, B, H, W);
+    } else {
+        auto kern = btc::recovery_fwd_tc_kernel<R, false, HAS_ICA, FAST, DBG>;
+        constexpr size_t smem = btc::Lay<R, false>::SMEM;
+        DD_ENSURE_SMEM(kern, smem, "recovery_fwd_tc_kernel (1xTF32)");
+        launch_pdl(kern, dim3(sc.G), dim3(btc::kThreadsTC), smem, st, x, A, IcA, feat, y, B, H, W);
+    }
+    count_launch();
+    return check_launch("dd_recovery_fwd (tensor-core blur)");
+}
+
 template <bool HAS_ICA, bool FAST, bool ALIGNED>
 static int launch_fwd3(const float* x, const float* A, const float* IcA, const float* feat, float* y, int B, int H,
                        int W, cudaStream_t st) {
+    if (ALIGNED && blur_on_tensor_cores()) return launch_fwd_tc<HAS_ICA, FAST, false>(x, A, IcA, feat, y, B, H, W, true, st);
     const Sched sc = make_sched(B, H, W);
     CUtensorMap xmap, xmap16;
     memset(&xmap, 0, sizeof(xmap));
@@ -312,6 +335,15 @@ static int launch_fwd2(const float* x, const float* A, const float* IcA, const f
 }
 
 }  // namespace dd
+
+// unit-test hook: the bare reflect-padded 25x25 Gaussian (filtersB.py:154-175: F.pad reflect + conv2d) of x through the
+// tensor-core engine, x3 != 0: 3xTF32, else 1xTF32.  Needs W % 4 == 0 and 16-byte aligned x.
+extern "C" int dd_debug_blur_tc(const float* x, float* y, int B, int H, int W, int x3, void* stream_) {
+    using namespace dd;
+    if (int e = check_recovery_shape("dd_debug_blur_tc", B, H, W)) return e;
+    DD_REQUIRE(x && y && x != y && (W & 3) == 0 && ((uintptr_t)x & 15) == 0, DD_ERR_INVALID, "dd_debug_blur_tc: W %% 4 == 0 and aligned x required");
+    return launch_fwd_tc<false, true, true>(x, nullptr, nullptr, x /* feat: unused */, y, B, H, W, x3 != 0, (cudaStream_t)stream_);
+}
 
 extern "C" int dd_recovery_fwd(const float* x, const float* A, const float* IcA, const float* feat, float* y, int B,
                                int H, int W, void* stream_) {

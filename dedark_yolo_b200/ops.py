@@ -188,6 +188,17 @@ def filters_backward(x, feat, g, A=None, IcA=None, need_dx: bool = False):
     return dfeat, dx
 
 
+def debug_blur_tc(x: torch.Tensor, x3: bool = True) -> torch.Tensor:
+    """Unit-test hook: the reflect-padded 25x25 Gaussian of ``x`` through the tensor-core engine (``dd_debug_blur_tc``)."""
+    _need_cuda(x)
+    x = _f32c(x)
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.dd_debug_blur_tc(_ptr(x), _ptr(y), B * Cc // 3, H, W, int(bool(x3)), _stream(x.device)))
+    return y
+
+
 def resize256_backward_(dr: torch.Tensor, dx: torch.Tensor) -> None:
     """dx += resize^T(dr), in place."""
     B, _, H, W = dx.shape

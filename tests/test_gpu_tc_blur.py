@@ -1,0 +1,95 @@
+"""GPU tests of the tensor-core blur engine (csrc/dd_blur_tc.cuh): the 25x25 reflect-padded Gaussian of the USM filter
+(nn/modules/filtersB.py:154-175) and its adjoint as banded-Toeplitz tcgen05 GEMMs.
+
+  * the bare blur (``dd_debug_blur_tc``) against an fp64 separable Gaussian: 3xTF32 (fp32 mode) and 1xTF32 (bf16 mode);
+  * the fused forward / backward kernels on the tensor cores (the default for 16-byte aligned rows) against the CUDA-core
+    (FFMA2) kernels selected with DEDARK_BLUR=cc, and both against the fp64 oracle, including caller-supplied A / IcA, dx,
+    image borders inside a strip and strips narrower than 128 columns;
+  * bit-reproducibility of the tensor-core backward.
+The golden-vector parity tests of tests/test_gpu_parity.py run on the tensor-core path as well (it is the default).
+"""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_to_max
+from oracle import lowlight_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from dedark_yolo_b200 import ops as o
+    return o
+
+
+@pytest.fixture
+def blur_env():
+    old = os.environ.get("DEDARK_BLUR")
+    yield
+    if old is None:
+        os.environ.pop("DEDARK_BLUR", None)
+    else:
+        os.environ["DEDARK_BLUR"] = old
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 96, 80), (2, 3, 64, 128), (1, 3, 200, 132), (1, 3, 13, 16), (1, 3, 333, 516), (1, 3, 640, 640),
+                                   (2, 3, 700, 1284)])
+def test_tc_blur_engine_matches_fp64_gaussian(ops, shape):
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.rand(shape, generator=g) * 2 - 0.5
+    ref = O.blur_separable(x.double())
+    y3 = ops.debug_blur_tc(x.cuda(), x3=True).cpu()
+    y1 = ops.debug_blur_tc(x.cuda(), x3=False).cpu()
+    e3, e1 = rel_to_max(y3, ref), rel_to_max(y1, ref)
+    print(f"[tc blur] {shape}: 3xTF32 {e3:.2e}, 1xTF32 {e1:.2e}")
+    assert e3 <= 2e-6, e3      # fp32 mode: well inside the module's 1e-5 gate
+    assert e1 <= 3e-3, e1      # bf16 mode: TF32 operand rounding (2e-2 gate)
+
+
+def _case(B, H, W, custom, seed):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, H, W, generator=gen)
+    g = torch.randn(B, 3, H, W, generator=gen)
+    feat = torch.randn(B, 15, generator=gen) * 0.8
+    A = (0.4 + 0.5 * torch.rand(B, 3, generator=gen)) if custom else None
+    IcA = torch.rand(B, 1, H, W, generator=gen) if custom else None
+    return x, g, feat, A, IcA
+
+
+def _run(ops, mode, x, g, feat, A, IcA, need_dx=True):
+    os.environ["DEDARK_BLUR"] = mode
+    c = lambda t: None if t is None else t.cuda()  # noqa: E731
+    y = ops.filters_forward(c(x), c(feat), c(A), c(IcA))
+    dfeat, dx = ops.filters_backward(c(x), c(feat), c(g), c(A), c(IcA), need_dx=need_dx)
+    torch.cuda.synchronize()
+    return y.cpu(), dfeat.cpu(), None if dx is None else dx.cpu()
+
+
+@pytest.mark.parametrize("B,H,W,custom", [(2, 96, 80, False), (2, 96, 80, True), (3, 200, 132, True), (1, 13, 16, False), (2, 150, 260, False)])
+def test_fused_kernels_tensor_core_vs_cuda_core_vs_fp64(ops, blur_env, B, H, W, custom):
+    x, g, feat, A, IcA = _case(B, H, W, custom, seed=B * H + W)
+    y_tc, df_tc, dx_tc = _run(ops, "tc", x, g, feat, A, IcA)
+    y_cc, df_cc, dx_cc = _run(ops, "cc", x, g, feat, A, IcA)
+    xr, fr = x.double().requires_grad_(True), feat.double().requires_grad_(True)
+    yr = O.filter_chain(xr, fr, None if A is None else A.double(), None if IcA is None else IcA.double(), dense_blur=False)
+    yr.backward(g.double())
+    errs = {"y": rel_to_max(y_tc, yr.detach()), "dfeat": rel_to_max(df_tc, fr.grad), "dx": rel_to_max(dx_tc, xr.grad)}
+    base = {"y": rel_to_max(y_cc, yr.detach()), "dfeat": rel_to_max(df_cc, fr.grad), "dx": rel_to_max(dx_cc, xr.grad)}
+    print(f"[tc fused] B={B} {H}x{W} custom={custom}: tensor cores {errs}, cuda cores {base}")
+    assert errs["y"] <= 1e-5 and errs["dfeat"] <= 1e-4 and errs["dx"] <= 2e-4, errs
+
+
+def test_fused_kernels_full_size_tensor_core_vs_cuda_core(ops, blur_env):
+    x, g, feat, A, IcA = _case(16, 640, 640, False, seed=77)
+    y_tc, df_tc, _ = _run(ops, "tc", x, g, feat, A, IcA, need_dx=False)
+    y_cc, df_cc, _ = _run(ops, "cc", x, g, feat, A, IcA, need_dx=False)
+    assert torch.isfinite(y_tc).all() and torch.isfinite(df_tc).all()
+    assert rel_to_max(y_tc, y_cc) <= 4e-6 and rel_to_max(df_tc, df_cc) <= 5e-5
+    # bit-reproducible: fixed-order reductions, no atomics
+    y2, df2, _ = _run(ops, "tc", x, g, feat, A, IcA, need_dx=False)
+    assert torch.equal(y_tc, y2) and torch.equal(df_tc, df2)
