@@ -23,7 +23,8 @@
 // the same operator applied to the mirror-extended cotangent with the image-border row / column doubled, followed by halving
 // the outputs on the border row / column:  with W(i,j) = k[j-i] + [j>=1] k[j+i] + [j<=n-2] k[2(n-1)-j-i]  (dd_recovery_bwd.cu),
 // sum_i W(i,j) g[i] = sum_i' k[j-i'] g^[i'] for 1 <= j <= n-2 where g^[-i] = g[i], g^[0] = 2 g[0], and exactly twice the true
-// value for j = 0 and j = n-1.
+// value for j = 0 and j = n-1 -- provided the two borders are more than one radius apart (n >= 14; n = 13, the smallest size
+// reflect padding accepts, is routed to the CUDA-core kernel).
 #pragma once
 #include "dd_tcgen05.cuh"
 #include "dd_recovery.cuh"
@@ -39,6 +40,25 @@ using tc::make_idesc;
 using tc::mma_commit;
 using tc::mma_tf32_ts;
 using tc::tf32_rna;
+
+// optional in-kernel time stamps (profiles/microbench/blur_tc_probe.cu defines DD_BTC_TIMING); no code otherwise.
+// Layout: [0] kernel start, [1] set-up done, [2] kernel end; block i of CTA 0 (i < 24):
+//   compute warp 0 lane 0: 16 + 8 i + {0 loop top, 1 pass 1 awaited, 2 split done, 3 pass 2 awaited, 4 epilogue done, 5 barrier, 6 stage done}
+//   MMA warp lane 0:      256 + 4 i + {0 tile awaited, 1 pass 1 issued, 2 split / accumulator awaited, 3 pass 2 issued}
+#ifdef DD_BTC_TIMING
+#ifndef DD_BTC_CTA
+#define DD_BTC_CTA 0
+#endif
+__device__ long long g_btc_stamp[512];
+#define BTC_STAMP(slot)                                                                          \
+    do {                                                                                        \
+        if (blockIdx.x == DD_BTC_CTA && (threadIdx.x & 31) == 0 && (slot) >= 0 && (slot) < 512) g_btc_stamp[(slot)] = clock64(); \
+    } while (0)
+#else
+#define BTC_STAMP(slot) \
+    do {                \
+    } while (0)
+#endif
 
 constexpr int kCW = 16;                  // compute warps (stage, split, epilogue)
 constexpr int kCT = kCW * 32;            // 512 compute threads
@@ -60,7 +80,8 @@ struct Lay {
     static constexpr int T_BYTES = kCH * T_LBO;           // one tile (hi or lo)
     static constexpr int T_BUF = (X3 ? 2 : 1) * T_BYTES;  // one buffer: [hi | lo]
     static constexpr int CC = R + 16, G_ROWS = 2 * R + 16, G_LBO = G_ROWS * 16, G_BYTES = 2 * G_LBO;  // G: one of hi / lo
-    static constexpr int SIDE_BYTES = kRadius * kStripW * 4;
+    static constexpr int S_LBO = kRadius * 16 + 16;       // side slot: [32 centre chunks][12 rows][4 floats], same row stride as a tile
+    static constexpr int SIDE_BYTES = (kStripW / 4) * S_LBO;
     static constexpr int KS2 = (R + 2 * kRadius) / 8;     // k-steps of pass 2
     static constexpr int RPW = R / 4;                     // ring / output columns per warp of a lane quarter (4 warps per quarter)
     static constexpr size_t SMEM = (size_t)kNBuf * T_BUF + (size_t)kSide * SIDE_BYTES + (size_t)(X3 ? 2 : 1) * G_BYTES;
@@ -70,7 +91,11 @@ struct Lay {
 struct Ctl {
     uint64_t tile_full[kNBuf], p1_done[kNBuf], split_done, p2_done, out_empty;
     uint32_t tmem_base;
+    float tap[32];  // tap[d] = k1[|d - 12|] for window positions d = 0..24, 0 beyond (set-up only)
 };
+
+static __constant__ float c_tap25[kTaps] = {DD_K12, DD_K11, DD_K10, DD_K9, DD_K8, DD_K7, DD_K6, DD_K5, DD_K4, DD_K3, DD_K2, DD_K1, DD_K0,
+                                      DD_K1,  DD_K2,  DD_K3,  DD_K4, DD_K5, DD_K6, DD_K7, DD_K8, DD_K9, DD_K10, DD_K11, DD_K12};
 
 // ---- tcgen05.ld / st, 4 columns ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float* v) {
@@ -80,17 +105,27 @@ __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// mbarrier traffic per WARP, not per thread: 512 arrivals on one barrier word are 512 serialised shared-memory atomics (measured:
+// ~2000 cycles per barrier), and 512 pollers contend for it.  Lane 0 arrives after __syncwarp() has ordered the warp's prior
+// writes (each thread has already executed the proxy / tcgen05 fence its own writes need); lane 0 polls and __syncwarp()
+// releases the other lanes.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+
 // named barrier of the compute warps only (the MMA warp never joins)
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
-
-__host__ __device__ __forceinline__ constexpr float tap_off(int d) {  // window position d in 0..24, else 0
-    return (d >= 0 && d < kTaps) ? tapj(d) : 0.f;
-}
 
 // ---- one-time set-up (all compute threads; the MMA warp allocates tensor memory) ------------------------------------------------
 // G[e][kk] = tap(kk - e + CC), K-major no-swizzle: 16-byte chunk kk/4 at chunk * G_LBO, row e at e * 16
 template <class L>
-__device__ __forceinline__ void build_constants(unsigned char* g_hi, unsigned char* g_lo, uint32_t tmem, int tid) {
+__device__ __forceinline__ void build_constants(const float* tap, unsigned char* g_hi, unsigned char* g_lo, uint32_t tmem, int tid) {
+    auto tap_off = [&](int d) { return (d >= 0 && d < kTaps) ? tap[d] : 0.f; };
     for (int i = tid; i < L::G_ROWS * 8; i += kCT) {
         const int e = i >> 3, kk = i & 7;
         const float v = tap_off(kk - e + L::CC);
@@ -102,7 +137,7 @@ __device__ __forceinline__ void build_constants(unsigned char* g_hi, unsigned ch
     if (tid < 128) {  // warps 0..3: lane quarter = warp; KhT[c][c'] = tap(c' - c) into TMEM lane c, columns A_HI + c' (A_LO + c')
         const int c = tid;
         const uint32_t base = tmem + ((uint32_t)(tid & ~31) << 16);
-#pragma unroll 1
+#pragma unroll 2
         for (int c0 = 0; c0 < kKC; c0 += 4) {
             float hi[4], lo[4];
 #pragma unroll
@@ -124,19 +159,20 @@ template <class L>
 __device__ __forceinline__ void issue_pass1(uint32_t tmem, uint32_t tile, int b) {
     const int start = (L::R * b) % L::RING;
     const int len1 = min(L::R, L::RING - start);
+    constexpr uint64_t kStep = (uint64_t)((2 * L::T_LBO) >> 4), kLo = (uint64_t)(L::T_BYTES >> 4);  // descriptor address increments
 #pragma unroll 1
     for (int piece = 0; piece < 2; ++piece) {
         const int n_off = piece ? len1 : 0, n = piece ? L::R - len1 : len1, col = piece ? 0 : start;
         if (n == 0) break;
         const uint32_t idesc = make_idesc(128, n, 0, 0);
         const uint32_t d = tmem + L::RING_HI + (uint32_t)col;
-#pragma unroll 1
+        const uint64_t d0 = make_desc(tile + (uint32_t)n_off * 16u, L::T_LBO, 128u);
+#pragma unroll
         for (int s = 0; s < kKC / 8; ++s) {
-            const uint32_t bt = tile + (uint32_t)(2 * s) * L::T_LBO + (uint32_t)n_off * 16u;
-            const uint64_t b_hi = make_desc(bt, L::T_LBO, 128u);
+            const uint64_t b_hi = d0 + (uint64_t)s * kStep;
             mma_tf32_ts(d, tmem + L::A_HI + 8u * s, b_hi, idesc, s > 0 ? 1u : 0u);
             if (L::X3) {
-                mma_tf32_ts(d, tmem + L::A_HI + 8u * s, make_desc(bt + L::T_BYTES, L::T_LBO, 128u), idesc, 1u);
+                mma_tf32_ts(d, tmem + L::A_HI + 8u * s, b_hi + kLo, idesc, 1u);
                 mma_tf32_ts(d, tmem + L::A_LO + 8u * s, b_hi, idesc, 1u);
             }
         }
@@ -144,24 +180,28 @@ __device__ __forceinline__ void issue_pass1(uint32_t tmem, uint32_t tile, int b)
 }
 template <class L>
 __device__ __forceinline__ void issue_pass2(uint32_t tmem, uint32_t g_hi, uint32_t g_lo, int b) {
-    bool first = true;
-#pragma unroll 1
+    // ring column of the first staged row of k-step 0 (v = R b - 24; negative only for b = 0, whose first three k-steps are skipped)
+    const int v0 = L::R * b - 2 * kRadius;
+    const int ring0 = ((v0 % L::RING) + L::RING) % L::RING;
+    const uint64_t dg_hi = make_desc(g_hi, L::G_LBO, 128u), dg_lo = make_desc(g_lo, L::G_LBO, 128u);
+    constexpr uint32_t idesc_full = make_idesc(128, L::R, 0, 0), idesc_band = make_idesc(128, 32, 0, 0);
+    const int s_first = b == 0 ? 2 * kRadius / 8 : 0;
+#pragma unroll
     for (int s = 0; s < L::KS2; ++s) {
-        const int v = L::R * b - 2 * kRadius + 8 * s;  // first staged (virtual) row of this k-step
-        if (v < 0) continue;                           // rows above the segment: nothing staged (first block only)
-        const int ring = v % L::RING;
-        const int n0 = first ? 0 : min(max(8 * s - 2 * kRadius, 0), L::R - 32);
-        const int n = first ? L::R : 32;
-        const uint32_t row = (uint32_t)(n0 + L::CC - 8 * s);
-        const uint32_t idesc = make_idesc(128, n, 0, 0);
+        if (s < s_first) continue;  // rows above the segment: nothing staged (first block only)
+        const bool first = s == s_first;
+        int ring = ring0 + 8 * s;
+        ring = ring >= L::RING ? ring - L::RING : ring;
+        const int n0_band = (8 * s - 2 * kRadius) < 0 ? 0 : ((8 * s - 2 * kRadius) > L::R - 32 ? L::R - 32 : 8 * s - 2 * kRadius);
+        const int n0 = first ? 0 : n0_band;
+        const uint64_t row = (uint64_t)(n0 + L::CC - 8 * s);  // 16-byte units: one row of G per unit
+        const uint32_t idesc = first ? idesc_full : idesc_band;
         const uint32_t d = tmem + L::OUT + (uint32_t)n0;
-        const uint64_t b_hi = make_desc(g_hi + row * 16u, L::G_LBO, 128u);
-        mma_tf32_ts(d, tmem + L::RING_HI + (uint32_t)ring, b_hi, idesc, first ? 0u : 1u);
+        mma_tf32_ts(d, tmem + L::RING_HI + (uint32_t)ring, dg_hi + row, idesc, first ? 0u : 1u);
         if (L::X3) {
-            mma_tf32_ts(d, tmem + L::RING_HI + (uint32_t)ring, make_desc(g_lo + row * 16u, L::G_LBO, 128u), idesc, 1u);
-            mma_tf32_ts(d, tmem + L::RING_LO + (uint32_t)ring, b_hi, idesc, 1u);
+            mma_tf32_ts(d, tmem + L::RING_HI + (uint32_t)ring, dg_lo + row, idesc, 1u);
+            mma_tf32_ts(d, tmem + L::RING_LO + (uint32_t)ring, dg_hi + row, idesc, 1u);
         }
-        first = false;
     }
 }
 
@@ -173,19 +213,23 @@ __device__ __forceinline__ void mma_warp_segment(Ctl& ctl, uint32_t tmem, unsign
         const uint32_t buf = gb % kNBuf, par3 = (gb / kNBuf) & 1u;
         mbar_wait(&ctl.tile_full[buf], par3);
         fence_after_sync();
+        BTC_STAMP(gb < 24 ? 256 + 4 * (int)gb : -1);
         if (elect_one()) {
             issue_pass1<L>(tmem, smem_u32(tiles + (size_t)buf * L::T_BUF), b);
             mma_commit(&ctl.p1_done[buf]);
         }
         __syncwarp();
+        BTC_STAMP(gb < 24 ? 257 + 4 * (int)gb : -1);
         if (L::X3) mbar_wait(&ctl.split_done, gb & 1u);       // the ring columns of this block are split into hi / lo
         if (gb > 0) mbar_wait(&ctl.out_empty, (gb - 1) & 1u);  // the previous block's accumulator has been read
         fence_after_sync();
+        BTC_STAMP(gb < 24 ? 258 + 4 * (int)gb : -1);
         if (elect_one()) {
             issue_pass2<L>(tmem, g_hi, g_lo, b);
             mma_commit(&ctl.p2_done);
         }
         __syncwarp();
+        BTC_STAMP(gb < 24 ? 259 + 4 * (int)gb : -1);
     }
 }
 
@@ -193,34 +237,38 @@ __device__ __forceinline__ void mma_warp_segment(Ctl& ctl, uint32_t tmem, unsign
 template <class L>
 __device__ __forceinline__ uint32_t setup(Ctl& ctl, unsigned char* g_hi, unsigned char* g_lo) {
     const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) BTC_STAMP(0);
     if (warp == kCW) tc::tmem_alloc(&ctl.tmem_base, L::TMEM_COLS);
     if (tid == 0) {
         for (int i = 0; i < kNBuf; ++i) {
-            mbar_init(&ctl.tile_full[i], kCT);
+            mbar_init(&ctl.tile_full[i], kCW);
             mbar_init(&ctl.p1_done[i], 1);
         }
-        mbar_init(&ctl.split_done, kCT);
+        mbar_init(&ctl.split_done, kCW);
         mbar_init(&ctl.p2_done, 1);
-        mbar_init(&ctl.out_empty, kCT);
+        mbar_init(&ctl.out_empty, kCW);
         fence_mbar_init();
     }
+    if (tid < 32) ctl.tap[tid] = tid < kTaps ? c_tap25[tid] : 0.f;
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = ctl.tmem_base;
     if (warp < kCW) {
-        build_constants<L>(g_hi, g_lo, tmem, tid);
+        build_constants<L>(ctl.tap, g_hi, g_lo, tmem, tid);
         fence_proxy_async();
         fence_before_sync();
     }
     __syncthreads();
     fence_after_sync();
+    if (tid == 0) BTC_STAMP(1);
     return tmem;
 }
 template <class L>
 __device__ __forceinline__ void teardown(uint32_t tmem) {
     fence_before_sync();
     __syncthreads();
+    if (threadIdx.x == 0) BTC_STAMP(2);
     if ((threadIdx.x >> 5) == kCW) tc::tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
@@ -253,10 +301,9 @@ __device__ __forceinline__ void split_ring(uint32_t tmem, int b, int warp) {
 template <class L>
 __device__ __forceinline__ int tile_off(int r, int sc) { return (sc >> 2) * L::T_LBO + r * 16 + (sc & 3) * 4; }
 
-// store four consecutive staged columns (one chunk) of one row, split when X3
+// store four consecutive staged columns (one chunk) of one row, split when X3; p = address of the chunk's row in the hi tile
 template <class L>
-__device__ __forceinline__ void tile_store4(unsigned char* tile, int r, int chunk, const float* o) {
-    unsigned char* p = tile + chunk * L::T_LBO + r * 16;
+__device__ __forceinline__ void tile_store4(unsigned char* p, const float* o) {
     if (L::X3) {
         float h[4];
 #pragma unroll
@@ -286,28 +333,78 @@ __device__ __forceinline__ float tile_load1(const unsigned char* tile, int r, in
     return v;
 }
 
-// Reflect halo of one staged row: the owner of the in-image columns col .. col+3 mirrors them into the staged columns of the
-// image columns -col (strip 0) and L + (L - col) (the strip that holds the right border); `vals` are the values to mirror.
+// ---- the CTA's work as one stream of blocks ----------------------------------------------------------------------------------------
+// A CTA owns a contiguous range of 32-row scheduling units (dd_layout.cuh) = a sequence of segments (runs of rows inside one
+// plane-strip), each cut into blocks of R staged rows.  The stage, the split and the epilogue of the software pipeline walk that
+// sequence with one iterator each (the stage runs three blocks ahead of the epilogue, possibly in a later segment), so the
+// tensor pipe is never drained at a segment boundary.  All fields are CTA-uniform.
+template <int R>
+struct SegIter {
+    long long blk, blk_end;
+    int ord;      // ordinal of the current segment (-1 before the first block)
+    int nB, b;    // blocks of the current segment, current block
+    Seg u;
+    __device__ __forceinline__ void init(const Sched& sc) {
+        blk = sched_begin(sc, blockIdx.x);
+        blk_end = sched_begin(sc, blockIdx.x + 1);
+        ord = -1;
+        nB = 0;
+        b = 0;
+    }
+    // step to the next block; false at the end of the stream.  `entered`: this block is the first of a new segment.
+    __device__ __forceinline__ bool next(const Sched& sc, int H, bool& entered) {
+        entered = false;
+        if (ord >= 0 && b + 1 < nB) {
+            ++b;
+            return true;
+        }
+        if (blk >= blk_end) return false;
+        u = next_seg(blk, blk_end, sc, H);
+        blk += seg_blocks(u);
+        nB = (u.nU + R - 1) / R;
+        b = 0;
+        ++ord;
+        entered = true;
+        return true;
+    }
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---- staging geometry of one thread, fixed for a segment ------------------------------------------------------------------------
+// The R x 38 (row, 16-byte column chunk) items of a block are dealt out as: thread t < (R/4) * 38 owns chunk j = t % 38 of the
+// four rows rg + (R/4) k, k = 0..3, rg = t / 38 (R = 48: 456 of the 512 compute threads, exactly four items each, the four
+// global loads of a block in flight together; the last 12 rows of a block -- the side-slot rows -- are exactly k = 3).
+// Reflect padding (F.pad(mode='reflect'), filtersB.py:167): a chunk in the reflect halo loads its four mirrored source columns
+// itself and then runs the same arithmetic as an in-image chunk -- no scattered mirror stores, no divergent code.
 template <class L>
-__device__ __forceinline__ void mirror_cols(unsigned char* tile, int r, int gc, int c0, int Lc, const float* vals) {
-    if (gc <= kRadius && c0 == 0) {
+struct StageGeo {
+    static constexpr int NG = L::R / 4;  // row groups
+    static constexpr int KIND_IDLE = 0, KIND_INSIDE = 1, KIND_ZERO = 2, KIND_MIRRORED = 3;
+    int rg, gc;
+    int kind;        // this thread's chunk: in-image data (one 128-bit load), reflect halo (four scalar loads of the mirrored
+                     // source columns), or zeros beyond the reflect range
+    int toff;        // byte offset of (row rg, chunk j) inside a tile
+    int soff;        // byte offset of (side row rg, chunk j) inside a side slot, -1 when the chunk is not a centre chunk
+    int mc[4];       // KIND_MIRRORED: source image columns reflect(gc + i, W)
+    __device__ __forceinline__ void init(int tid, int c0, int W) {
+        rg = tid / kCH;
+        const int j = tid - rg * kCH;
+        gc = c0 - kRadius + 4 * j;
+        const bool inside = gc >= 0 && gc < W;
+        const bool mirrored = (gc < 0 && gc >= -kRadius) || (gc >= W && gc < W + kRadius);
+        kind = tid >= NG * kCH ? KIND_IDLE : inside ? KIND_INSIDE : mirrored ? KIND_MIRRORED : KIND_ZERO;
+        toff = j * L::T_LBO + rg * 16;
+        soff = (j >= kRadius / 4 && j < kRadius / 4 + kStripW / 4) ? (j - kRadius / 4) * L::S_LBO + rg * 16 : -1;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int col = gc + i;
-            if (col >= 1 && col <= kRadius) tile_store1<L>(tile, r, kRadius - col, vals[i]);
-        }
+        for (int i = 0; i < 4; ++i) mc[i] = min(max(reflect(gc + i, W), 0), W - 1);
     }
-    if (gc + 3 >= Lc - kRadius) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int d = Lc - (gc + i);
-            const int t = Lc + d - c0 + kRadius;
-            if (d >= 1 && d <= kRadius && t < kKC) tile_store1<L>(tile, r, t, vals[i]);
-        }
+    // the four staged values of (image row offset `off` = row * W, this thread's chunk); KIND_INSIDE or KIND_MIRRORED only
+    __device__ __forceinline__ float4 load4(const float* __restrict__ plane, unsigned off) const {
+        if (kind == KIND_INSIDE) return __ldg(reinterpret_cast<const float4*>(plane + off + gc));
+        return make_float4(__ldg(plane + off + mc[0]), __ldg(plane + off + mc[1]), __ldg(plane + off + mc[2]), __ldg(plane + off + mc[3]));
     }
-}
-// does the staged chunk that starts at image column gc (outside [0, W)) receive mirror writes?
-__device__ __forceinline__ bool chunk_is_mirrored(int gc, int W) { return (gc < 0 && gc >= -kRadius) || (gc >= W && gc < W + kRadius); }
+};
 
 }  // namespace btc
 }  // namespace dd

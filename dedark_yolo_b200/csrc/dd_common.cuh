@@ -147,7 +147,7 @@ inline cudaError_t launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 bl
 
 // ---- peer exchange (dd_predictor_bwd_allreduce) ----------------------------------------------------
 // world <= 1: no exchange.  Otherwise gradient element `off` (canonical flat order) is also stored into slot [rank] of
-// the current parity in every rank's exchange buffer (peer memory over NVLink) as ONE 8-byte word {value, tag}: the tag
+// the current parity in every rank's exchange buffer (peer memory over NVLink) as ONE 8-byte word {value, tag} (one b64 store): the tag
 // (epoch + 1) travels with the data, so the receiver polls the element itself -- no fence, no separate flag, no second
 // NVLink round trip (the "LL" idea of collective libraries).
 struct PushCtx {
@@ -159,11 +159,14 @@ __device__ __forceinline__ uint2* exchange_slot(unsigned char* buf, unsigned int
     return reinterpret_cast<uint2*>(buf + kHdr) + ((size_t)parity * kPeers + rank) * kPitch;
 }
 __device__ __forceinline__ void push_grad(const PushCtx& px, unsigned int tag, int off, float v) {
-    const uint2 word = make_uint2(__float_as_uint(v), tag);
+    // ONE naturally aligned 64-bit store: value in the low half, tag in the high half.  A b64 access is single-copy atomic
+    // in the PTX memory model; a v2.u32 access is two scalar accesses whose order is unspecified (the receiver could see the
+    // new tag beside a stale value).
+    const unsigned long long word = (unsigned long long)__float_as_uint(v) | ((unsigned long long)tag << 32);
 #pragma unroll 1
     for (int p = 0; p < px.world; ++p) {
         uint2* dst = exchange_slot(px.buf[p], (tag - 1u) & 1u, px.rank) + off;
-        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(word.x), "r"(word.y) : "memory");
+        asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
     }
 }
 // tag of the exchange in progress = epoch of the local buffer + 1 (stable during a step); 0 when there is no exchange

@@ -811,13 +811,13 @@ allreduce_exchange_kernel(const PushCtx px, const GradPtrs gp) {
         float acc = 0.f;
         for (int r = 0; r < px.world; ++r) {
             const uint2* src = slots + (size_t)r * kGradPad + i;
-            uint2 wv;
+            unsigned long long wv;  // {value, tag} read with ONE 64-bit load (single-copy atomic, see push_grad)
             unsigned int spin = 0;
             do {
-                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(wv.x), "=r"(wv.y) : "l"(src) : "memory");
+                asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(wv) : "l"(src) : "memory");
                 if (++spin > (1u << 27)) __trap();  // a peer never arrived (about a minute): fail the launch instead of hanging the device
-            } while (wv.y != tag);
-            acc += __uint_as_float(wv.x);
+            } while ((unsigned int)(wv >> 32) != tag);
+            acc += __uint_as_float((unsigned int)wv);
         }
         const int seg = segment(i);
         gp.p[seg][i - kOff[seg]] = acc;

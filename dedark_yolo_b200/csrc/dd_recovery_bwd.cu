@@ -589,7 +589,10 @@ static int launch_bwd_tc(const float* x, const float* A, const float* IcA, const
 template <bool HAS_ICA, bool FAST, bool ALIGNED>
 static int launch_bwd3(const float* x, const float* A, const float* IcA, const float* feat, const float* g, float* dfeat,
                        float* dx, int B, int H, int W, float* ws, cudaStream_t st) {
-    if (ALIGNED && blur_on_tensor_cores()) return launch_bwd_tc<HAS_ICA, FAST>(x, A, IcA, feat, g, dfeat, dx, B, H, W, ws, st);
+    // (H or W == 13: the two image borders are exactly one blur radius apart and the doubled-border form of the reflect adjoint
+    //  used by the tensor-core kernel does not hold -- dd_blur_tc.cuh -- so those shapes stay on the CUDA-core kernel)
+    if (ALIGNED && H > kRadius + 1 && W > kRadius + 1 && blur_on_tensor_cores())
+        return launch_bwd_tc<HAS_ICA, FAST>(x, A, IcA, feat, g, dfeat, dx, B, H, W, ws, st);
     const Sched sc = make_sched(B, H, W);
     float* part = ws;
     float* Spart = part + (size_t)(sc.G + sc.nPS) * kBwdSums;

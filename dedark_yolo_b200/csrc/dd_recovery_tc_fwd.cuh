@@ -3,14 +3,16 @@
 // Reference: nn/modules/llie.py:34-40,49-52; filtersB.py:144-259,289-303; util_filters.py:270-273,295-304,316-317.
 //
 // One persistent CTA per SM (16 compute warps + 1 MMA warp).  The CTAs share the marching-strip work list of the CUDA-core
-// kernel (dd_layout.cuh: plane-strips cut into 32-row scheduling units, contiguous equal ranges per CTA); inside a segment the
-// rows are processed in blocks of R staged rows:
-//     stage(b)     x0 -> DeDark -> WB -> Gamma -> Contrast (pointwise, in registers) -> x4, split, into tile buffer b % 3
+// kernel (dd_layout.cuh: plane-strips cut into 32-row scheduling units, contiguous equal ranges per CTA); a CTA's range is one
+// stream of blocks of R staged rows (SegIter):
+//     stage(G)     x0 -> DeDark -> WB -> Gamma -> Contrast (pointwise, in registers) -> x4, split, into tile buffer G % 3
 //                  (reflect halo: mirrored columns, reflected rows), last 12 rows also into a side slot
 //     pass 1, [split], pass 2   on the tensor cores (MMA warp), accumulators in tensor memory
-//     epilogue(b)  y = (x4 - blur) p + x4 for the R output rows whose 25-row window pass 1 has completed; thread <-> column
-// software-pipelined: in iteration b the compute warps split block b, run the epilogue of block b-1 and stage block b+2 while
-// the tensor pipe runs pass 2 of block b and pass 1 of block b+1.
+//     epilogue(G)  y = (x4 - blur) p + x4 for the R output rows whose 25-row window pass 1 has completed; thread <-> column
+// software-pipelined: iteration G runs the epilogue of block G-1, issues the global loads of block G+2, splits block G (in
+// the shadow of those loads) and finishes staging block G+2, while the tensor pipe runs pass 2 of block G and pass 1 of block
+// G+1.  The stage may already be in the next segment (another image plane or strip): the per-segment set-up (regressors,
+// per-row contrast scalars) runs inside the stream, the tensor pipe is not drained at segment boundaries.
 #pragma once
 #include "dd_blur_tc.cuh"
 
@@ -23,141 +25,220 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
 recovery_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
                        const float* __restrict__ feat, float* __restrict__ y, int B, int H, int W) {
     using L = Lay<R, X3>;
-    pdl_begin();
+    using SG = StageGeo<L>;
+    static_assert(R == 48, "the stage / epilogue work split assumes 48-row blocks (12 row groups x 4 rows, 12 outputs per warp)");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* tiles = smem_raw;
-    float* side = reinterpret_cast<float*>(tiles + (size_t)kNBuf * L::T_BUF);
-    unsigned char* g_hi = reinterpret_cast<unsigned char*>(side) + (size_t)kSide * L::SIDE_BYTES;
+    unsigned char* side = tiles + (size_t)kNBuf * L::T_BUF;
+    unsigned char* g_hi = side + (size_t)kSide * L::SIDE_BYTES;
     unsigned char* g_lo = g_hi + L::G_BYTES;
-    __shared__ float MS[kMaxU];  // per staged row: m = (1 - c) + c q
+    __shared__ float MS[kMaxU];   // per staged row of the segment being staged: m = (1 - c) + c q
+    __shared__ float s_pp[4];     // USM strength p of the last four segments (the epilogue runs up to three blocks behind the stage)
     __shared__ ImgParams sp;
     __shared__ Ctl ctl;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t tmem = setup<L>(ctl, g_hi, g_lo);
+    const uint32_t tmem = setup<L>(ctl, g_hi, g_lo);   // reads no global memory: overlaps the tail of the previous kernel
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const Sched sc = make_sched(B, H, W, kSchedCtasTC);
-    const long long blk_end = sched_begin(sc, blockIdx.x + 1);
-    const int Lc = W - 1;
-    uint32_t gb = 0;  // running block counter of this CTA (identical in every warp): barrier parities and buffer rotation
 
-    for (long long blk = sched_begin(sc, blockIdx.x); blk < blk_end;) {
-        const Seg u = next_seg(blk, blk_end, sc, H);
-        blk += seg_blocks(u);
-        const int nB = (u.nU + R - 1) / R;
-
-        if (warp == kCW) {
-            mma_warp_segment<L>(ctl, tmem, tiles, smem_u32(g_hi), smem_u32(g_lo), nB, gb);
-            continue;
+    if (warp == kCW) {
+        // ================================ MMA warp ================================
+        uint32_t gb = 0;
+        const long long blk_end = sched_begin(sc, blockIdx.x + 1);
+        for (long long blk = sched_begin(sc, blockIdx.x); blk < blk_end;) {
+            const Seg u = next_seg(blk, blk_end, sc, H);
+            blk += seg_blocks(u);
+            mma_warp_segment<L>(ctl, tmem, tiles, smem_u32(g_hi), smem_u32(g_lo), (u.nU + R - 1) / R, gb);
         }
-
+    } else {
         // ================================ compute warps ================================
-        compute_sync();  // the previous segment is fully drained: MS, sp, side slots and tile buffers may be rewritten
-        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
-        compute_sync();
-        const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
-        const float pc = sp.c, pp = sp.p;
-        const float* xp = x + (size_t)u.plane * H * W;
-        const float* ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
-        float* yp = y + (size_t)u.plane * H * W;
+        SegIter<R> itS, itM, itE;   // stage, split and epilogue positions in the block stream
+        itS.init(sc);
+        itM.init(sc);
+        itE.init(sc);
+        bool entered;
 
-        if (!DBG) {  // per-row contrast scalars of the segment (rgb2lum quirk: columns 0..2 of each row, util_filters.py:270-273)
-            for (int v = tid; v < u.nU; v += kCT) {
-                const int row = reflect(u.r0 - kRadius + v, H);
-                float x3[3];
+        // ---- stage side -------------------------------------------------------------------------------------------------------
+        SG sg;
+        ChainK ck;
+        const float* xp = x;
+        const float* ip = IcA;
+        int rowbase = 0, nU = 0;
+        float4 in[4], ic[4];  // the block in flight between stage_load and stage_store
+        auto stage_enter = [&]() {  // first block of a new segment: regressors of its image, per-row contrast scalars, geometry
+            const Seg& u = itS.u;
+            compute_sync();  // every warp has finished staging the previous segment (MS, sp are about to be rewritten)
+            if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
+            compute_sync();
+            ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
+            const float pc = sp.c;
+            if (tid == 0) s_pp[itS.ord & 3] = sp.p;
+            xp = x + (size_t)u.plane * H * W;
+            ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
+            rowbase = u.r0 - kRadius;
+            nU = u.nU;
+            sg.init(tid, u.c0, W);
+            if (!DBG) {  // rgb2lum quirk: columns 0..2 of each row (util_filters.py:270-273)
+                for (int v = tid; v < nU; v += kCT) {
+                    const size_t ro = (size_t)reflect(rowbase + v, H) * W;
+                    float x3[3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    x3[c] = chain_x3<HAS_ICA, FAST>(ck, __ldg(xp + (size_t)row * W + c), HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA);
-                const RowLum rl = row_lum<true>(x3[0], x3[1], x3[2]);
-                MS[v] = (1.f - pc) + pc * rl.q;
+                    for (int c = 0; c < 3; ++c) x3[c] = chain_x3<HAS_ICA, FAST>(ck, __ldg(xp + ro + c), HAS_ICA ? __ldg(ip + ro + c) : kDefaultIcA);
+                    const RowLum rl = row_lum<true>(x3[0], x3[1], x3[2]);
+                    MS[v] = (1.f - pc) + pc * rl.q;
+                }
             }
             compute_sync();
-        }
-
-        auto stage = [&](int b) {
-            const uint32_t g = gb + (uint32_t)b;
-            unsigned char* tile = tiles + (size_t)(g % kNBuf) * L::T_BUF;
-            float* sd = side + (size_t)(g % kSide) * (L::SIDE_BYTES / 4);
-#pragma unroll 1
-            for (int idx = tid; idx < R * kCH; idx += kCT) {
-                const int r = idx / kCH, j = idx - r * kCH;
-                const int v = R * b + r;
-                const int gc = u.c0 - kRadius + 4 * j;
-                const bool inside = gc >= 0 && gc < W, vrow = v < u.nU;
-                float o[4] = {0.f, 0.f, 0.f, 0.f};
-                if (inside && vrow) {
-                    const int row = reflect(u.r0 - kRadius + v, H);
-                    const float4 in = __ldg(reinterpret_cast<const float4*>(xp + (size_t)row * W + gc));
-                    if (DBG) {
-                        o[0] = in.x; o[1] = in.y; o[2] = in.z; o[3] = in.w;
-                    } else {
-                        float4 ic = make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
-                        if (HAS_ICA) ic = __ldg(reinterpret_cast<const float4*>(ip + (size_t)row * W + gc));
-                        const float m = MS[v];
-                        o[0] = chain_x3<HAS_ICA, FAST>(ck, in.x, ic.x) * m;
-                        o[1] = chain_x3<HAS_ICA, FAST>(ck, in.y, ic.y) * m;
-                        o[2] = chain_x3<HAS_ICA, FAST>(ck, in.z, ic.z) * m;
-                        o[3] = chain_x3<HAS_ICA, FAST>(ck, in.w, ic.w) * m;
-                    }
-                    mirror_cols<L>(tile, r, gc, u.c0, Lc, o);
+        };
+        auto stage_load = [&]() {  // the four global loads of this thread's items of block itS.b
+            if (sg.kind == SG::KIND_INSIDE || sg.kind == SG::KIND_MIRRORED) {
+                const int v0 = R * itS.b + sg.rg;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned off = (unsigned)reflect(rowbase + min(v0 + SG::NG * k, nU - 1), H) * (unsigned)W;
+                    in[k] = sg.load4(xp, off);
+                    if (HAS_ICA) ic[k] = sg.load4(ip, off);
                 }
-                if (inside || !vrow || !chunk_is_mirrored(gc, W)) tile_store4<L>(tile, r, j, o);
-                if (r >= R - kRadius && j >= kRadius / 4 && j < kRadius / 4 + kStripW / 4)
-                    *reinterpret_cast<float4*>(sd + (r - (R - kRadius)) * kStripW + 4 * j - kRadius) = make_float4(o[0], o[1], o[2], o[3]);
+                if (sg.kind == SG::KIND_INSIDE && itS.b + 1 < itS.nB) {  // next block of the segment: towards L2 while this one is processed
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        prefetch_l2(xp + (unsigned)reflect(rowbase + min(v0 + R + SG::NG * k, nU - 1), H) * (unsigned)W + sg.gc);
+                }
+            }
+        };
+        auto stage_store = [&](uint32_t g) {  // pointwise chain, split, tile buffer g % 3 (+ side slot g % 4)
+            unsigned char* trow = tiles + (size_t)(g % kNBuf) * L::T_BUF + sg.toff;  // row rg; row rg + 12 k at + 192 k bytes
+            const int v0 = R * itS.b + sg.rg;
+            if (sg.kind == SG::KIND_INSIDE || sg.kind == SG::KIND_MIRRORED) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int v = v0 + SG::NG * k;
+                    float o[4];
+                    if (DBG) {
+                        o[0] = in[k].x; o[1] = in[k].y; o[2] = in[k].z; o[3] = in[k].w;
+                    } else {
+                        const float m = MS[min(v, nU - 1)];
+                        const float4 q = HAS_ICA ? ic[k] : make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
+                        o[0] = chain_x3<HAS_ICA, FAST>(ck, in[k].x, q.x) * m;
+                        o[1] = chain_x3<HAS_ICA, FAST>(ck, in[k].y, q.y) * m;
+                        o[2] = chain_x3<HAS_ICA, FAST>(ck, in[k].z, q.z) * m;
+                        o[3] = chain_x3<HAS_ICA, FAST>(ck, in[k].w, q.w) * m;
+                    }
+                    if (v >= nU) o[0] = o[1] = o[2] = o[3] = 0.f;  // rows past the segment (its last block only): zeros
+                    tile_store4<L>(trow + 16 * SG::NG * k, o);
+                    if (k == 3 && sg.soff >= 0)  // rows R-12 .. R-1: centre values of the next block's first outputs
+                        *reinterpret_cast<float4*>(side + (size_t)(g % kSide) * L::SIDE_BYTES + sg.soff) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            } else if (sg.kind == SG::KIND_ZERO) {  // halo chunks beyond the reflect range
+                const float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tile_store4<L>(trow + 16 * SG::NG * k, z);
             }
             fence_proxy_async();
-            mbar_arrive(&ctl.tile_full[g % kNBuf]);
+            mbar_arrive_warp(&ctl.tile_full[g % kNBuf]);
         };
 
-        auto epilogue = [&](int bb) {  // outputs o = R * bb - 24 + n, n in [0, R)
-            const uint32_t g = gb + (uint32_t)bb;
-            mbar_wait(&ctl.p2_done, g & 1u);
+        // ---- epilogue side ----------------------------------------------------------------------------------------------------
+        const int q = warp & 3, gq = warp >> 2, c = 32 * q + lane;   // lane quarter, output-row group (12 rows), strip column
+        // centre values: the first 12 outputs of a block sit on the tail of the previous block (side slot, exact fp32), the others
+        // on rows 12 (gq - 1) + i of the block's own tile (hi + lo); 16 bytes between consecutive rows in both
+        const int ctr_off = gq == 0 ? (c >> 2) * L::S_LBO + (c & 3) * 4 : tile_off<L>(L::RPW * (gq - 1), c + kRadius);
+        float* ys = y;
+        bool col_ok = false;
+        float pp = 0.f;
+        int e_r0 = 0, e_len = 0;
+        int ep_ts = -100;  // time-stamp slot of the epilogue in flight (DD_BTC_TIMING only)
+        auto epilogue_enter = [&]() {
+            const Seg& u = itE.u;
+            pp = s_pp[itE.ord & 3];
+            col_ok = u.c0 + c < W;
+            ys = y + (size_t)u.plane * H * W + (u.c0 + c);
+            e_r0 = u.r0;
+            e_len = u.seg_len;
+        };
+        auto epilogue = [&](uint32_t g) {  // block itE.b of the segment: outputs o = R b - 24 + 12 gq + i, i in [0, 12)
+            mbar_wait_warp(&ctl.p2_done, g & 1u);
             fence_after_sync();
-            const int q = warp & 3, n_first = (warp >> 2) * L::RPW, c = 32 * q + lane;
+            BTC_STAMP(ep_ts);
             float bl[L::RPW];
 #pragma unroll
-            for (int i = 0; i < L::RPW; i += 4) tmem_ld4_nowait(tmem + ((uint32_t)(32 * q) << 16) + L::OUT + (uint32_t)(n_first + i), bl + i);
+            for (int i = 0; i < L::RPW; i += 4) tmem_ld4_nowait(tmem + ((uint32_t)(32 * q) << 16) + L::OUT + (uint32_t)(L::RPW * gq + i), bl + i);
             tmem_ld_wait();
             fence_before_sync();
-            mbar_arrive(&ctl.out_empty);  // the accumulator is in registers: pass 2 of the next block may overwrite it
-            const unsigned char* tile = tiles + (size_t)(g % kNBuf) * L::T_BUF;
-            const float* sd = side + (size_t)((g + kSide - 1) % kSide) * (L::SIDE_BYTES / 4);  // tail of block bb - 1
-            const int gc = u.c0 + c;
+            mbar_arrive_warp(&ctl.out_empty);  // the accumulator is in registers: pass 2 of the next block may overwrite it
+            const int o0 = R * itE.b - 2 * kRadius + L::RPW * gq;           // first output row of this warp
+            const int i_lo = max(0, -o0), i_hi = min(L::RPW, e_len - o0);
+            if (!col_ok || i_lo >= i_hi) return;
+            const unsigned char* ctr = (gq == 0 ? side + (size_t)((g + kSide - 1) % kSide) * L::SIDE_BYTES : tiles + (size_t)(g % kNBuf) * L::T_BUF) + ctr_off;
+            const int yoff = (e_r0 + o0) * W;  // 32-bit element offset of the warp's first output row (negative rows are never touched)
+            auto one = [&](int i) {
+                float x4 = *reinterpret_cast<const float*>(ctr + 16 * i);
+                if (X3 && gq != 0) x4 += *reinterpret_cast<const float*>(ctr + 16 * i + L::T_BYTES);
+                __stcs(ys + (yoff + i * W), DBG ? bl[i] : fmaf(x4 - bl[i], pp, x4));
+            };
+            if (i_lo == 0 && i_hi == L::RPW) {  // the common case: every output row of the warp lies inside the segment
 #pragma unroll
-            for (int i = 0; i < L::RPW; ++i) {
-                const int o = R * bb - 2 * kRadius + n_first + i;
-                if (o < 0 || o >= u.seg_len) continue;  // warp-uniform
-                const int rr = o + kRadius - R * bb;     // centre row relative to block bb (negative: tail of block bb - 1)
-                const float x4 = rr < 0 ? sd[(rr + kRadius) * kStripW + c] : tile_load1<L>(tile, rr, c + kRadius);
-                const float yv = DBG ? bl[i] : fmaf(x4 - bl[i], pp, x4);
-                if (gc < W) __stcs(yp + (size_t)(u.r0 + o) * W + gc, yv);
+                for (int i = 0; i < L::RPW; ++i) one(i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < L::RPW; ++i)
+                    if (i >= i_lo && i < i_hi) one(i);
             }
         };
 
-        stage(0);
-        if (nB > 1) stage(1);
-        for (int b = 0; b < nB; ++b) {
-            const uint32_t g = gb + (uint32_t)b;
-            mbar_wait(&ctl.p1_done[g % kNBuf], (g / kNBuf) & 1u);  // pass 1 of block b complete: ring columns valid, tile buffer read
+        // ---- the stream -------------------------------------------------------------------------------------------------------
+        bool moreS = true;
+        for (uint32_t g = 0; g < 2 && moreS; ++g) {  // prime: blocks 0 and 1
+            moreS = itS.next(sc, H, entered);
+            if (!moreS) break;
+            if (entered) stage_enter();
+            stage_load();
+            stage_store(g);
+        }
+        uint32_t G = 0;
+        while (itM.next(sc, H, entered)) {
+            const int ts = (warp == 0 && G < 24) ? 16 + 8 * (int)G : -100;
+            BTC_STAMP(ts);
+            if (G > 0) {  // epilogue of block G - 1
+                itE.next(sc, H, entered);
+                if (entered) epilogue_enter();
+                ep_ts = ts + 3;
+                epilogue(G - 1);
+            }
+            BTC_STAMP(ts + 4);
+            compute_sync();  // every warp is done with block G-1's tile buffer and side slots before block G+2 is staged into them
+            BTC_STAMP(ts + 5);
+            if (moreS) moreS = itS.next(sc, H, entered);
+            if (moreS) {
+                if (entered) stage_enter();
+                stage_load();
+            }
+            mbar_wait_warp(&ctl.p1_done[G % kNBuf], (G / kNBuf) & 1u);  // pass 1 of block G complete: ring columns valid
+            BTC_STAMP(ts + 1);
             if (X3) {
                 fence_after_sync();
-                split_ring<L>(tmem, b, warp);
+                split_ring<L>(tmem, itM.b, warp);
                 fence_before_sync();
-                mbar_arrive(&ctl.split_done);
+                mbar_arrive_warp(&ctl.split_done);
             }
-            if (b > 0) epilogue(b - 1);
-            compute_sync();  // every warp is done with block b-1's buffer and side slots before they are restaged
-            if (b + 2 < nB) stage(b + 2);
+            BTC_STAMP(ts + 2);
+            if (moreS) stage_store(G + 2);
+            BTC_STAMP(ts + 6);
+            ++G;
         }
-        epilogue(nB - 1);
-        gb += (uint32_t)nB;
+        if (G > 0) {
+            itE.next(sc, H, entered);
+            if (entered) epilogue_enter();
+            ep_ts = -100;
+            epilogue(G - 1);
+        }
     }
 
     teardown<L>(tmem);
 }
-
-template <int R, bool X3>
-constexpr size_t fwd_tc_smem() { return Lay<R, X3>::SMEM; }
 
 }  // namespace btc
 }  // namespace dd

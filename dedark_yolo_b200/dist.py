@@ -46,7 +46,13 @@ class GradExchange:
     their address space: through ``torch.distributed._symmetric_memory`` when it is available, otherwise through CUDA IPC
     handles of a plain allocation.  ``self.px`` is the descriptor the C-ABI takes; the predictor backward then stores its
     gradients straight into the peers' buffers and sums the world's contributions itself -- no collective library call.
-    Raises if the buffers cannot be shared (the caller then keeps the NCCL all-reduce and says so)."""
+    Raises -- on every rank together, the ranks agree on each step of the set-up -- if the buffers cannot be shared (the
+    caller then keeps the NCCL all-reduce and says so).
+
+    Scope: the receiving kernel polls for its peers' words with a bounded spin and TRAPS (the launch fails, the context is
+    lost) if a peer has not arrived after about a minute.  That is the right behaviour for lock-step data-parallel steps
+    (bench.py, RecoveryPipeline) and the wrong one for a job in which one rank may legitimately stall for minutes between
+    the backward passes of a step (rank-0 validation, checkpointing inside a step): such jobs keep the NCCL path."""
 
     def __init__(self, device, group=None):
         from . import _lib
@@ -58,32 +64,65 @@ class GradExchange:
         dev = torch.device(device)
         nbytes = int(_lib.lib.dd_exchange_bytes())
         self.how, self._keep = None, []
+
+        def all_ok(flag: bool) -> bool:
+            """Every rank takes the same branch: a path is used only if it worked on ALL ranks (a rank that entered the
+            fallback's collective alone would hang the others)."""
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(t.item())
+
+        ptrs, errs = None, []
+        # (1) symmetric memory: local allocation first, agreement, then the collective rendezvous, agreement again
+        buf = None
         try:
             import torch.distributed._symmetric_memory as symm_mem
             buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
             buf.zero_()
-            hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
-            ptrs = [int(p) for p in hdl.buffer_ptrs]
-            self._keep += [buf, hdl]
-            self.how = "symmetric_memory"
-        except Exception as e_symm:  # pragma: no cover - depends on driver / fabric support
+        except Exception as e:  # pragma: no cover - depends on driver / fabric support
+            errs.append(f"symmetric memory allocation: {e!r}")
+            buf = None
+        if all_ok(buf is not None):
+            try:
+                hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                self._keep += [buf, hdl]
+            except Exception as e:  # pragma: no cover
+                errs.append(f"symmetric memory rendezvous: {e!r}")
+                ptrs = None
+            if all_ok(ptrs is not None):
+                self.how = "symmetric_memory"
+            else:
+                ptrs = None
+        # (2) CUDA IPC handles of a plain allocation, exchanged with all_gather_object (all ranks or none)
+        if self.how is None:
+            self._keep = []
+            info = None
             try:
                 buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
                 info = buf.untyped_storage()._share_cuda_()
+            except Exception as e:  # pragma: no cover
+                errs.append(f"CUDA IPC export: {e!r}")
+            if all_ok(info is not None):
                 infos = [None] * self.world
                 dist.all_gather_object(infos, info, group=group)
-                ptrs = []
-                for r, inf in enumerate(infos):
-                    if r == self.rank:
-                        ptrs.append(buf.data_ptr())
-                    else:
-                        st = torch.UntypedStorage._new_shared_cuda(*inf)
-                        self._keep.append(st)
-                        ptrs.append(st.data_ptr())
-                self._keep.append(buf)
-                self.how = "cuda_ipc"
-            except Exception as e_ipc:
-                raise RuntimeError(f"GradExchange: cannot share buffers (symmetric memory: {e_symm!r}; CUDA IPC: {e_ipc!r})")
+                try:
+                    ptrs = []
+                    for r, inf in enumerate(infos):
+                        if r == self.rank:
+                            ptrs.append(buf.data_ptr())
+                        else:
+                            st = torch.UntypedStorage._new_shared_cuda(*inf)
+                            self._keep.append(st)
+                            ptrs.append(st.data_ptr())
+                    self._keep.append(buf)
+                except Exception as e:  # pragma: no cover
+                    errs.append(f"CUDA IPC import: {e!r}")
+                    ptrs = None
+                if all_ok(ptrs is not None):
+                    self.how = "cuda_ipc"
+        if self.how is None:  # every rank raises together: the caller keeps the NCCL all-reduce
+            raise RuntimeError("GradExchange: the exchange buffers cannot be shared on every rank (" + "; ".join(errs or ["a peer failed"]) + ")")
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)  # every buffer is zero-filled and mapped before anyone stores into it
         self.px = _lib.PeerExchange.from_pointers(self.rank, ptrs)

@@ -151,8 +151,9 @@ int dd_recovery_bwd(const float* x, const float* A, const float* IcA, const floa
 /* ---- unit-test hook of the tensor-core blur engine -------------------------------------------------
  * y = the reflect-padded 25x25 Gaussian of x (filtersB.py:154-175: F.pad(..., 'reflect') + conv2d per channel), computed by
  * the same tcgen05 engine the fused kernels use (x3 != 0: 3xTF32 operand split, the fp32 mode; 0: plain TF32, the bf16
- * mode).  Needs W % 4 == 0 and a 16-byte aligned x.  Selecting the engine: the fused kernels use the tensor cores whenever
- * the rows are 16-byte aligned unless the environment variable DEDARK_BLUR=cc asks for the CUDA-core (FFMA2) kernels. */
+ * mode).  Needs W % 4 == 0 and a 16-byte aligned x.  Selecting the engine of the fp32 entry points: the CUDA-core (FFMA2)
+ * kernels by default (still the faster ones at fp32 precision), the tensor-core kernels (3xTF32) with the environment
+ * variable DEDARK_BLUR=tc when the rows are 16-byte aligned; the bf16 entry points always use the tensor cores. */
 int dd_debug_blur_tc(const float* x, float* y, int B, int H, int W, int x3, void* stream);
 
 #ifdef __cplusplus

@@ -291,10 +291,16 @@ def test_full_size_properties(dd, ops, B, H, W):
     params = [p.detach() for p in m.extractor.ordered_parameters()]
     feat, _ = ops.predictor_forward(ops.resize256(x), params)
     y = ops.filters_forward(x, feat)
-    # (1) batch independence / determinism: permuting the batch permutes the output bit-for-bit
+    # (1) batch independence: permuting the batch permutes the output.  Bit for bit on the CUDA-core kernels (W % 4 != 0); the
+    #     tensor-core blur sums a row's 25 taps in k-steps of 8 staged rows whose alignment follows the CTA's work range, so an
+    #     image at another batch position may differ in the last bits (far inside the 1e-5 gate); run to run it is bit-exact.
     perm = torch.arange(B - 1, -1, -1).cuda()
     y_p = ops.filters_forward(x[perm].contiguous(), feat[perm].contiguous())
-    assert torch.equal(y_p, y[perm])
+    if W % 4:
+        assert torch.equal(y_p, y[perm])
+    else:
+        report(f"batch permutation {H}x{W}", y_p, y[perm], 2e-6)
+    assert torch.equal(ops.filters_forward(x, feat), y), "forward must be bit-reproducible"
     # (2) forward and backward of image 0 and image B-1 against the fp64 oracle (one image at a time keeps the CPU
     #     cost at seconds); covers multi-strip / multi-segment decompositions at BASELINE sizes
     d1, _ = ops.filters_backward(x, feat, g)

