@@ -26,6 +26,8 @@
 // value for j = 0 and j = n-1 -- provided the two borders are more than one radius apart (n >= 14; n = 13, the smallest size
 // reflect padding accepts, is routed to the CUDA-core kernel).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "dd_tcgen05.cuh"
 #include "dd_recovery.cuh"
 
@@ -333,6 +335,30 @@ __device__ __forceinline__ float tile_load1(const unsigned char* tile, int r, in
     return v;
 }
 
+// ---- image element types: fp32 (the reference's dtype) and bf16 (the bf16 I/O mode) -------------------------
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+    static __device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ float load1(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ void store1_streaming(float* p, float v) { __stcs(p, v); }
+    static __device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+    static __device__ __forceinline__ float bits(unsigned short u) { return __uint_as_float((unsigned)u << 16); }
+    static __device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {  // four consecutive elements, 8-byte aligned
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+        return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+    }
+    static __device__ __forceinline__ float load1(const __nv_bfloat16* p) { return bits(__ldg(reinterpret_cast<const unsigned short*>(p))); }
+    static __device__ __forceinline__ void store1_streaming(__nv_bfloat16* p, float v) {
+        __stcs(reinterpret_cast<unsigned short*>(p), __bfloat16_as_ushort(__float2bfloat16_rn(v)));
+    }
+    static __device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
 // ---- the CTA's work as one stream of blocks ----------------------------------------------------------------------------------------
 // A CTA owns a contiguous range of 32-row scheduling units (dd_layout.cuh) = a sequence of segments (runs of rows inside one
 // plane-strip), each cut into blocks of R staged rows.  The stage, the split and the epilogue of the software pipeline walk that
@@ -400,9 +426,11 @@ struct StageGeo {
         for (int i = 0; i < 4; ++i) mc[i] = min(max(reflect(gc + i, W), 0), W - 1);
     }
     // the four staged values of (image row offset `off` = row * W, this thread's chunk); KIND_INSIDE or KIND_MIRRORED only
-    __device__ __forceinline__ float4 load4(const float* __restrict__ plane, unsigned off) const {
-        if (kind == KIND_INSIDE) return __ldg(reinterpret_cast<const float4*>(plane + off + gc));
-        return make_float4(__ldg(plane + off + mc[0]), __ldg(plane + off + mc[1]), __ldg(plane + off + mc[2]), __ldg(plane + off + mc[3]));
+    template <typename T>
+    __device__ __forceinline__ float4 load4(const T* __restrict__ plane, unsigned off) const {
+        if (kind == KIND_INSIDE) return Elem<T>::load4(plane + off + gc);
+        return make_float4(Elem<T>::load1(plane + off + mc[0]), Elem<T>::load1(plane + off + mc[1]), Elem<T>::load1(plane + off + mc[2]),
+                           Elem<T>::load1(plane + off + mc[3]));
     }
 };
 

@@ -14,6 +14,8 @@
 #include <cstring>
 
 #include "dd_common.cuh"
+#include <cuda_bf16.h>
+
 #include "dd_conv_tc.cuh"
 #include "dd_conv_tiled.cuh"
 #include "dd_layout.cuh"
@@ -32,8 +34,13 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int n, int& i
     lam = s - (float)i0;
 }
 
+__device__ __forceinline__ float ld_elem(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_elem(const __nv_bfloat16* p) {
+    return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+template <typename T>
 __global__ void __launch_bounds__(256)
-resize256_kernel(const float* __restrict__ x, float* __restrict__ r, int B, int H, int W) {
+resize256_kernel(const T* __restrict__ x, float* __restrict__ r, int B, int H, int W) {
     pdl_begin();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;  // output column (256 per row)
     const int i = blockIdx.y;                              // output row
@@ -44,9 +51,9 @@ resize256_kernel(const float* __restrict__ x, float* __restrict__ r, int B, int 
     float ly, lx;
     bilinear_src(i, sh, H, y0, y1, ly);
     bilinear_src(j, sw, W, x0, x1, lx);
-    const float* p = x + (size_t)plane * H * W;
-    const float v00 = __ldg(p + (size_t)y0 * W + x0), v01 = __ldg(p + (size_t)y0 * W + x1);
-    const float v10 = __ldg(p + (size_t)y1 * W + x0), v11 = __ldg(p + (size_t)y1 * W + x1);
+    const T* p = x + (size_t)plane * H * W;
+    const float v00 = ld_elem(p + (size_t)y0 * W + x0), v01 = ld_elem(p + (size_t)y0 * W + x1);
+    const float v10 = ld_elem(p + (size_t)y1 * W + x0), v11 = ld_elem(p + (size_t)y1 * W + x1);
     r[((size_t)plane * DD_RESIZE + i) * DD_RESIZE + j] = bilerp(v00, v01, v10, v11, lx, ly);
 }
 
@@ -374,9 +381,21 @@ extern "C" int dd_resize256(const float* x, float* r, int B, int H, int W, void*
     DD_REQUIRE(x && r && B > 0 && H > 0 && W > 0, DD_ERR_INVALID, "dd_resize256: bad arguments");
     DD_REQUIRE((long long)B * 3 <= 65535, DD_ERR_INVALID, "dd_resize256: B too large (%d)", B);
     dim3 grid(1, DD_RESIZE, B * 3);
-    launch_pdl(resize256_kernel, grid, dim3(256), 0, (cudaStream_t)stream_, x, r, B, H, W);
+    launch_pdl(resize256_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream_, x, r, B, H, W);
     count_launch();
     return check_launch("dd_resize256");
+}
+
+extern "C" int dd_resize256_ex(const void* x, int x_dtype, float* r, int B, int H, int W, void* stream_) {
+    using namespace dd;
+    if (x_dtype == DD_F32) return dd_resize256(reinterpret_cast<const float*>(x), r, B, H, W, stream_);
+    DD_REQUIRE(x_dtype == DD_BF16, DD_ERR_INVALID, "dd_resize256_ex: unknown dtype %d", x_dtype);
+    DD_REQUIRE(x && r && B > 0 && H > 0 && W > 0, DD_ERR_INVALID, "dd_resize256_ex: bad arguments");
+    DD_REQUIRE((long long)B * 3 <= 65535, DD_ERR_INVALID, "dd_resize256_ex: B too large (%d)", B);
+    dim3 grid(1, DD_RESIZE, B * 3);
+    launch_pdl(resize256_kernel<__nv_bfloat16>, grid, dim3(256), 0, (cudaStream_t)stream_, reinterpret_cast<const __nv_bfloat16*>(x), r, B, H, W);
+    count_launch();
+    return check_launch("dd_resize256_ex");
 }
 
 extern "C" int dd_resize256_bwd(const float* dr, float* dx, int B, int H, int W, void* stream_) {

@@ -412,12 +412,12 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
 // fixed-order sum of the (CTA, plane-strip) partials, the row-coupled fix-up of columns 0..2 (d lum / d x3[:, :, :, 0..2]),
 // each CTA on a quarter of the rows; the four partial results meet through distributed shared memory in rank order and
 // CTA 0 applies the regressor Jacobians -> dfeat[b, 0..14].
-template <bool HAS_ICA, bool FAST>
+template <bool HAS_ICA, bool FAST, typename TX = float>
 __global__ void __launch_bounds__(kFinThreads)
-recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restrict__ A,
+recovery_bwd_finalize_kernel(const TX* __restrict__ x, const float* __restrict__ A,
                              const float* __restrict__ IcA, const float* __restrict__ feat,
                              const float* __restrict__ part, const float* __restrict__ Spart,
-                             float* __restrict__ dfeat, float* __restrict__ dx, int B, int H, int W, int ctas, int nsp) {
+                             float* __restrict__ dfeat, TX* __restrict__ dx, int B, int H, int W, int ctas, int nsp) {
     pdl_begin();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -444,7 +444,7 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
                 const size_t off = ((size_t)plane * H + row) * W;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    x0[e][k] = __ldg(x + off + k);
+                    x0[e][k] = btc::Elem<TX>::load1(x + off + k);
                     ica[e][k] = HAS_ICA ? __ldg(IcA + ((size_t)b * H + row) * W + k) : kDefaultIcA;
                 }
             }
@@ -481,7 +481,7 @@ recovery_bwd_finalize_kernel(const float* __restrict__ x, const float* __restric
                     ds[ch] += (double)(e2 * x1[k]);
                     const float e1 = e2 * ck.s;
                     if (tx[k] >= kTxMin) dw += (double)(e1 * (x0[e][k] - a) * ica[e][k] / (txc[k] * txc[k]));
-                    if (dx) dx[off + k] += e1 / txc[k];
+                    if (dx) btc::Elem<TX>::store1(dx + off + k, btc::Elem<TX>::load1(dx + off + k) + e1 / txc[k]);
                 }
             }
         }
@@ -586,6 +586,25 @@ static int launch_bwd_tc(const float* x, const float* A, const float* IcA, const
     return check_launch("dd_recovery_bwd (tensor-core blur)");
 }
 
+// bf16 I/O mode: x (and dx) and / or the cotangent are bf16; plain TF32 blur on the tensor cores; same finalize kernel, which
+// re-reads columns 0..2 of x -- it takes the element type as a template parameter
+template <bool HAS_ICA, typename TX, typename TG>
+static int launch_bwd_tc_io(const TX* x, const float* A, const float* IcA, const float* feat, const TG* g, float* dfeat, TX* dx, int B, int H,
+                            int W, float* ws, cudaStream_t st) {
+    constexpr int R = 48;
+    const Sched sc = make_sched(B, H, W, btc::kSchedCtasTC);
+    float* part = ws;
+    float* Spart = part + (size_t)(sc.G + sc.nPS) * kBwdSums;
+    auto kern = btc::recovery_bwd_tc_kernel<R, false, HAS_ICA, true, TX, TG>;
+    constexpr size_t smem = btc::Lay<R, false>::SMEM;
+    DD_ENSURE_SMEM(kern, smem, "recovery_bwd_tc_kernel (bf16 I/O)");
+    launch_pdl(kern, dim3(sc.G), dim3(btc::kThreadsTC), smem, st, x, A, IcA, feat, g, part, Spart, dx, B, H, W);
+    launch_pdl_cluster(recovery_bwd_finalize_kernel<HAS_ICA, true, TX>, dim3(B * kFinCluster), dim3(kFinThreads), 0, st, kFinCluster, x, A, IcA, feat,
+                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W, sc.G, sc.strips * btc::kSpartPerStrip);
+    count_launch(2);
+    return check_launch("dd_recovery_bwd_ex");
+}
+
 template <bool HAS_ICA, bool FAST, bool ALIGNED>
 static int launch_bwd3(const float* x, const float* A, const float* IcA, const float* feat, const float* g, float* dfeat,
                        float* dx, int B, int H, int W, float* ws, cudaStream_t st) {
@@ -618,6 +637,36 @@ static int launch_bwd2(const float* x, const float* A, const float* IcA, const f
 }
 
 }  // namespace dd
+
+extern "C" int dd_recovery_bwd(const float* x, const float* A, const float* IcA, const float* feat, const float* g_, float* dfeat, float* dx, int B,
+                               int H, int W, void* ws, size_t ws_bytes, void* stream_);
+
+extern "C" int dd_recovery_bwd_ex(const void* x, int x_dtype, const float* A, const float* IcA, const float* feat, const void* g_, int g_dtype,
+                                  float* dfeat, void* dx, int B, int H, int W, void* ws, size_t ws_bytes, void* stream_) {
+    using namespace dd;
+    typedef __nv_bfloat16 bf16;
+    if (x_dtype == DD_F32 && g_dtype == DD_F32)
+        return dd_recovery_bwd(reinterpret_cast<const float*>(x), A, IcA, feat, reinterpret_cast<const float*>(g_), dfeat, reinterpret_cast<float*>(dx), B, H,
+                               W, ws, ws_bytes, stream_);
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (int e = check_recovery_shape("dd_recovery_bwd_ex", B, H, W)) return e;
+    DD_REQUIRE((x_dtype == DD_F32 || x_dtype == DD_BF16) && (g_dtype == DD_F32 || g_dtype == DD_BF16), DD_ERR_INVALID, "dd_recovery_bwd_ex: unknown dtype");
+    DD_REQUIRE(x && feat && g_ && dfeat, DD_ERR_INVALID, "dd_recovery_bwd_ex: null pointer");
+    DD_REQUIRE(ws && ws_bytes >= recovery_bwd_ws_bytes(B, H, W), DD_ERR_WORKSPACE, "dd_recovery_bwd_ex: workspace %zu < %zu", ws_bytes,
+               recovery_bwd_ws_bytes(B, H, W));
+    DD_REQUIRE((W & 3) == 0 && H > kRadius + 1 && W > kRadius + 1 && (((uintptr_t)x | (uintptr_t)g_ | (uintptr_t)dx) & 15) == 0, DD_ERR_INVALID,
+               "dd_recovery_bwd_ex: the bf16 I/O mode needs W %% 4 == 0, H and W >= 14 and 16-byte aligned x / g / dx (got %d x %d)", H, W);
+    float* w = reinterpret_cast<float*>(ws);
+#define DD_BWD_IO(TX, TG)                                                                                                                       \
+    return IcA ? launch_bwd_tc_io<true, TX, TG>(reinterpret_cast<const TX*>(x), A, IcA, feat, reinterpret_cast<const TG*>(g_), dfeat,              \
+                                                reinterpret_cast<TX*>(dx), B, H, W, w, st)                                                        \
+               : launch_bwd_tc_io<false, TX, TG>(reinterpret_cast<const TX*>(x), A, nullptr, feat, reinterpret_cast<const TG*>(g_), dfeat,         \
+                                                 reinterpret_cast<TX*>(dx), B, H, W, w, st)
+    if (x_dtype == DD_BF16 && g_dtype == DD_BF16) { DD_BWD_IO(bf16, bf16); }
+    if (x_dtype == DD_BF16) { DD_BWD_IO(bf16, float); }
+    DD_BWD_IO(float, bf16);
+#undef DD_BWD_IO
+}
 
 extern "C" int dd_recovery_bwd(const float* x, const float* A, const float* IcA, const float* feat, const float* g_,
                                float* dfeat, float* dx, int B, int H, int W, void* ws, size_t ws_bytes,

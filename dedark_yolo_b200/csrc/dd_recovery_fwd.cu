@@ -336,6 +336,45 @@ static int launch_fwd2(const float* x, const float* A, const float* IcA, const f
 
 }  // namespace dd
 
+namespace dd {
+// bf16 I/O mode (the reference trains under autocast, engine/trainer.py:330): x and / or y are bf16, the
+// blur runs as plain TF32 on the tensor cores (no operand split: bf16 values are exact in TF32), fp32 arithmetic in between.
+template <bool HAS_ICA, typename TX, typename TY>
+static int launch_fwd_tc_io(const TX* x, const float* A, const float* IcA, const float* feat, TY* y, int B, int H, int W, cudaStream_t st) {
+    constexpr int R = 48;
+    const Sched sc = make_sched(B, H, W, btc::kSchedCtasTC);
+    auto kern = btc::recovery_fwd_tc_kernel<R, false, HAS_ICA, true, false, TX, TY>;
+    constexpr size_t smem = btc::Lay<R, false>::SMEM;
+    DD_ENSURE_SMEM(kern, smem, "recovery_fwd_tc_kernel (bf16 I/O)");
+    launch_pdl(kern, dim3(sc.G), dim3(btc::kThreadsTC), smem, st, x, A, IcA, feat, y, B, H, W);
+    count_launch();
+    return check_launch("dd_recovery_fwd_ex");
+}
+}  // namespace dd
+
+extern "C" int dd_recovery_fwd(const float* x, const float* A, const float* IcA, const float* feat, float* y, int B, int H, int W, void* stream_);
+
+extern "C" int dd_recovery_fwd_ex(const void* x, int x_dtype, const float* A, const float* IcA, const float* feat, void* y, int y_dtype,
+                                  int B, int H, int W, void* stream_) {
+    using namespace dd;
+    typedef __nv_bfloat16 bf16;
+    if (x_dtype == DD_F32 && y_dtype == DD_F32)
+        return dd_recovery_fwd(reinterpret_cast<const float*>(x), A, IcA, feat, reinterpret_cast<float*>(y), B, H, W, stream_);
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (int e = check_recovery_shape("dd_recovery_fwd_ex", B, H, W)) return e;
+    DD_REQUIRE((x_dtype == DD_F32 || x_dtype == DD_BF16) && (y_dtype == DD_F32 || y_dtype == DD_BF16), DD_ERR_INVALID, "dd_recovery_fwd_ex: unknown dtype");
+    DD_REQUIRE(x && feat && y && x != y, DD_ERR_INVALID, "dd_recovery_fwd_ex: null pointer or y aliases x");
+    DD_REQUIRE((W & 3) == 0 && ((uintptr_t)x & 15) == 0 && (!IcA || ((uintptr_t)IcA & 15) == 0), DD_ERR_INVALID,
+               "dd_recovery_fwd_ex: the bf16 I/O mode needs W %% 4 == 0 and 16-byte aligned x / IcA (got W = %d)", W);
+#define DD_FWD_IO(TX, TY)                                                                                                          \
+    return IcA ? launch_fwd_tc_io<true, TX, TY>(reinterpret_cast<const TX*>(x), A, IcA, feat, reinterpret_cast<TY*>(y), B, H, W, st) \
+               : launch_fwd_tc_io<false, TX, TY>(reinterpret_cast<const TX*>(x), A, nullptr, feat, reinterpret_cast<TY*>(y), B, H, W, st)
+    if (x_dtype == DD_BF16 && y_dtype == DD_BF16) { DD_FWD_IO(bf16, bf16); }
+    if (x_dtype == DD_BF16) { DD_FWD_IO(bf16, float); }
+    DD_FWD_IO(float, bf16);
+#undef DD_FWD_IO
+}
+
 // unit-test hook: the bare reflect-padded 25x25 Gaussian (filtersB.py:154-175: F.pad reflect + conv2d) of x through the
 // tensor-core engine, x3 != 0: 3xTF32, else 1xTF32.  Needs W % 4 == 0 and 16-byte aligned x.
 extern "C" int dd_debug_blur_tc(const float* x, float* y, int B, int H, int W, int x3, void* stream_) {

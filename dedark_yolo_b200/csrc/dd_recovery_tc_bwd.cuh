@@ -15,11 +15,12 @@ namespace btc {
 
 constexpr int kSpartPerStrip = 4;  // row-sum partials per (row, strip): one per 32-column quarter
 
-template <int R, bool X3, bool HAS_ICA, bool FAST>
+// TX / TG: element types of x (and dx) and of the cotangent g (float, or __nv_bfloat16 in the bf16 I/O mode)
+template <int R, bool X3, bool HAS_ICA, bool FAST, typename TX = float, typename TG = float>
 __global__ void __launch_bounds__(kThreadsTC, 1)
-recovery_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
-                       const float* __restrict__ feat, const float* __restrict__ g, float* __restrict__ part,
-                       float* __restrict__ Spart, float* __restrict__ dx, int B, int H, int W) {
+recovery_bwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
+                       const float* __restrict__ feat, const TG* __restrict__ g, float* __restrict__ part,
+                       float* __restrict__ Spart, TX* __restrict__ dx, int B, int H, int W) {
     using L = Lay<R, X3>;
     using SG = StageGeo<L>;
     static_assert(R == 48, "the stage / epilogue work split assumes 48-row blocks (12 row groups x 4 rows, 12 outputs per warp)");
@@ -62,7 +63,7 @@ recovery_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A,
 
         // ---- stage side: the cotangent needs no parameters, only geometry ---------------------------------------------------------
         SG sg;
-        const float* gp = g;
+        const TG* gp = g;
         int rowbase = 0, nU = 0;
         float fc[4];   // column factors of g^: the image-border columns are doubled in place; mirrored copies (halo chunks) are not
         float4 in[4];  // the block in flight between stage_load and stage_store
@@ -135,9 +136,9 @@ recovery_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A,
         ChainK ck;
         float pp = 0.f, hc = 1.f;
         bool col_ok = false;
-        const float* xcol = x;
+        const TX* xcol = x;
         const float* icol = IcA;
-        float* dxcol = nullptr;
+        TX* dxcol = nullptr;
         float* spcol = Spart;
         int e_r0 = 0, e_len = 0;
         int ep_ts = -100;  // time-stamp slot of the epilogue in flight (DD_BTC_TIMING only)
@@ -151,7 +152,7 @@ recovery_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A,
             ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
             const float pc = sp.c;
             pp = sp.p;
-            const float* xp = x + (size_t)u.plane * H * W;
+            const TX* xp = x + (size_t)u.plane * H * W;
             const float* ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
             for (int v = tid; v < u.nU; v += kCT) {  // rows outside the image: 0
                 const int row = u.r0 - kRadius + v;
@@ -160,7 +161,7 @@ recovery_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A,
                     float x3[3];
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc)
-                        x3[cc] = chain_x3<HAS_ICA, FAST>(ck, __ldg(xp + (size_t)row * W + cc), HAS_ICA ? __ldg(ip + (size_t)row * W + cc) : kDefaultIcA);
+                        x3[cc] = chain_x3<HAS_ICA, FAST>(ck, Elem<TX>::load1(xp + (size_t)row * W + cc), HAS_ICA ? __ldg(ip + (size_t)row * W + cc) : kDefaultIcA);
                     const RowLum rl = row_lum<false>(x3[0], x3[1], x3[2]);
                     q1 = rl.q - 1.f;
                     m = (1.f - pc) + pc * rl.q;
@@ -191,7 +192,7 @@ recovery_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A,
                 x0v[i] = 0.f;
                 icv[i] = kDefaultIcA;
                 if (i >= i_lo && i < i_hi && col_ok) {
-                    x0v[i] = __ldg(xcol + (eoff + i * W));
+                    x0v[i] = Elem<TX>::load1(xcol + (eoff + i * W));
                     if (HAS_ICA) icv[i] = __ldg(icol + (eoff + i * W));
                 }
             }
@@ -218,7 +219,7 @@ recovery_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A,
                     float srow = 0.f;
                     if (col_ok) {
                         const float d = px_bwd<HAS_ICA, FAST>(x0v[i], icv[i], gext * fac, bt[i] * fac, msm[i], msq[i], ck, pp, acc, srow);
-                        if (dx) dxcol[eoff + i * W] = d;
+                        if (dx) Elem<TX>::store1(dxcol + (eoff + i * W), d);
                     }
                     srow = warp_sum(srow);
                     if (lane == 0) spcol[(size_t)jr * nsp] = srow;

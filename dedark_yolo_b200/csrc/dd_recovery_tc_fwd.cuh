@@ -20,10 +20,11 @@ namespace dd {
 namespace btc {
 
 // DBG: identity chain (x4 = x0) and y = blur -- the bare reflect-padded 25x25 Gaussian, for the tensor-core unit test
-template <int R, bool X3, bool HAS_ICA, bool FAST, bool DBG>
+// TX / TY: element types of x and y (float, or __nv_bfloat16 in the bf16 I/O mode; IcA, A and feat are always fp32)
+template <int R, bool X3, bool HAS_ICA, bool FAST, bool DBG, typename TX = float, typename TY = float>
 __global__ void __launch_bounds__(kThreadsTC, 1)
-recovery_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
-                       const float* __restrict__ feat, float* __restrict__ y, int B, int H, int W) {
+recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, const float* __restrict__ IcA,
+                       const float* __restrict__ feat, TY* __restrict__ y, int B, int H, int W) {
     using L = Lay<R, X3>;
     using SG = StageGeo<L>;
     static_assert(R == 48, "the stage / epilogue work split assumes 48-row blocks (12 row groups x 4 rows, 12 outputs per warp)");
@@ -64,7 +65,7 @@ recovery_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A,
         // ---- stage side -------------------------------------------------------------------------------------------------------
         SG sg;
         ChainK ck;
-        const float* xp = x;
+        const TX* xp = x;
         const float* ip = IcA;
         int rowbase = 0, nU = 0;
         float4 in[4], ic[4];  // the block in flight between stage_load and stage_store
@@ -86,7 +87,7 @@ recovery_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A,
                     const size_t ro = (size_t)reflect(rowbase + v, H) * W;
                     float x3[3];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) x3[c] = chain_x3<HAS_ICA, FAST>(ck, __ldg(xp + ro + c), HAS_ICA ? __ldg(ip + ro + c) : kDefaultIcA);
+                    for (int c = 0; c < 3; ++c) x3[c] = chain_x3<HAS_ICA, FAST>(ck, Elem<TX>::load1(xp + ro + c), HAS_ICA ? __ldg(ip + ro + c) : kDefaultIcA);
                     const RowLum rl = row_lum<true>(x3[0], x3[1], x3[2]);
                     MS[v] = (1.f - pc) + pc * rl.q;
                 }
@@ -146,7 +147,7 @@ recovery_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A,
         // centre values: the first 12 outputs of a block sit on the tail of the previous block (side slot, exact fp32), the others
         // on rows 12 (gq - 1) + i of the block's own tile (hi + lo); 16 bytes between consecutive rows in both
         const int ctr_off = gq == 0 ? (c >> 2) * L::S_LBO + (c & 3) * 4 : tile_off<L>(L::RPW * (gq - 1), c + kRadius);
-        float* ys = y;
+        TY* ys = y;
         bool col_ok = false;
         float pp = 0.f;
         int e_r0 = 0, e_len = 0;
@@ -177,7 +178,7 @@ recovery_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ A,
             auto one = [&](int i) {
                 float x4 = *reinterpret_cast<const float*>(ctr + 16 * i);
                 if (X3 && gq != 0) x4 += *reinterpret_cast<const float*>(ctr + 16 * i + L::T_BYTES);
-                __stcs(ys + (yoff + i * W), DBG ? bl[i] : fmaf(x4 - bl[i], pp, x4));
+                Elem<TY>::store1_streaming(ys + (yoff + i * W), DBG ? bl[i] : fmaf(x4 - bl[i], pp, x4));
             };
             if (i_lo == 0 && i_hi == L::RPW) {  // the common case: every output row of the warp lies inside the segment
 #pragma unroll

@@ -94,6 +94,12 @@ class _FilterSlot(nn.Module):
 
 
 class lowlight_recovery(nn.Module):
+    # bf16 I/O mode (the reference trains under autocast, engine/trainer.py:330).  A bf16 input is read
+    # in place (half the bytes; the blur then runs as TF32 tensor-core GEMMs, 2e-2 gate); the OUTPUT stays fp32 -- the dtype
+    # the reference returns, because its fp32 defaults promote -- unless ``out_dtype = torch.bfloat16`` is set, in which case
+    # y and therefore the cotangent autograd hands back are bf16 as well.  An extra attribute, not part of the state-dict.
+    out_dtype = None
+
     def __init__(self, in_channels=3, out_channels=3):
         super().__init__()
         self.extractor = ExtractParameters2()

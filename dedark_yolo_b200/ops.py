@@ -37,16 +37,35 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
+_DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16}
+
+
+def bf16_io_supported(H: int, W: int) -> bool:
+    """Shapes the bf16 I/O kernels accept (16-byte rows; the tensor-core backward needs the borders > one blur radius apart)."""
+    return W % 4 == 0 and H >= 14 and W >= 14
+
+
+def _img(t: torch.Tensor) -> torch.Tensor:
+    """An image operand as the kernels read it: contiguous fp32 or bf16 (anything else is promoted to fp32)."""
+    t = t.detach()
+    if t.dtype not in _DT:
+        t = t.to(torch.float32)
+    return t.contiguous()
+
+
 # ---- a1 + a2 ---------------------------------------------------------------------------------------
 def synth_forward(src: torch.Tensor, p: float, lut: Optional[torch.Tensor] = None,
                   clean_lut: Optional[torch.Tensor] = None, want_clean: bool = True,
-                  want_dark: bool = True, want_u8: bool = False, want_rec: bool = True):
+                  want_dark: bool = True, want_u8: bool = False, want_rec: bool = True, dark_dtype=torch.float32):
     """Low-light synthesis + recovery-loss scalar in one pass (train.py:72,79,103,108-109).
 
     ``src``: uint8 or float32 CUDA tensor of any shape.  ``lut`` / ``clean_lut``: optional 256-entry tables that
     override the device-computed ``pow(k/255, p)`` / ``k/255`` (see ``reference_cpu_tables``).  Returns ``(clean, dark, dark_u8, rec)``; entries not
-    requested are None.  For a float32 source ``clean`` is ``src`` itself."""
+    requested are None.  For a float32 source ``clean`` is ``src`` itself.  ``dark_dtype=torch.bfloat16`` (bf16 I/O mode) stores the
+    darkened image rounded to bf16; the loss is always reduced from the exact fp32 values."""
     _need_cuda(src, lut)
+    if dark_dtype not in _DT:
+        raise TypeError(f"synth_forward: dark_dtype must be float32 or bfloat16, got {dark_dtype}")
     if src.dtype not in (torch.uint8, torch.float32):
         raise TypeError(f"synth_forward: uint8 or float32 source expected, got {src.dtype}")
     src = src.contiguous()
@@ -54,7 +73,7 @@ def synth_forward(src: torch.Tensor, p: float, lut: Optional[torch.Tensor] = Non
     dev, n = src.device, src.numel()
     with torch.cuda.device(dev):
         clean = torch.empty(src.shape, dtype=torch.float32, device=dev) if (is_u8 and want_clean) else None
-        dark = torch.empty(src.shape, dtype=torch.float32, device=dev) if want_dark else None
+        dark = torch.empty(src.shape, dtype=dark_dtype, device=dev) if want_dark else None
         dark_u8 = torch.empty(src.shape, dtype=torch.uint8, device=dev) if want_u8 else None
         rec = torch.empty((), dtype=torch.float32, device=dev) if want_rec else None
         ws_bytes = _lib.workspace_bytes(_lib.WS_SYNTH, 1)
@@ -68,9 +87,9 @@ def synth_forward(src: torch.Tensor, p: float, lut: Optional[torch.Tensor] = Non
                     raise ValueError("lookup tables must have 256 entries")
             luts.append(t)
         lut, clean_lut = luts
-        check(lib.dd_synth_fwd(_ptr(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, float(p), _ptr(lut), _ptr(clean_lut), _ptr(clean),
-                               _ptr(dark), _ptr(dark_u8), _ptr(rec), n, _ptr(ws), ws_bytes if want_rec else 0,
-                               _stream(dev)))
+        check(lib.dd_synth_fwd_ex(_ptr(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, float(p), _ptr(lut), _ptr(clean_lut), _ptr(clean),
+                                  _ptr(dark), _DT[dark_dtype], _ptr(dark_u8), _ptr(rec), n, _ptr(ws), ws_bytes if want_rec else 0,
+                                  _stream(dev)))
     if not is_u8 and want_clean:
         clean = src
     return clean, dark, dark_u8, rec
@@ -119,13 +138,14 @@ def reference_cpu_tables(p: float, device):
 
 # ---- a4 / a5 ---------------------------------------------------------------------------------------
 def resize256(x: torch.Tensor) -> torch.Tensor:
+    """[B,3,H,W] fp32 or bf16 -> [B,3,256,256] fp32 (llie.py:43)."""
     _need_cuda(x)
-    x = _f32c(x)
+    x = _img(x)
     B, Cc, H, W = x.shape
     assert Cc == 3
     r = torch.empty(B, 3, RESIZE, RESIZE, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib.dd_resize256(_ptr(x), _ptr(r), B, H, W, _stream(x.device)))
+        check(lib.dd_resize256_ex(_ptr(x), _DT[x.dtype], _ptr(r), B, H, W, _stream(x.device)))
     return r
 
 
@@ -164,17 +184,19 @@ def predictor_backward(r, params, acts, dfeat, need_dr: bool = False, flat_grad:
 
 
 # ---- a6..a12, a14 ----------------------------------------------------------------------------------
-def filters_forward(x, feat, A=None, IcA=None) -> torch.Tensor:
+def filters_forward(x, feat, A=None, IcA=None, out_dtype=None) -> torch.Tensor:
+    """The fused filter chain.  ``x`` fp32 or bf16; ``out_dtype`` fp32 (default, the reference's output dtype) or bf16.  With a
+    bf16 operand the call runs in the bf16 I/O mode (``dd_recovery_fwd_ex``: TF32 blur on the tensor cores, 2e-2 gate)."""
     _need_cuda(x, feat, A, IcA)
     B, _, H, W = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty(x.shape, dtype=out_dtype or torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib.dd_recovery_fwd(_ptr(x), _ptr(A), _ptr(IcA), _ptr(feat), _ptr(y), B, H, W, _stream(x.device)))
+        check(lib.dd_recovery_fwd_ex(_ptr(x), _DT[x.dtype], _ptr(A), _ptr(IcA), _ptr(feat), _ptr(y), _DT[y.dtype], B, H, W, _stream(x.device)))
     return y
 
 
 def filters_backward(x, feat, g, A=None, IcA=None, need_dx: bool = False):
-    """Returns (dfeat [B,15], dx or None)."""
+    """Returns (dfeat [B,15], dx or None).  ``x`` / ``g`` fp32 or bf16 (bf16 I/O mode when either is bf16); dx has x's dtype."""
     _need_cuda(x, feat, g, A, IcA)
     B, _, H, W = x.shape
     dev = x.device
@@ -183,8 +205,8 @@ def filters_backward(x, feat, g, A=None, IcA=None, need_dx: bool = False):
     ws_bytes = _lib.workspace_bytes(_lib.WS_RECOVERY_BWD, B, H, W)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        check(lib.dd_recovery_bwd(_ptr(x), _ptr(A), _ptr(IcA), _ptr(feat), _ptr(g), _ptr(dfeat), _ptr(dx), B, H, W,
-                                  _ptr(ws), ws_bytes, _stream(dev)))
+        check(lib.dd_recovery_bwd_ex(_ptr(x), _DT[x.dtype], _ptr(A), _ptr(IcA), _ptr(feat), _ptr(g), _DT[g.dtype], _ptr(dfeat), _ptr(dx), B, H, W,
+                                     _ptr(ws), ws_bytes, _stream(dev)))
     return dfeat, dx
 
 
@@ -288,6 +310,13 @@ def _ready(t: torch.Tensor, dev) -> bool:
     return t.device == dev and t.dtype == torch.float32 and t.is_contiguous()
 
 
+def _ready_img(t: torch.Tensor, dev) -> bool:
+    """An image the kernels can read in place: fp32, or bf16 on a shape the bf16 I/O kernels accept."""
+    if t.device != dev or not t.is_contiguous():
+        return False
+    return t.dtype == torch.float32 or (t.dtype == torch.bfloat16 and bf16_io_supported(t.shape[2], t.shape[3]))
+
+
 class RecoveryFunction(torch.autograd.Function):
     """lowlight_recovery.forward as one autograd node: resize -> predictor -> fused filter chain.
 
@@ -304,8 +333,17 @@ class RecoveryFunction(torch.autograd.Function):
             raise NotImplementedError("lowlight_recovery (dedark_yolo_b200): gradients w.r.t. dedark_A / IcA are not implemented; "
                                       "detach them (the reference trainer passes constants)")
         out_dev = x.device
-        xd = x.detach() if _ready(x, device) else _f32c(x.to(device))
+        # bf16 input on a supported shape: read in place (bf16 I/O mode); anything else is promoted to fp32 as in the reference
+        # (a bf16 x that requires grad -- ad-hoc tests only, x is data in training -- takes the fp32 route: the resize adjoint
+        # accumulates into an fp32 dx)
+        in_place = _ready_img(x, device) and not (x.dtype == torch.bfloat16 and ctx.needs_input_grad[2])
+        xd = x.detach() if in_place else _f32c(x.to(device))
         B, _, H, W = xd.shape
+        out_dtype = getattr(owner, "out_dtype", None)
+        if out_dtype not in (None, torch.float32, torch.bfloat16):
+            raise TypeError(f"lowlight_recovery.out_dtype must be None, float32 or bfloat16, got {out_dtype}")
+        if out_dtype == torch.bfloat16 and not bf16_io_supported(H, W):
+            out_dtype = None  # shapes the bf16 kernels do not take: fp32 kernels, fp32 output
         Ad = None if A is None else _f32c(A.to(device)).reshape(B, 3)
         Id = None if IcA is None else _f32c(IcA.to(device)).expand(B, 1, H, W).contiguous()
         pd = [q.detach() if _ready(q, device) else _f32c(q.to(device)) for q in params]
@@ -316,10 +354,10 @@ class RecoveryFunction(torch.autograd.Function):
         try:
             st = _stream(device)
             w = _weights_struct(pl, pd)
-            y = torch.empty_like(xd)
-            check(lib.dd_resize256(_ptr(xd), _ptr(pl.r), B, H, W, st))
+            y = torch.empty(xd.shape, dtype=out_dtype or torch.float32, device=device)
+            check(lib.dd_resize256_ex(_ptr(xd), _DT[xd.dtype], _ptr(pl.r), B, H, W, st))
             check(lib.dd_predictor_fwd(_ptr(pl.r), C.byref(w), _ptr(pl.acts), _ptr(pl.feat), B, st))
-            check(lib.dd_recovery_fwd(_ptr(xd), _ptr(Ad), _ptr(Id), _ptr(pl.feat), _ptr(y), B, H, W, st))
+            check(lib.dd_recovery_fwd_ex(_ptr(xd), _DT[xd.dtype], _ptr(Ad), _ptr(Id), _ptr(pl.feat), _ptr(y), _DT[y.dtype], B, H, W, st))
         finally:
             if prev != device.index:
                 torch.cuda.set_device(prev)
@@ -337,7 +375,7 @@ class RecoveryFunction(torch.autograd.Function):
         pl, dev = ctx.plan, ctx.st_dev
         B, _, H, W = xd.shape
         need_dx = ctx.needs_input_grad[2]
-        gd = g if _ready(g, dev) else _f32c(g.to(dev))
+        gd = g if _ready_img(g, dev) else _f32c(g.to(dev))
         prev = torch.cuda.current_device()
         if prev != dev.index:
             torch.cuda.set_device(dev)
@@ -352,7 +390,7 @@ class RecoveryFunction(torch.autograd.Function):
         st = _stream(dev)
         w = _weights_struct(pl, pd)
         if pl.version != ctx.version:  # another forward of this shape ran in between: its activations replaced ours
-            check(lib.dd_resize256(_ptr(xd), _ptr(pl.r), B, H, W, st))
+            check(lib.dd_resize256_ex(_ptr(xd), _DT[xd.dtype], _ptr(pl.r), B, H, W, st))
             check(lib.dd_predictor_fwd(_ptr(pl.r), C.byref(w), _ptr(pl.acts), _ptr(pl.feat), B, st))
             pl.version += 1
             ctx.version = pl.version
@@ -362,8 +400,8 @@ class RecoveryFunction(torch.autograd.Function):
         flat = torch.empty(_OFFS[14], dtype=torch.float32, device=dev)
         dx = torch.empty_like(xd) if need_dx else None
         dr = torch.empty_like(pl.r) if need_dx else None
-        check(lib.dd_recovery_bwd(_ptr(xd), _ptr(Ad), _ptr(Id), _ptr(pl.feat), _ptr(gd), _ptr(pl.dfeat), _ptr(dx), B, H, W,
-                                  _ptr(pl.ws_rb), pl.ws_rb.numel(), st))
+        check(lib.dd_recovery_bwd_ex(_ptr(xd), _DT[xd.dtype], _ptr(Ad), _ptr(Id), _ptr(pl.feat), _ptr(gd), _DT[gd.dtype], _ptr(pl.dfeat), _ptr(dx),
+                                     B, H, W, _ptr(pl.ws_rb), pl.ws_rb.numel(), st))
         gs = _grad_struct(flat.data_ptr())
         check(lib.dd_predictor_bwd(_ptr(pl.r), C.byref(w), _ptr(pl.acts), _ptr(pl.dfeat), C.byref(gs), _ptr(dr), B, _ptr(pl.ws_pb),
                                    pl.ws_pb.numel(), st))

@@ -33,12 +33,18 @@ def _p(t):
 class RecoveryPipeline:
     def __init__(self, module: lowlight_recovery, B: int, H: int, W: int, dark_param: float = 15.0,
                  src_dtype: torch.dtype = torch.float32, device=None, process_group=None, allreduce: bool = False,
-                 exchange=None, keep_clean: bool = False):
+                 exchange=None, keep_clean: bool = False, io_dtype: torch.dtype = torch.float32):
         dev = torch.device(device if device is not None else next(module.parameters()).device)
         if dev.type != "cuda":
             raise RuntimeError("RecoveryPipeline needs a CUDA device (no CPU fallback)")
         self.dev, self.B, self.H, self.W, self.p = dev, B, H, W, float(dark_param)
         self.src_dtype = src_dtype
+        # bf16 I/O mode: the darkened batch, y and the cotangent g are bf16 (TF32 blur on the tensor cores, 2e-2 gate); r, the
+        # predictor, feat / dfeat and the gradients stay fp32
+        if io_dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("io_dtype must be float32 or bfloat16")
+        self.io_dtype = io_dtype
+        self._dt = _lib.DT_BF16 if io_dtype == torch.bfloat16 else _lib.DT_F32
         # uint8 sources: the fp32 clean image (train.py:72, ``batch["clean_img"]``) is only an operand of the recovery loss, which
         # the synthesis pass has already reduced -- it is materialised (one more full-size write) only on request
         self.keep_clean = keep_clean
@@ -57,7 +63,7 @@ class RecoveryPipeline:
         self._side = None
         self.acts = torch.empty(_lib.workspace_bytes(_lib.WS_PREDICTOR_ACTS, B) // 4, **f32)
         self.feat = torch.empty(B, 15, **f32)
-        self.y = torch.empty(B, 3, H, W, **f32)
+        self.y = torch.empty(B, 3, H, W, dtype=io_dtype, device=dev)
         self.dfeat = torch.empty(B, 15, **f32)
         self._ws_pb = torch.empty(_lib.workspace_bytes(_lib.WS_PREDICTOR_BWD, B), dtype=torch.uint8, device=dev)
         self._ws_rb = torch.empty(_lib.workspace_bytes(_lib.WS_RECOVERY_BWD, B, H, W), dtype=torch.uint8, device=dev)
@@ -71,7 +77,7 @@ class RecoveryPipeline:
         # uint8 batches: synthesis and the module's 256x256 resize in ONE pass when the size allows it (W % 4 == 0, band fits in
         # shared memory) -- that pass is HBM bound and the fusion saves the re-read of the dark batch (e2e +7 %).  fp32 sources stay
         # on two passes: their synthesis is issue bound on the exact powf and the fused kernel measured 8 us slower than the pair.
-        self.fused_resize = src_dtype == torch.uint8 and bool(lib.dd_synth_resize_supported(H, W))
+        self.fused_resize = src_dtype == torch.uint8 and io_dtype == torch.float32 and bool(lib.dd_synth_resize_supported(H, W))
         self.graphs = {}
 
     # -- per-batch buffers: what the synthesis writes and the rest of the step reads ---------------------
@@ -83,7 +89,7 @@ class RecoveryPipeline:
         B, H, W = self.B, self.H, self.W
         s = self._Slot()
         s.clean = torch.empty(B, 3, H, W, **f32) if (self.src_dtype == torch.uint8 and self.keep_clean) else None
-        s.dark = torch.empty(B, 3, H, W, **f32)
+        s.dark = torch.empty(B, 3, H, W, dtype=self.io_dtype, device=self.dev)
         s.rec = torch.zeros((), **f32)
         s.r = torch.empty(B, 3, 256, 256, **f32)
         s.ws_syn = torch.empty(_lib.workspace_bytes(_lib.WS_SYNTH, B), dtype=torch.uint8, device=self.dev)
@@ -104,25 +110,25 @@ class RecoveryPipeline:
                                           _p(s.clean), _p(s.dark), _p(s.r), _p(s.rec), self.B, self.H,
                                           self.W, _p(s.ws_syn), s.ws_syn.numel(), st))
             return
-        check(lib.dd_synth_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None, _p(s.clean),
-                               _p(s.dark), None, _p(s.rec), src.numel(), _p(s.ws_syn), s.ws_syn.numel(), st))
+        check(lib.dd_synth_fwd_ex(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None, _p(s.clean),
+                                  _p(s.dark), self._dt, None, _p(s.rec), src.numel(), _p(s.ws_syn), s.ws_syn.numel(), st))
 
     def resize(self, st, slot=None):
         s = self._slots[self._cur if slot is None else slot]
         if not self.fused_resize:
-            check(lib.dd_resize256(_p(s.dark), _p(s.r), self.B, self.H, self.W, st))
+            check(lib.dd_resize256_ex(_p(s.dark), self._dt, _p(s.r), self.B, self.H, self.W, st))
 
     def forward(self, st, A=None, IcA=None, resize=True):
         B, H, W = self.B, self.H, self.W
         if resize:
             self.resize(st)
         check(lib.dd_predictor_fwd(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.feat), B, st))
-        check(lib.dd_recovery_fwd(_p(self.dark), _p(A), _p(IcA), _p(self.feat), _p(self.y), B, H, W, st))
+        check(lib.dd_recovery_fwd_ex(_p(self.dark), self._dt, _p(A), _p(IcA), _p(self.feat), _p(self.y), self._dt, B, H, W, st))
 
     def backward_filters(self, g, st, A=None, IcA=None):
         B, H, W = self.B, self.H, self.W
-        check(lib.dd_recovery_bwd(_p(self.dark), _p(A), _p(IcA), _p(self.feat), _p(g), _p(self.dfeat), None, B, H, W,
-                                  _p(self._ws_rb), self._ws_rb.numel(), st))
+        check(lib.dd_recovery_bwd_ex(_p(self.dark), self._dt, _p(A), _p(IcA), _p(self.feat), _p(g), self._dt, _p(self.dfeat), None, B, H, W,
+                                     _p(self._ws_rb), self._ws_rb.numel(), st))
 
     def backward_predictor(self, st):
         B = self.B
@@ -139,7 +145,7 @@ class RecoveryPipeline:
 
     def step(self, src: torch.Tensor, g: torch.Tensor):
         """One full pass: ``src`` is the clean batch (uint8 or fp32 [B,3,H,W]), ``g`` the cotangent dL/dy."""
-        assert src.shape == (self.B, 3, self.H, self.W) and g.shape == src.shape and g.dtype == torch.float32
+        assert src.shape == (self.B, 3, self.H, self.W) and g.shape == src.shape and g.dtype == self.io_dtype
         with torch.cuda.device(self.dev):
             st = torch.cuda.current_stream(self.dev).cuda_stream
             self.synth(src, st)
@@ -171,7 +177,7 @@ class RecoveryPipeline:
         ``src_next`` overlapped with the predictor backward on a side stream.  Returns ``(y, rec, flat_grad)`` of the batch
         consumed; ``rec`` is that batch's recovery loss.  ``src_next=None`` ends the sequence (nothing is synthesised)."""
         assert self._side is not None, "call prime() first"
-        assert g.shape == (self.B, 3, self.H, self.W) and g.dtype == torch.float32
+        assert g.shape == (self.B, 3, self.H, self.W) and g.dtype == self.io_dtype
         with torch.cuda.device(self.dev):
             main = torch.cuda.current_stream(self.dev)
             st = main.cuda_stream

@@ -44,6 +44,10 @@ extern "C" {
 #define DD_WS_PREDICTOR_BWD 2  /* scratch of dd_predictor_bwd                                      */
 #define DD_WS_RECOVERY_BWD 3   /* partial sums of dd_recovery_bwd                                  */
 
+/* element types of the *_ex entry points (bf16 I/O mode) */
+#define DD_F32 1
+#define DD_BF16 2
+
 /* source dtypes for dd_synth_fwd */
 #define DD_SRC_U8 0
 #define DD_SRC_F32 1
@@ -147,6 +151,23 @@ int dd_recovery_fwd(const float* x, const float* A, const float* IcA, const floa
 int dd_recovery_bwd(const float* x, const float* A, const float* IcA, const float* feat,
                     const float* g, float* dfeat, float* dx, int B, int H, int W, void* ws,
                     size_t ws_bytes, void* stream);
+
+/* ---- bf16 I/O mode ---------------------------------------------------------------------------------
+ * The reference trains under autocast (engine/trainer.py:330); SURVEY.md section 8(d): x and the cotangent are read as bf16
+ * (6 bytes per pixel instead of 12), y is fp32 like the reference's output unless the caller opts into bf16.  Same
+ * semantics as the fp32 entry points with element types DD_F32 / DD_BF16 for x (and dx), y and g; A, IcA, feat, dfeat and r
+ * stay fp32.  When any of them is bf16 the blur runs as plain TF32 tcgen05 GEMMs (bf16 values are exact in TF32; gate
+ * 2e-2 relative to the reference on the same bf16-rounded input) and the shape must satisfy W % 4 == 0 (backward: also H,
+ * W >= 14); with all-fp32 types the calls forward to dd_recovery_fwd / dd_recovery_bwd / dd_resize256. */
+int dd_synth_fwd_ex(const void* src, int src_dtype, float p, const float* lut256, const float* clean_lut256,
+                    float* clean_out, void* dark_out, int dark_dtype, uint8_t* dark_u8, float* rec_out, long long n,
+                    void* ws, size_t ws_bytes, void* stream);   /* dark_out fp32 or bf16 (rounded to nearest even from the exact fp32 value; the loss uses the fp32 value) */
+int dd_resize256_ex(const void* x, int x_dtype, float* r, int B, int H, int W, void* stream);
+int dd_recovery_fwd_ex(const void* x, int x_dtype, const float* A, const float* IcA, const float* feat, void* y,
+                       int y_dtype, int B, int H, int W, void* stream);
+int dd_recovery_bwd_ex(const void* x, int x_dtype, const float* A, const float* IcA, const float* feat,
+                       const void* g, int g_dtype, float* dfeat, void* dx, int B, int H, int W, void* ws,
+                       size_t ws_bytes, void* stream);
 
 /* ---- unit-test hook of the tensor-core blur engine -------------------------------------------------
  * y = the reflect-padded 25x25 Gaussian of x (filtersB.py:154-175: F.pad(..., 'reflect') + conv2d per channel), computed by

@@ -107,3 +107,28 @@ if __name__ == "__main__":
     check_fused()
     if "quick" not in sys.argv:
         timing()
+
+
+def timing_bf16():
+    """Filter forward / backward in the bf16 I/O mode (bf16 x, y, g) at 16x3x640x640."""
+    B, H, W = 16, 640, 640
+    gen = torch.Generator(device=dev).manual_seed(1)
+    xs = [torch.rand(B, 3, H, W, generator=gen, device=dev).to(torch.bfloat16) for _ in range(4)]
+    gs = [torch.randn(B, 3, H, W, generator=gen, device=dev).to(torch.bfloat16) for _ in range(4)]
+    feat = torch.randn(B, 15, generator=gen, device=dev) * 0.3
+    for name, fn in (("fwd", lambda i: ops.filters_forward(xs[i % 4], feat, out_dtype=torch.bfloat16)),
+                     ("bwd", lambda i: ops.filters_backward(xs[i % 4], feat, gs[i % 4]))):
+        for i in range(5):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(20):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"timing bf16 {name}: {1e3 * e0.elapsed_time(e1) / 20:.1f} us per call (eager, incl. allocation)", flush=True)
+
+
+if __name__ == "__main__" and "quick" not in sys.argv:
+    timing_bf16()
