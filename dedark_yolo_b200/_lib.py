@@ -18,7 +18,7 @@ DT_F32, DT_BF16 = 1, 2   # element types of the *_ex entry points
 EXPORTS = (
     "dd_version", "dd_last_error", "dd_launch_count", "dd_workspace_bytes", "dd_synth_fwd", "dd_resize256",
     "dd_resize256_bwd", "dd_predictor_fwd", "dd_predictor_bwd", "dd_recovery_fwd", "dd_recovery_bwd",
-    "dd_synth_resize_fwd", "dd_synth_resize_supported", "dd_predictor_bwd_allreduce", "dd_debug_blur_tc", "dd_synth_fwd_ex", "dd_resize256_ex",
+    "dd_synth_resize_fwd", "dd_synth_resize_supported", "dd_predictor_bwd_allreduce", "dd_predictor_bwd_part", "dd_debug_blur_tc", "dd_synth_fwd_ex", "dd_resize256_ex",
     "dd_recovery_fwd_ex", "dd_recovery_bwd_ex", "dd_exchange_bytes",
 )
 MAX_PEERS = 8
@@ -72,6 +72,7 @@ def _load():
     lib.dd_resize256_bwd.argtypes = [vp, vp, i, i, i, vp]
     lib.dd_predictor_fwd.argtypes = [vp, C.POINTER(PredictorTensors), vp, vp, i, vp]
     lib.dd_predictor_bwd.argtypes = [vp, C.POINTER(PredictorTensors), vp, vp, C.POINTER(PredictorTensors), vp, i, vp, sz, vp]
+    lib.dd_predictor_bwd_part.argtypes = [vp, C.POINTER(PredictorTensors), vp, vp, C.POINTER(PredictorTensors), vp, i, vp, sz, i, vp]
     lib.dd_recovery_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
     lib.dd_recovery_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, vp, sz, vp]
     lib.dd_synth_resize_fwd.argtypes = [vp, i, f, vp, vp, vp, vp, vp, vp, i, i, i, vp, sz, vp]

@@ -434,9 +434,11 @@ extern "C" int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, f
 }
 
 namespace dd {
+// part: 0 = the whole backward; 1 = the fully connected layers only (their gradients -- 80 % of the bytes -- are final after this
+// one launch, so a caller can start reducing them over the ranks while the convolutions run); 2 = the convolutions only
 static int predictor_bwd_impl(const float* r, const dd_predictor_tensors* w, const float* acts, const float* dfeat,
                               const dd_predictor_tensors* g, float* dr, int B, void* ws, size_t ws_bytes,
-                              const dd_peer_exchange* pxh, cudaStream_t st) {
+                              const dd_peer_exchange* pxh, cudaStream_t st, int part = 0) {
     PushCtx px;
     memset(&px, 0, sizeof(px));
     if (pxh && pxh->world > 1) {
@@ -456,12 +458,13 @@ static int predictor_bwd_impl(const float* r, const dd_predictor_tensors* w, con
     }
     float* partial = reinterpret_cast<float*>(ws) + predictor_acts_elems(B);
 
-    {
+    if (part != 2) {
         const int n_w = kFc1Out * kFc1In / 256, n_d = (B * kFc1In + 255) / 256;
         launch_pdl(fc_bwd_kernel, dim3(n_w + n_d + 1), dim3(256), 0, st, dfeat, a[5], (const float*)w->fc2_w, a[4], (const float*)w->fc1_w,
                    g->fc2_w, g->fc2_b, g->fc1_w, g->fc1_b, d[4], B, n_w, n_d, px);
+        count_launch();
+        if (part == 1) return check_launch("dd_predictor_bwd_part(fc)");
     }
-    count_launch();
     // conv5 .. conv2: weight-gradient slices and the data gradient of a layer in one tensor-core launch; conv1: weight
     // gradient on the CUDA cores; one deferred reduction of all slice buffers at the end
     const float* prep = acts + predictor_acts_elems(B);
@@ -518,6 +521,13 @@ extern "C" int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, c
                                 const float* dfeat, const dd_predictor_tensors* g, float* dr, int B, void* ws,
                                 size_t ws_bytes, void* stream_) {
     return dd::predictor_bwd_impl(r, w, acts, dfeat, g, dr, B, ws, ws_bytes, nullptr, (cudaStream_t)stream_);
+}
+
+extern "C" int dd_predictor_bwd_part(const float* r, const dd_predictor_tensors* w, const float* acts, const float* dfeat,
+                                     const dd_predictor_tensors* g, float* dr, int B, void* ws, size_t ws_bytes, int part,
+                                     void* stream_) {
+    DD_REQUIRE(part >= 0 && part <= 2, DD_ERR_INVALID, "dd_predictor_bwd_part: part must be 0, 1 or 2 (got %d)", part);
+    return dd::predictor_bwd_impl(r, w, acts, dfeat, g, dr, B, ws, ws_bytes, nullptr, (cudaStream_t)stream_, part);
 }
 
 extern "C" size_t dd_exchange_bytes(void) { return dd::exchange_bytes(); }

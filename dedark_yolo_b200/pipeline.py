@@ -130,6 +130,23 @@ class RecoveryPipeline:
         check(lib.dd_recovery_bwd_ex(_p(self.dark), self._dt, _p(A), _p(IcA), _p(self.feat), _p(g), self._dt, _p(self.dfeat), None, B, H, W,
                                      _p(self._ws_rb), self._ws_rb.numel(), st))
 
+    # flat gradient layout (state-dict order): [conv w/b x5 | fc1.w fc1.b fc2.w fc2.b]; the fc tail is final after part 1
+    FC_OFFSET = 448 + 4640 + 3 * 9248
+
+    def backward_predictor_part(self, st, part: int):
+        """``dd_predictor_bwd_part``: 1 = fully connected layers (their gradients, flat_grad[FC_OFFSET:], are final afterwards),
+        2 = the convolutions."""
+        check(lib.dd_predictor_bwd_part(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.dfeat), C.byref(self._g), None, self.B,
+                                        _p(self._ws_pb), self._ws_pb.numel(), int(part), st))
+
+    def allreduce_fc_async(self):
+        """Start the sum over ranks of the fc gradients (80 % of the bytes) on the collective's own stream, ordered after
+        everything enqueued on the current stream so far; returns the work handle (``wait()`` it before reading)."""
+        return torch.distributed.all_reduce(self.flat_grad[self.FC_OFFSET:], group=self.pg, async_op=True)
+
+    def allreduce_conv_async(self):
+        return torch.distributed.all_reduce(self.flat_grad[:self.FC_OFFSET], group=self.pg, async_op=True)
+
     def backward_predictor(self, st):
         B = self.B
         if self.exchange is not None:
@@ -193,11 +210,21 @@ class RecoveryPipeline:
                 self.synth(src_next, sst, slot=cur ^ 1)
                 self.resize(sst, slot=cur ^ 1)
                 self._ev_join.record(self._side)
-            self.backward_predictor(st)
+            bucketed = self.allreduce and self.exchange is None
+            if bucketed:
+                # two buckets: the fc gradients are reduced over the ranks while the convolution backward (and the synthesis
+                # of the next batch) still run; only the small conv bucket (131 KB) is exposed at the end of the step
+                self.backward_predictor_part(st, 1)
+                w1 = self.allreduce_fc_async()
+                self.backward_predictor_part(st, 2)
+            else:
+                self.backward_predictor(st)
             if src_next is not None:
                 main.wait_event(self._ev_join)
-            if self.allreduce and self.exchange is None:
-                torch.distributed.all_reduce(self.flat_grad, group=self.pg)
+            if bucketed:
+                w2 = self.allreduce_conv_async()
+                w1.wait()
+                w2.wait()
             self._cur = cur ^ 1
         return self.y, rec, self.flat_grad
 
@@ -207,6 +234,8 @@ class RecoveryPipeline:
         ``epilogue(y, rec, flat_grad)``: optional work captured behind the step in the same graph (reading the step's results
         back to pinned host memory, say) -- only meaningful when no collective has to run between the two."""
         self.enable_overlap()
+        if self.allreduce and self.exchange is None:
+            return self._capture_overlapped_bucketed(key, src_next, g, slot)
         ar, self.allreduce = self.allreduce, False
         try:
             self._cur = slot
@@ -225,13 +254,56 @@ class RecoveryPipeline:
             self.allreduce = ar
         return graph
 
+    def _step_halves(self, src_next, g, half: int):
+        """The overlapped step in two halves around the point where the fc gradients are final: half 0 = forward, filter
+        backward, fc backward; half 1 = convolution backward with the synthesis of the next batch beside it."""
+        main = torch.cuda.current_stream(self.dev)
+        st = main.cuda_stream
+        if half == 0:
+            self.forward(st, resize=False)
+            self.backward_filters(g, st)
+            self.backward_predictor_part(st, 1)
+            return
+        self._ev_fork.record(main)
+        self._side.wait_event(self._ev_fork)
+        sst = self._side.cuda_stream
+        self.synth(src_next, sst, slot=self._cur ^ 1)
+        self.resize(sst, slot=self._cur ^ 1)
+        self._ev_join.record(self._side)
+        self.backward_predictor_part(st, 2)
+        main.wait_event(self._ev_join)
+
+    def _capture_overlapped_bucketed(self, key, src_next, g, slot):
+        """Data-parallel variant of ``capture_overlapped``: two graphs per step with the NCCL all-reduce of the fc bucket issued
+        between them (collectives stay outside the graphs: capturing them hung at teardown)."""
+        with torch.cuda.device(self.dev):
+            graphs = []
+            for half in (0, 1):
+                self._cur = slot
+                self._step_halves(src_next, g, half)  # warm-up outside capture
+                torch.cuda.synchronize(self.dev)
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    self._step_halves(src_next, g, half)
+                graphs.append(gr)
+            self.graphs[key] = (tuple(graphs), slot)
+        return graphs
+
     def replay_overlapped(self, key):
         graph, slot = self.graphs[key]
         assert slot == self._cur, "overlapped graphs must be replayed in the order they alternate buffer sets"
         rec = self._slots[slot].rec
-        graph.replay()
-        if self.allreduce and self.exchange is None:
-            torch.distributed.all_reduce(self.flat_grad, group=self.pg)
+        if isinstance(graph, tuple):  # bucketed data-parallel step: fc bucket reduced beside the second half
+            graph[0].replay()
+            w1 = self.allreduce_fc_async()
+            graph[1].replay()
+            w2 = self.allreduce_conv_async()
+            w1.wait()
+            w2.wait()
+        else:
+            graph.replay()
+            if self.allreduce and self.exchange is None:
+                torch.distributed.all_reduce(self.flat_grad, group=self.pg)
         self._cur = slot ^ 1
         return self.y, rec, self.flat_grad
 

@@ -115,6 +115,14 @@ int dd_predictor_bwd(const float* r, const dd_predictor_tensors* w, const float*
                      const float* dfeat, const dd_predictor_tensors* grads, float* dr, int B,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* The same backward in two calls, for callers that overlap the reduction of the gradients over the ranks with the rest of
+ * the backward (DDP does the same with its buckets, engine/trainer.py:223): part 1 = the fully connected layers (one launch;
+ * fc1 / fc2 gradients -- 132 111 of the 164 943 floats, the tail of the flat state-dict order -- are final afterwards),
+ * part 2 = the five convolutions, part 0 = everything (== dd_predictor_bwd). */
+int dd_predictor_bwd_part(const float* r, const dd_predictor_tensors* w, const float* acts,
+                          const float* dfeat, const dd_predictor_tensors* grads, float* dr, int B, void* ws,
+                          size_t ws_bytes, int part, void* stream);
+
 /* ---- 8(e): predictor backward fused with the exchange of its gradients over peer memory ----------------------
  * One process per GPU on one NVLink/NVSwitch node.  Every rank owns an exchange buffer of dd_exchange_bytes() bytes
  * (zero-filled once by the caller, then owned by the library) that is mapped into every peer (CUDA IPC / symmetric

@@ -86,20 +86,33 @@ def test_module_bf16_input_and_bf16_output(dd):
 
 
 def test_pipeline_bf16_step_full_size(dd):
-    """RecoveryPipeline(io_dtype=bf16) at BASELINE configs[1] size: bf16 dark / y / g, against the fp32 pipeline on the same input."""
+    """RecoveryPipeline(io_dtype=bf16) at BASELINE configs[1] size: bf16 dark / y / g.  Reference: the fp32 kernels fed the SAME
+    bf16-rounded darkened batch and cotangent (what the reference module computes when it is handed bf16 tensors)."""
+    from dedark_yolo_b200 import ops
     torch.manual_seed(0)
     m = dd.lowlight_recovery(3).cuda().train()
+    params = [p.detach() for p in m.extractor.ordered_parameters()]
     B, H, W = 16, 640, 640
     gen = torch.Generator(device="cuda").manual_seed(5)
     clean = torch.rand(B, 3, H, W, generator=gen, device="cuda")
-    g = torch.randn(B, 3, H, W, generator=gen, device="cuda")
-    p32 = dd.RecoveryPipeline(m, B, H, W, dark_param=5.0)
-    y32, rec32, flat32 = (t.clone() for t in p32.step(clean, g))
+    g16 = torch.randn(B, 3, H, W, generator=gen, device="cuda").to(torch.bfloat16)
     p16 = dd.RecoveryPipeline(m, B, H, W, dark_param=5.0, io_dtype=torch.bfloat16)
-    y16, rec16, flat16 = p16.step(clean, g.to(torch.bfloat16))
+    y16, rec16, flat16 = p16.step(clean, g16)
     torch.cuda.synchronize()
     assert y16.dtype == torch.bfloat16 and p16.dark.dtype == torch.bfloat16
-    assert torch.equal(rec16, rec32)                        # the loss is reduced from the exact fp32 values in both modes
+    # the darkened batch is the exact fp32 value rounded to bf16; the loss is reduced from the fp32 values
+    dark32 = torch.pow(clean, 5.0)
+    assert torch.equal(p16.dark, dark32.to(torch.bfloat16))
+    rec_ref = torch.nn.functional.mse_loss(dark32.double(), clean.double())
+    assert abs(float(rec16) - float(rec_ref)) <= 1e-6 * float(rec_ref)
+    # fp32 kernels on the same rounded operands
+    x32, g32 = p16.dark.float(), g16.float()
+    r = ops.resize256(x32)
+    feat, acts = ops.predictor_forward(r, params)
+    y32 = ops.filters_forward(x32, feat)
+    dfeat, _ = ops.filters_backward(x32, feat, g32)
+    grads, _ = ops.predictor_backward(r, params, acts, dfeat)
+    flat32 = torch.cat([t.reshape(-1) for t in grads])
     e_y, e_g = rel_to_max(y16.float().cpu(), y32.cpu()), rel_to_max(flat16.cpu(), flat32.cpu())
-    print(f"[bf16] pipeline 16x3x640x640: y {e_y:.2e}, flat gradient {e_g:.2e} vs the fp32 pipeline")
+    print(f"[bf16] pipeline 16x3x640x640: y {e_y:.2e}, flat gradient {e_g:.2e} vs the fp32 kernels on the same bf16-rounded operands")
     assert e_y <= BF16_TOL and e_g <= BF16_TOL
