@@ -17,6 +17,7 @@ out in state-dict order -- the buffer the single all-reduce runs on (SURVEY.md s
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -28,6 +29,27 @@ from .llie import lowlight_recovery, ordered_parameters
 
 def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+# NVTX ranges around the five stages of a step (SURVEY.md section 5 "tracing"): DEDARK_NVTX=1; off by default (a range costs
+# ~1 us of host time, the eager step has ~25 of them)
+_NVTX = os.environ.get("DEDARK_NVTX", "0") == "1"
+
+
+class _Range:
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 class RecoveryPipeline:
@@ -103,6 +125,10 @@ class RecoveryPipeline:
 
     # -- individual stages (each is one C-ABI call) -------------------------------------------------------
     def synth(self, src, st, slot=None):
+        with _Range("dedark/synthesis+recovery_loss"):
+            self._synth(src, st, slot)
+
+    def _synth(self, src, st, slot=None):
         s = self._slots[self._cur if slot is None else slot]
         is_u8 = src.dtype == torch.uint8
         if self.fused_resize:  # also produces r: forward() then skips dd_resize256
@@ -121,11 +147,22 @@ class RecoveryPipeline:
     def forward(self, st, A=None, IcA=None, resize=True):
         B, H, W = self.B, self.H, self.W
         if resize:
-            self.resize(st)
-        check(lib.dd_predictor_fwd(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.feat), B, st))
+            with _Range("dedark/resize256"):
+                self.resize(st)
+        with _Range("dedark/predictor_fwd"):
+            check(lib.dd_predictor_fwd(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.feat), B, st))
+        with _Range("dedark/filters_fwd"):
+            self._filters_fwd(st, A, IcA)
+
+    def _filters_fwd(self, st, A, IcA):
+        B, H, W = self.B, self.H, self.W
         check(lib.dd_recovery_fwd_ex(_p(self.dark), self._dt, _p(A), _p(IcA), _p(self.feat), _p(self.y), self._dt, B, H, W, st))
 
     def backward_filters(self, g, st, A=None, IcA=None):
+        with _Range("dedark/filters_bwd"):
+            self._filters_bwd(g, st, A, IcA)
+
+    def _filters_bwd(self, g, st, A=None, IcA=None):
         B, H, W = self.B, self.H, self.W
         check(lib.dd_recovery_bwd_ex(_p(self.dark), self._dt, _p(A), _p(IcA), _p(self.feat), _p(g), self._dt, _p(self.dfeat), None, B, H, W,
                                      _p(self._ws_rb), self._ws_rb.numel(), st))
@@ -148,6 +185,10 @@ class RecoveryPipeline:
         return torch.distributed.all_reduce(self.flat_grad[:self.FC_OFFSET], group=self.pg, async_op=True)
 
     def backward_predictor(self, st):
+        with _Range("dedark/predictor_bwd"):
+            self._predictor_bwd(st)
+
+    def _predictor_bwd(self, st):
         B = self.B
         if self.exchange is not None:
             check(lib.dd_predictor_bwd_allreduce(_p(self.r), C.byref(self._w), _p(self.acts), _p(self.dfeat), C.byref(self._g), B,
