@@ -275,25 +275,34 @@ __device__ __forceinline__ void teardown(uint32_t tmem) {
 }
 
 // ---- between the passes (X3 only): split the R new ring columns into hi (in place) and lo ---------------------------------------
+// hi = x rounded to TF32 (two integer ops), lo = x - hi exactly (at most 13 significant bits; the tensor core ignores the bits
+// of an operand below TF32 precision, an error of 2^-11 |lo| <= 2^-23 |x| -- no second rounding).  Groups of four columns never
+// straddle the end of the ring (start and RING are multiples of 4).
 template <class L>
 __device__ __forceinline__ void split_ring(uint32_t tmem, int b, int warp) {
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int start = (L::R * b) % L::RING + (warp >> 2) * L::RPW;
+    int col = (L::R * b) % L::RING + (warp >> 2) * L::RPW;
+    col = col >= L::RING ? col - L::RING : col;
+    uint32_t c[L::RPW / 4];
     float v[L::RPW];
 #pragma unroll
-    for (int i = 0; i < L::RPW; i += 4) tmem_ld4_nowait(lane_base + L::RING_HI + (uint32_t)((start + i) % L::RING), v + i);
+    for (int i = 0; i < L::RPW / 4; ++i) {
+        c[i] = (uint32_t)col;
+        tmem_ld4_nowait(lane_base + L::RING_HI + c[i], v + 4 * i);
+        col += 4;
+        col = col >= L::RING ? col - L::RING : col;
+    }
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < L::RPW; i += 4) {
+    for (int i = 0; i < L::RPW / 4; ++i) {
         float hi[4], lo[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            hi[k] = tf32_rna(v[i + k]);
-            lo[k] = tf32_rna(v[i + k] - hi[k]);
+            hi[k] = tf32_rna(v[4 * i + k]);
+            lo[k] = v[4 * i + k] - hi[k];
         }
-        const uint32_t col = (uint32_t)((start + i) % L::RING);
-        tc::tmem_st4(lane_base + L::RING_HI + col, hi);
-        tc::tmem_st4(lane_base + L::RING_LO + col, lo);
+        tc::tmem_st4(lane_base + L::RING_HI + c[i], hi);
+        tc::tmem_st4(lane_base + L::RING_LO + c[i], lo);
     }
     tc::tmem_st_wait();
 }
@@ -311,7 +320,7 @@ __device__ __forceinline__ void tile_store4(unsigned char* p, const float* o) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = tf32_rna(o[i]);
         *reinterpret_cast<float4*>(p) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(p + L::T_BYTES) = make_float4(tf32_rna(o[0] - h[0]), tf32_rna(o[1] - h[1]), tf32_rna(o[2] - h[2]), tf32_rna(o[3] - h[3]));
+        *reinterpret_cast<float4*>(p + L::T_BYTES) = make_float4(o[0] - h[0], o[1] - h[1], o[2] - h[2], o[3] - h[3]);  // exact; see split_ring
     } else {
         *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
     }

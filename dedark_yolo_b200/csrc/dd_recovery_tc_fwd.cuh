@@ -63,12 +63,19 @@ recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, co
         bool entered;
 
         // ---- stage side -------------------------------------------------------------------------------------------------------
+        // Lean by construction: a thread's four items of a block are the same chunk of rows rg, rg+12, rg+24, rg+36, so one 64-bit
+        // address per block and a constant row step reach all four loads; a block whose R staged rows all lie inside the image and
+        // inside the segment (all but the first and last block of an image column) takes a path without any per-row index logic.
         SG sg;
         ChainK ck;
         const TX* xp = x;
         const float* ip = IcA;
         int rowbase = 0, nU = 0;
-        float4 in[4], ic[4];  // the block in flight between stage_load and stage_store
+        const size_t wstep = (size_t)SG::NG * (size_t)W;   // elements between two items of a thread
+        float4 in[4], ic[4];      // the block in flight between stage_load and stage_store
+        int s_vb = 0;             // its first staged row
+        bool s_inner = false;     // ... and whether it takes the lean path (CTA-uniform)
+        uint32_t sbuf = 0, sside = 0;   // tile buffer / side slot the next stage_store fills (block counter mod 3, mod 4)
         auto stage_enter = [&]() {  // first block of a new segment: regressors of its image, per-row contrast scalars, geometry
             const Seg& u = itS.u;
             compute_sync();  // every warp has finished staging the previous segment (MS, sp are about to be rewritten)
@@ -95,43 +102,59 @@ recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, co
             compute_sync();
         };
         auto stage_load = [&]() {  // the four global loads of this thread's items of block itS.b
-            if (sg.kind == SG::KIND_INSIDE || sg.kind == SG::KIND_MIRRORED) {
-                const int v0 = R * itS.b + sg.rg;
+            s_vb = R * itS.b;
+            const int row0 = rowbase + s_vb;
+            s_inner = row0 >= 0 && row0 + R <= H && s_vb + R <= nU;
+            if (sg.kind == SG::KIND_INSIDE && s_inner) {   // one 64-bit offset per block, a constant row step between the four items
+                const size_t off = (size_t)(row0 + sg.rg) * (size_t)W + (size_t)sg.gc;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    in[k] = Elem<TX>::load4(xp + off + k * wstep);
+                    if (HAS_ICA) ic[k] = Elem<float>::load4(ip + off + k * wstep);
+                }
+                if (row0 + 2 * R <= H) {  // the rows of the next block: towards L2 while this block is processed (its loads then hit L2)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) prefetch_l2(xp + off + (size_t)R * (size_t)W + k * wstep);
+                }
+            } else if (sg.kind == SG::KIND_INSIDE || sg.kind == SG::KIND_MIRRORED) {
+                const int v0 = s_vb + sg.rg;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const unsigned off = (unsigned)reflect(rowbase + min(v0 + SG::NG * k, nU - 1), H) * (unsigned)W;
                     in[k] = sg.load4(xp, off);
                     if (HAS_ICA) ic[k] = sg.load4(ip, off);
                 }
-                if (sg.kind == SG::KIND_INSIDE && itS.b + 1 < itS.nB) {  // next block of the segment: towards L2 while this one is processed
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        prefetch_l2(xp + (unsigned)reflect(rowbase + min(v0 + R + SG::NG * k, nU - 1), H) * (unsigned)W + sg.gc);
-                }
             }
         };
-        auto stage_store = [&](uint32_t g) {  // pointwise chain, split, tile buffer g % 3 (+ side slot g % 4)
-            unsigned char* trow = tiles + (size_t)(g % kNBuf) * L::T_BUF + sg.toff;  // row rg; row rg + 12 k at + 192 k bytes
-            const int v0 = R * itS.b + sg.rg;
+        auto stage_item = [&](unsigned char* trow, int k, float m, bool zero) {   // pointwise chain of one item -> tile (+ side slot)
+            float o[4];
+            if (DBG) {
+                o[0] = in[k].x; o[1] = in[k].y; o[2] = in[k].z; o[3] = in[k].w;
+            } else {
+                const float4 q = HAS_ICA ? ic[k] : make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
+                o[0] = chain_x3<HAS_ICA, FAST>(ck, in[k].x, q.x) * m;
+                o[1] = chain_x3<HAS_ICA, FAST>(ck, in[k].y, q.y) * m;
+                o[2] = chain_x3<HAS_ICA, FAST>(ck, in[k].z, q.z) * m;
+                o[3] = chain_x3<HAS_ICA, FAST>(ck, in[k].w, q.w) * m;
+            }
+            if (zero) o[0] = o[1] = o[2] = o[3] = 0.f;  // rows past the segment (its last block only)
+            tile_store4<L>(trow + 16 * SG::NG * k, o);
+            if (k == 3 && sg.soff >= 0)  // rows R-12 .. R-1: centre values of the next block's first outputs
+                *reinterpret_cast<float4*>(side + (size_t)sside * L::SIDE_BYTES + sg.soff) = make_float4(o[0], o[1], o[2], o[3]);
+        };
+        auto stage_store = [&]() {  // pointwise chain, split, tile buffer sbuf (+ side slot sside)
+            unsigned char* trow = tiles + (size_t)sbuf * L::T_BUF + sg.toff;  // row rg; row rg + 12 k at + 192 k bytes
             if (sg.kind == SG::KIND_INSIDE || sg.kind == SG::KIND_MIRRORED) {
+                const float* ms = MS + s_vb + sg.rg;
+                if (s_inner) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int v = v0 + SG::NG * k;
-                    float o[4];
-                    if (DBG) {
-                        o[0] = in[k].x; o[1] = in[k].y; o[2] = in[k].z; o[3] = in[k].w;
-                    } else {
-                        const float m = MS[min(v, nU - 1)];
-                        const float4 q = HAS_ICA ? ic[k] : make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
-                        o[0] = chain_x3<HAS_ICA, FAST>(ck, in[k].x, q.x) * m;
-                        o[1] = chain_x3<HAS_ICA, FAST>(ck, in[k].y, q.y) * m;
-                        o[2] = chain_x3<HAS_ICA, FAST>(ck, in[k].z, q.z) * m;
-                        o[3] = chain_x3<HAS_ICA, FAST>(ck, in[k].w, q.w) * m;
+                    for (int k = 0; k < 4; ++k) stage_item(trow, k, DBG ? 1.f : ms[SG::NG * k], false);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int v = s_vb + sg.rg + SG::NG * k;
+                        stage_item(trow, k, DBG ? 1.f : MS[min(v, nU - 1)], v >= nU);
                     }
-                    if (v >= nU) o[0] = o[1] = o[2] = o[3] = 0.f;  // rows past the segment (its last block only): zeros
-                    tile_store4<L>(trow + 16 * SG::NG * k, o);
-                    if (k == 3 && sg.soff >= 0)  // rows R-12 .. R-1: centre values of the next block's first outputs
-                        *reinterpret_cast<float4*>(side + (size_t)(g % kSide) * L::SIDE_BYTES + sg.soff) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             } else if (sg.kind == SG::KIND_ZERO) {  // halo chunks beyond the reflect range
                 const float z[4] = {0.f, 0.f, 0.f, 0.f};
@@ -139,7 +162,9 @@ recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, co
                 for (int k = 0; k < 4; ++k) tile_store4<L>(trow + 16 * SG::NG * k, z);
             }
             fence_proxy_async();
-            mbar_arrive_warp(&ctl.tile_full[g % kNBuf]);
+            mbar_arrive_warp(&ctl.tile_full[sbuf]);
+            sbuf = sbuf == kNBuf - 1 ? 0 : sbuf + 1;
+            sside = (sside + 1) & (kSide - 1);
         };
 
         // ---- epilogue side ----------------------------------------------------------------------------------------------------
@@ -147,10 +172,12 @@ recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, co
         // centre values: the first 12 outputs of a block sit on the tail of the previous block (side slot, exact fp32), the others
         // on rows 12 (gq - 1) + i of the block's own tile (hi + lo); 16 bytes between consecutive rows in both
         const int ctr_off = gq == 0 ? (c >> 2) * L::S_LBO + (c & 3) * 4 : tile_off<L>(L::RPW * (gq - 1), c + kRadius);
+        const size_t ystep_b = (size_t)W * sizeof(TY);   // bytes between two output rows
         TY* ys = y;
         bool col_ok = false;
         float pp = 0.f;
         int e_r0 = 0, e_len = 0;
+        uint32_t ebuf = 0, eside = kSide - 1, epar = 0;   // tile buffer / previous side slot / p2_done parity of the block in the epilogue
         int ep_ts = -100;  // time-stamp slot of the epilogue in flight (DD_BTC_TIMING only)
         auto epilogue_enter = [&]() {
             const Seg& u = itE.u;
@@ -160,8 +187,8 @@ recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, co
             e_r0 = u.r0;
             e_len = u.seg_len;
         };
-        auto epilogue = [&](uint32_t g) {  // block itE.b of the segment: outputs o = R b - 24 + 12 gq + i, i in [0, 12)
-            mbar_wait_warp(&ctl.p2_done, g & 1u);
+        auto epilogue = [&]() {  // block itE.b of the segment: outputs o = R b - 24 + 12 gq + i, i in [0, 12)
+            mbar_wait_warp(&ctl.p2_done, epar);
             fence_after_sync();
             BTC_STAMP(ep_ts);
             float bl[L::RPW];
@@ -170,23 +197,30 @@ recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, co
             tmem_ld_wait();
             fence_before_sync();
             mbar_arrive_warp(&ctl.out_empty);  // the accumulator is in registers: pass 2 of the next block may overwrite it
+            const unsigned char* ctr = (gq == 0 ? side + (size_t)eside * L::SIDE_BYTES : tiles + (size_t)ebuf * L::T_BUF) + ctr_off;
+            epar ^= 1u;
+            ebuf = ebuf == kNBuf - 1 ? 0 : ebuf + 1;
+            eside = (eside + 1) & (kSide - 1);
             const int o0 = R * itE.b - 2 * kRadius + L::RPW * gq;           // first output row of this warp
             const int i_lo = max(0, -o0), i_hi = min(L::RPW, e_len - o0);
             if (!col_ok || i_lo >= i_hi) return;
-            const unsigned char* ctr = (gq == 0 ? side + (size_t)((g + kSide - 1) % kSide) * L::SIDE_BYTES : tiles + (size_t)(g % kNBuf) * L::T_BUF) + ctr_off;
-            const int yoff = (e_r0 + o0) * W;  // 32-bit element offset of the warp's first output row (negative rows are never touched)
+            // byte pointer advanced row by row (one 64-bit add per output; rows with i < i_lo are never dereferenced)
+            char* yp = reinterpret_cast<char*>(ys) + (ptrdiff_t)(e_r0 + o0) * (ptrdiff_t)ystep_b;
             auto one = [&](int i) {
                 float x4 = *reinterpret_cast<const float*>(ctr + 16 * i);
                 if (X3 && gq != 0) x4 += *reinterpret_cast<const float*>(ctr + 16 * i + L::T_BYTES);
-                Elem<TY>::store1_streaming(ys + (yoff + i * W), DBG ? bl[i] : fmaf(x4 - bl[i], pp, x4));
+                Elem<TY>::store1_streaming(reinterpret_cast<TY*>(yp), DBG ? bl[i] : fmaf(x4 - bl[i], pp, x4));
+                yp += ystep_b;
             };
             if (i_lo == 0 && i_hi == L::RPW) {  // the common case: every output row of the warp lies inside the segment
 #pragma unroll
                 for (int i = 0; i < L::RPW; ++i) one(i);
             } else {
 #pragma unroll
-                for (int i = 0; i < L::RPW; ++i)
+                for (int i = 0; i < L::RPW; ++i) {
                     if (i >= i_lo && i < i_hi) one(i);
+                    else yp += ystep_b;
+                }
             }
         };
 
@@ -197,7 +231,7 @@ recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, co
             if (!moreS) break;
             if (entered) stage_enter();
             stage_load();
-            stage_store(g);
+            stage_store();
         }
         uint32_t G = 0;
         while (itM.next(sc, H, entered)) {
@@ -207,7 +241,7 @@ recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, co
                 itE.next(sc, H, entered);
                 if (entered) epilogue_enter();
                 ep_ts = ts + 3;
-                epilogue(G - 1);
+                epilogue();
             }
             BTC_STAMP(ts + 4);
             compute_sync();  // every warp is done with block G-1's tile buffer and side slots before block G+2 is staged into them
@@ -226,7 +260,7 @@ recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, co
                 mbar_arrive_warp(&ctl.split_done);
             }
             BTC_STAMP(ts + 2);
-            if (moreS) stage_store(G + 2);
+            if (moreS) stage_store();
             BTC_STAMP(ts + 6);
             ++G;
         }
@@ -234,7 +268,7 @@ recovery_fwd_tc_kernel(const TX* __restrict__ x, const float* __restrict__ A, co
             itE.next(sc, H, entered);
             if (entered) epilogue_enter();
             ep_ts = -100;
-            epilogue(G - 1);
+            epilogue();
         }
     }
 
