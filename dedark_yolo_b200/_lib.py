@@ -11,7 +11,7 @@ import os
 from .build import LIB_PATH
 
 DD_OK, DD_ERR_INVALID, DD_ERR_REFLECT_PAD, DD_ERR_WIDTH_LT3, DD_ERR_WORKSPACE, DD_ERR_CUDA = range(6)
-WS_SYNTH, WS_PREDICTOR_ACTS, WS_PREDICTOR_BWD, WS_RECOVERY_BWD = range(4)
+WS_SYNTH, WS_PREDICTOR_ACTS, WS_PREDICTOR_BWD, WS_RECOVERY_BWD, WS_DARK_PRIOR = range(5)
 SRC_U8, SRC_F32 = 0, 1
 DT_F32, DT_BF16 = 1, 2   # element types of the *_ex entry points
 
@@ -19,7 +19,7 @@ EXPORTS = (
     "dd_version", "dd_last_error", "dd_launch_count", "dd_workspace_bytes", "dd_synth_fwd", "dd_resize256",
     "dd_resize256_bwd", "dd_predictor_fwd", "dd_predictor_bwd", "dd_recovery_fwd", "dd_recovery_bwd",
     "dd_synth_resize_fwd", "dd_synth_resize_supported", "dd_predictor_bwd_allreduce", "dd_predictor_bwd_part", "dd_debug_blur_tc", "dd_synth_fwd_ex", "dd_resize256_ex",
-    "dd_recovery_fwd_ex", "dd_recovery_bwd_ex", "dd_exchange_bytes",
+    "dd_recovery_fwd_ex", "dd_recovery_bwd_ex", "dd_dark_prior", "dd_exchange_bytes",
 )
 MAX_PEERS = 8
 
@@ -84,6 +84,7 @@ def _load():
     lib.dd_resize256_ex.argtypes = [vp, i, vp, i, i, i, vp]
     lib.dd_recovery_fwd_ex.argtypes = [vp, i, vp, vp, vp, vp, i, i, i, i, vp]
     lib.dd_recovery_bwd_ex.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, i, i, i, vp, sz, vp]
+    lib.dd_dark_prior.argtypes = [vp, f, vp, vp, vp, i, i, i, vp, sz, vp]
     lib.dd_exchange_bytes.restype = sz
     lib.dd_exchange_bytes.argtypes = []
     for name in EXPORTS[4:-1]:

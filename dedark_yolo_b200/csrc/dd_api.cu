@@ -48,6 +48,7 @@ size_t dd_workspace_bytes(int kind, int B, int H, int W) {
         case DD_WS_PREDICTOR_ACTS: return dd::predictor_acts_bytes(B);
         case DD_WS_PREDICTOR_BWD: return dd::predictor_bwd_ws_bytes(B);
         case DD_WS_RECOVERY_BWD: return (H > 0 && W > 0) ? dd::recovery_bwd_ws_bytes(B, H, W) : 0;
+        case DD_WS_DARK_PRIOR: return dd::prior_ws_bytes(B);
         default: return 0;
     }
 }

@@ -20,6 +20,12 @@ inline size_t synth_resize_smem_bytes(int H, int W, int rpb) {
     return (size_t)rows * W * sizeof(float);
 }
 
+// ---- dark-channel prior (train.py:42-68,81-97) -------------------------------------------------
+// workspace: partial histograms [B][kPriorChunks][4][256] uint32 ({count, sum R, sum G, sum B} per dark-channel value and CTA),
+// then the atmospheric light in uint8 units [B][4] float
+constexpr int kPriorChunks = 32;   // CTAs per image in the histogram pass
+inline size_t prior_ws_bytes(int B) { return (size_t)(B > 0 ? B : 0) * ((size_t)kPriorChunks * 4 * 256 * sizeof(unsigned) + 4 * sizeof(float)); }
+
 // ---- predictor (common.py:52-78): channels 3->16->32->32->32->32, spatial 256->128->64->32->16->8 --
 constexpr int kPredLayers = 5;
 __host__ __device__ constexpr int pred_cin(int l) { return l == 0 ? 3 : l == 1 ? 16 : 32; }

@@ -17,7 +17,7 @@ from . import ops
 
 def preprocess_batch(batch: dict, device, dark_param: float = 15.0, lowlight_FLAG: bool = True,
                      dedark_FLAG: bool = True, lut: Optional[torch.Tensor] = None,
-                     clean_lut: Optional[torch.Tensor] = None) -> dict:
+                     clean_lut: Optional[torch.Tensor] = None, dedark_prior: bool = False) -> dict:
     """Same keys and semantics as the reference trainer hook (defaults = cfg/default.yaml:32-34: ``dark_param: 15.0``,
     ``lowlight_FLAG: True``, ``dedark_FLAG: True``):
 
@@ -28,6 +28,10 @@ def preprocess_batch(batch: dict, device, dark_param: float = 15.0, lowlight_FLA
     (train.py:81-97) produces ``dedark_A``/``IcA`` from uninitialised memory (train.py:65-67) that no training-mode
     consumer reads (tasks.py:107-110): the keys are emitted as None, which ``_predict_once``
     (tasks.py:87-91) and the module treat as "use the defaults A = 0.8, IcA = 0.5".
+
+    ``dedark_prior=True`` (opt-in, a behaviour change -- SURVEY.md section 8(f) N3) fills those two keys with the dark-channel
+    prior computed on the GPU (``ops.dark_prior``: channel minimum, atmospheric light from the brightest 0.1 % of the dark
+    channel, per-channel divide), i.e. what train.py:42-68,81-97 set out to compute.
 
     ``batch['img']`` must be uint8 (what the dataloader's collate hands over, data/dataset.py:172-188): the reference
     divides whatever it gets by 255 (train.py:72), so a float image in [0, 1] would silently be darkened from
@@ -47,8 +51,11 @@ def preprocess_batch(batch: dict, device, dark_param: float = 15.0, lowlight_FLA
     if dedark_FLAG:
         batch["clean_img"] = dark
         batch["img"] = dark
-        batch["dedark_A"] = None
-        batch["IcA"] = None
+        if dedark_prior:
+            batch["dedark_A"], batch["IcA"] = ops.dark_prior(src, dark_param, lut=lut)
+        else:
+            batch["dedark_A"] = None
+            batch["IcA"] = None
         batch["recovery_loss_batch"] = torch.zeros((), dtype=torch.float32, device=src.device)
     else:
         batch["clean_img"] = clean

@@ -136,6 +136,26 @@ def reference_cpu_tables(p: float, device):
     return torch.pow(clean, float(p)).to(device), clean.to(device)
 
 
+# ---- SURVEY.md section 8(f) N3 ------------------------------------------------------------------------
+def dark_prior(src_u8: torch.Tensor, p: float, lut: Optional[torch.Tensor] = None):
+    """The dark-channel prior of the darkened batch on the GPU (train.py:42-68,81-97 as intended; ``dd_dark_prior``):
+    ``src_u8`` uint8 ``[B,3,H,W]`` -> ``(dedark_A [B,3] in the image's [0,1] units, IcA [B,1,H,W])``, both fp32."""
+    _need_cuda(src_u8, lut)
+    if src_u8.dtype != torch.uint8 or src_u8.dim() != 4 or src_u8.shape[1] != 3:
+        raise TypeError(f"dark_prior: uint8 [B,3,H,W] expected, got {src_u8.dtype} {tuple(src_u8.shape)}")
+    src_u8 = src_u8.contiguous()
+    B, _, H, W = src_u8.shape
+    dev = src_u8.device
+    with torch.cuda.device(dev):
+        A = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        ica = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+        ws_bytes = _lib.workspace_bytes(_lib.WS_DARK_PRIOR, B)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        lut = None if lut is None else _f32c(lut)
+        check(lib.dd_dark_prior(_ptr(src_u8), float(p), _ptr(lut), _ptr(A), _ptr(ica), B, H, W, _ptr(ws), ws_bytes, _stream(dev)))
+    return A, ica
+
+
 # ---- a4 / a5 ---------------------------------------------------------------------------------------
 def resize256(x: torch.Tensor) -> torch.Tensor:
     """[B,3,H,W] fp32 or bf16 -> [B,3,256,256] fp32 (llie.py:43)."""

@@ -43,6 +43,7 @@ extern "C" {
 #define DD_WS_PREDICTOR_ACTS 1 /* activations + prepared tensor-core weights kept from dd_predictor_fwd for dd_predictor_bwd */
 #define DD_WS_PREDICTOR_BWD 2  /* scratch of dd_predictor_bwd                                      */
 #define DD_WS_RECOVERY_BWD 3   /* partial sums of dd_recovery_bwd                                  */
+#define DD_WS_DARK_PRIOR 4     /* histograms of dd_dark_prior (depends on B)                       */
 
 /* element types of the *_ex entry points (bf16 I/O mode) */
 #define DD_F32 1
@@ -86,6 +87,22 @@ int dd_synth_resize_supported(int H, int W);
 int dd_synth_resize_fwd(const void* src, int src_dtype, float p, const float* lut256, const float* clean_lut256,
                         float* clean_out, float* dark_out, float* r_out, float* rec_out, int B, int H, int W, void* ws,
                         size_t ws_bytes, void* stream);
+
+/* ---- the dark-channel prior on the GPU ------------------------------------------
+ * Replaces the per-batch D2H + numpy loop of DetectionTrainer.preprocess_batch (models/yolo/detect/train.py:81-97:
+ * DarkChannel :42-45, AtmLight :47-61, DarkIcA :63-67) that produces batch['dedark_A'] / batch['IcA'].  Works on the
+ * uint8 source batch directly: the darkened image is quantised exactly as train.py:84 does
+ * (`(pow(u8/255, p) * 255).astype(uint8)`, a 256-entry table), then
+ *   dc[h,w]  = min_c dark_u8[c,h,w]                                            (DarkChannel)
+ *   A_u8[c]  = (sum of dark_u8[c] over the numpx - 1 pixels of largest dc) / numpx,  numpx = max(HW / 1000, 1)
+ *              (AtmLight, including its `range(1, numpx)` off-by-one; pixels tied at the selection threshold contribute
+ *              in equal shares -- numpy's argsort picks an arbitrary subset of them)
+ *   IcA[h,w] = min_c dark_u8[c,h,w] / max(A_u8[c], 1)                          (DarkIcA as intended: the reference
+ *              indexes rows instead of channels of an uninitialised uint8 array, so its own IcA is not reproducible)
+ * Outputs: A_out [B,3] = A_u8 / 255 (the image's [0,1] units, what DeDarkFilter expects), IcA_out [B,1,H,W] fp32.
+ * lut256: optional darkening table as for dd_synth_fwd.  ws: DD_WS_DARK_PRIOR bytes.  Integer histograms: bit-reproducible. */
+int dd_dark_prior(const uint8_t* src, float p, const float* lut256, float* A_out, float* IcA_out, int B, int H, int W, void* ws,
+                  size_t ws_bytes, void* stream);
 
 /* ---- a4: bilinear resize to 256x256 (llie.py:43; align_corners=False, no antialias) ----------- */
 int dd_resize256(const float* x, float* r, int B, int H, int W, void* stream);
