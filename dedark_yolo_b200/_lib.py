@@ -19,7 +19,7 @@ EXPORTS = (
     "dd_version", "dd_last_error", "dd_launch_count", "dd_workspace_bytes", "dd_synth_fwd", "dd_resize256",
     "dd_resize256_bwd", "dd_predictor_fwd", "dd_predictor_bwd", "dd_recovery_fwd", "dd_recovery_bwd",
     "dd_synth_resize_fwd", "dd_synth_resize_supported", "dd_predictor_bwd_allreduce", "dd_predictor_bwd_part", "dd_debug_blur_tc", "dd_synth_fwd_ex", "dd_resize256_ex",
-    "dd_recovery_fwd_ex", "dd_recovery_bwd_ex", "dd_dark_prior", "dd_exchange_bytes",
+    "dd_recovery_fwd_ex", "dd_recovery_bwd_ex", "dd_dark_prior", "dd_dark_table", "dd_recovery_fwd_u8", "dd_recovery_bwd_u8", "dd_exchange_bytes",
 )
 MAX_PEERS = 8
 
@@ -85,6 +85,9 @@ def _load():
     lib.dd_recovery_fwd_ex.argtypes = [vp, i, vp, vp, vp, vp, i, i, i, i, vp]
     lib.dd_recovery_bwd_ex.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, i, i, i, vp, sz, vp]
     lib.dd_dark_prior.argtypes = [vp, f, vp, vp, vp, i, i, i, vp, sz, vp]
+    lib.dd_dark_table.argtypes = [f, vp, vp, vp]
+    lib.dd_recovery_fwd_u8.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.dd_recovery_bwd_u8.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, vp, sz, vp]
     lib.dd_exchange_bytes.restype = sz
     lib.dd_exchange_bytes.argtypes = []
     for name in EXPORTS[4:-1]:

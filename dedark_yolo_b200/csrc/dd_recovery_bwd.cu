@@ -127,12 +127,23 @@ namespace dd {
 // TMA: the g halo tile of every row-block arrives as two 16-row x 156-column boxes (cp.async.bulk.tensor through a tensor
 // map of the [planes][H][W] cotangent; everything outside the image is zero-filled by the copy engine), issued by one
 // thread and counted on an mbarrier: no per-thread address arithmetic, no staging instructions at all.
-template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA>
+// U8: x is the uint8 source batch, read through the 256-entry darkening table `dark_tab` (one 32-bit load
+// per four pixels; needs ALIGNED); no dx (x is data).
+template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA, bool U8 = false>
 __global__ void __launch_bounds__(kThreads, 2)
 recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __restrict__ x, const float* __restrict__ A,
                     const float* __restrict__ IcA, const float* __restrict__ feat, const float* __restrict__ g,
-                    float* __restrict__ part, float* __restrict__ Spart, float* __restrict__ dx, int B, int H, int W) {
+                    float* __restrict__ part, float* __restrict__ Spart, float* __restrict__ dx, int B, int H, int W,
+                    const float* __restrict__ dark_tab = nullptr) {
+    static_assert(!U8 || ALIGNED, "uint8 sources need 4-byte aligned rows");
     pdl_begin();
+    __shared__ float s_tab[U8 ? 256 : 1];
+    if (U8) {
+        if (threadIdx.x < 256) s_tab[threadIdx.x] = __ldg(dark_tab + threadIdx.x);
+        __syncthreads();
+    }
+    const unsigned char* x8 = reinterpret_cast<const unsigned char*>(x);
+    auto lut4 = [&](unsigned w) { return make_float4(s_tab[w & 255u], s_tab[(w >> 8) & 255u], s_tab[(w >> 16) & 255u], s_tab[w >> 24]); };
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t tma_bar;
     uint32_t tma_phase = 0;
@@ -186,6 +197,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
         const float pc = sp.c, pp = sp.p;
         const float* xp = x + (size_t)u.plane * H * W;
+        const unsigned char* xp8 = x8 + (size_t)u.plane * H * W;
         const float* gp = g + (size_t)u.plane * H * W;
         const float* ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
 
@@ -241,7 +253,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                 if (v < u.nU && row >= 0 && row < H) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        x0r[k][c] = __ldg(xp + (size_t)row * W + c);
+                        x0r[k][c] = U8 ? s_tab[__ldg(xp8 + (size_t)row * W + c)] : __ldg(xp + (size_t)row * W + c);
                         icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
                     }
                 }
@@ -296,7 +308,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                         const float4 g5 = *reinterpret_cast<const float4*>(XS + (o % kXRingB) * kXP + 4 * c4 + kRadius);
                         const float4 bt = *reinterpret_cast<const float4*>(BT + rr * kBP + 4 * c4);
                         const float m = MSm[o], q1 = MSq[o];
-                        const float4 x0 = x0p[k];
+                        const float4 x0 = U8 ? lut4(__float_as_uint(x0p[k].x)) : x0p[k];
                         const size_t off = (size_t)jr * W + gc;
                         float4 ic = make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
                         if (HAS_ICA) {
@@ -373,7 +385,9 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                     x0p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (o >= kRadius && o < kRadius + u.seg_len && gc < W) {
                         const float* rp = xp + (size_t)(u.r0 + o - kRadius) * W + gc;
-                        if (ALIGNED) {
+                        if (U8) {
+                            x0p[k].x = __uint_as_float(__ldg(reinterpret_cast<const unsigned*>(xp8 + (size_t)(u.r0 + o - kRadius) * W + gc)));
+                        } else if (ALIGNED) {
                             x0p[k] = __ldg(reinterpret_cast<const float4*>(rp));
                         } else {
                             x0p[k].x = __ldg(rp);
@@ -408,6 +422,16 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
     if (cur_ps >= 0) flush();
 }
 
+// x0 of the column 0..2 fix-up: fp32 / bf16 images are read directly, a uint8 source through the darkening table
+template <typename TX>
+__device__ __forceinline__ float load_x0(const TX* x, size_t i, const float*) { return btc::Elem<TX>::load1(x + i); }
+template <>
+__device__ __forceinline__ float load_x0<unsigned char>(const unsigned char* x, size_t i, const float* tab) { return __ldg(tab + __ldg(x + i)); }
+template <typename TX>
+__device__ __forceinline__ void add_dx(TX* dx, size_t i, float v) { btc::Elem<TX>::store1(dx + i, btc::Elem<TX>::load1(dx + i) + v); }
+template <>
+__device__ __forceinline__ void add_dx<unsigned char>(unsigned char*, size_t, float) {}   // a uint8 source has no gradient
+
 // One CLUSTER of 4 CTAs per image (the kernel is a chain of latencies on ~2000 rows, one CTA per image left 132 SMs idle):
 // fixed-order sum of the (CTA, plane-strip) partials, the row-coupled fix-up of columns 0..2 (d lum / d x3[:, :, :, 0..2]),
 // each CTA on a quarter of the rows; the four partial results meet through distributed shared memory in rank order and
@@ -417,7 +441,8 @@ __global__ void __launch_bounds__(kFinThreads)
 recovery_bwd_finalize_kernel(const TX* __restrict__ x, const float* __restrict__ A,
                              const float* __restrict__ IcA, const float* __restrict__ feat,
                              const float* __restrict__ part, const float* __restrict__ Spart,
-                             float* __restrict__ dfeat, TX* __restrict__ dx, int B, int H, int W, int ctas, int nsp) {
+                             float* __restrict__ dfeat, TX* __restrict__ dx, int B, int H, int W, int ctas, int nsp,
+                             const float* __restrict__ dark_tab = nullptr) {
     pdl_begin();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -444,7 +469,7 @@ recovery_bwd_finalize_kernel(const TX* __restrict__ x, const float* __restrict__
                 const size_t off = ((size_t)plane * H + row) * W;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    x0[e][k] = btc::Elem<TX>::load1(x + off + k);
+                    x0[e][k] = load_x0(x, off + k, dark_tab);
                     ica[e][k] = HAS_ICA ? __ldg(IcA + ((size_t)b * H + row) * W + k) : kDefaultIcA;
                 }
             }
@@ -481,7 +506,7 @@ recovery_bwd_finalize_kernel(const TX* __restrict__ x, const float* __restrict__
                     ds[ch] += (double)(e2 * x1[k]);
                     const float e1 = e2 * ck.s;
                     if (tx[k] >= kTxMin) dw += (double)(e1 * (x0[e][k] - a) * ica[e][k] / (txc[k] * txc[k]));
-                    if (dx) btc::Elem<TX>::store1(dx + off + k, btc::Elem<TX>::load1(dx + off + k) + e1 / txc[k]);
+                    if (dx) add_dx(dx, off + k, e1 / txc[k]);
                 }
             }
         }
@@ -563,8 +588,35 @@ static int launch_bwd4(const CUtensorMap& gmap, const float* x, const float* A, 
                        float* part, float* Spart, float* dx, int B, int H, int W, const Sched& sc, cudaStream_t st) {
     DD_ENSURE_SMEM((recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>), kBwdSmem, "recovery kernel");
     launch_pdl(recovery_bwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>, dim3(sc.G), dim3(kThreads), kBwdSmem, st, gmap, x, A, IcA, feat, g, part,
-               Spart, dx, B, H, W);
+               Spart, dx, B, H, W, (const float*)nullptr);
     return DD_OK;
+}
+
+// x is the uint8 batch, read through the darkening table
+template <bool HAS_ICA, bool FAST>
+static int launch_bwd_u8(const uint8_t* src, const float* tab, const float* A, const float* IcA, const float* feat, const float* g, float* dfeat,
+                         int B, int H, int W, float* ws, cudaStream_t st) {
+    const Sched sc = make_sched(B, H, W);
+    float* part = ws;
+    float* Spart = part + (size_t)(sc.G + sc.nPS) * kBwdSums;
+    CUtensorMap gmap;
+    memset(&gmap, 0, sizeof(gmap));
+    const bool tma = W >= kXP && H >= 16 && make_tensor_map_3d(&gmap, g, B * 3, H, W, kXP, 16);
+    const float* xf = reinterpret_cast<const float*>(src);
+    if (tma) {
+        auto kern = recovery_bwd_kernel<HAS_ICA, FAST, true, true, true>;
+        DD_ENSURE_SMEM(kern, kBwdSmem, "recovery kernel (uint8 source)");
+        launch_pdl(kern, dim3(sc.G), dim3(kThreads), kBwdSmem, st, gmap, xf, A, IcA, feat, g, part, Spart, (float*)nullptr, B, H, W, tab);
+    } else {
+        auto kern = recovery_bwd_kernel<HAS_ICA, FAST, true, false, true>;
+        DD_ENSURE_SMEM(kern, kBwdSmem, "recovery kernel (uint8 source)");
+        launch_pdl(kern, dim3(sc.G), dim3(kThreads), kBwdSmem, st, gmap, xf, A, IcA, feat, g, part, Spart, (float*)nullptr, B, H, W, tab);
+    }
+    launch_pdl_cluster(recovery_bwd_finalize_kernel<HAS_ICA, FAST, unsigned char>, dim3(B * kFinCluster), dim3(kFinThreads), 0, st, kFinCluster,
+                       (const unsigned char*)src, A, IcA, feat, (const float*)part, (const float*)Spart, dfeat, (unsigned char*)nullptr, B, H, W, sc.G,
+                       sc.strips, tab);
+    count_launch(2);
+    return check_launch("dd_recovery_bwd_u8");
 }
 
 // tensor-core variant: 148 persistent CTAs, 3xTF32 (fp32 gates).  Same workspace, same finalize kernel.
@@ -581,7 +633,7 @@ static int launch_bwd_tc(const float* x, const float* A, const float* IcA, const
     DD_ENSURE_SMEM(kern, smem, "recovery_bwd_tc_kernel");
     launch_pdl(kern, dim3(sc.G), dim3(btc::kThreadsTC), smem, st, x, A, IcA, feat, g, part, Spart, dx, B, H, W);
     launch_pdl_cluster(recovery_bwd_finalize_kernel<HAS_ICA, FAST>, dim3(B * kFinCluster), dim3(kFinThreads), 0, st, kFinCluster, x, A, IcA, feat,
-                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W, sc.G, sc.strips * btc::kSpartPerStrip);
+                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W, sc.G, sc.strips * btc::kSpartPerStrip, (const float*)nullptr);
     count_launch(2);
     return check_launch("dd_recovery_bwd (tensor-core blur)");
 }
@@ -600,7 +652,7 @@ static int launch_bwd_tc_io(const TX* x, const float* A, const float* IcA, const
     DD_ENSURE_SMEM(kern, smem, "recovery_bwd_tc_kernel (bf16 I/O)");
     launch_pdl(kern, dim3(sc.G), dim3(btc::kThreadsTC), smem, st, x, A, IcA, feat, g, part, Spart, dx, B, H, W);
     launch_pdl_cluster(recovery_bwd_finalize_kernel<HAS_ICA, true, TX>, dim3(B * kFinCluster), dim3(kFinThreads), 0, st, kFinCluster, x, A, IcA, feat,
-                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W, sc.G, sc.strips * btc::kSpartPerStrip);
+                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W, sc.G, sc.strips * btc::kSpartPerStrip, (const float*)nullptr);
     count_launch(2);
     return check_launch("dd_recovery_bwd_ex");
 }
@@ -623,7 +675,7 @@ static int launch_bwd3(const float* x, const float* A, const float* IcA, const f
                     : launch_bwd4<HAS_ICA, FAST, ALIGNED, false>(gmap, x, A, IcA, feat, g, part, Spart, dx, B, H, W, sc, st))
         return e;
     launch_pdl_cluster(recovery_bwd_finalize_kernel<HAS_ICA, FAST>, dim3(B * kFinCluster), dim3(kFinThreads), 0, st, kFinCluster, x, A, IcA, feat,
-                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W, sc.G, sc.strips);
+                       (const float*)part, (const float*)Spart, dfeat, dx, B, H, W, sc.G, sc.strips, (const float*)nullptr);
     count_launch(2);
     return check_launch("dd_recovery_bwd");
 }
@@ -684,4 +736,24 @@ extern "C" int dd_recovery_bwd(const float* x, const float* A, const float* IcA,
                     : launch_bwd2<true, false>(x, A, IcA, feat, g_, dfeat, dx, B, H, W, w, st);
     return fast ? launch_bwd2<false, true>(x, A, nullptr, feat, g_, dfeat, dx, B, H, W, w, st)
                 : launch_bwd2<false, false>(x, A, nullptr, feat, g_, dfeat, dx, B, H, W, w, st);
+}
+
+// ---- backward of the chain on the uint8 batch (no darkened fp32 batch in HBM) --------------------------
+extern "C" int dd_recovery_bwd_u8(const uint8_t* src, const float* dark_table, const float* A, const float* IcA, const float* feat, const float* g_,
+                                  float* dfeat, int B, int H, int W, void* ws, size_t ws_bytes, void* stream_) {
+    using namespace dd;
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (int e = check_recovery_shape("dd_recovery_bwd_u8", B, H, W)) return e;
+    DD_REQUIRE(src && dark_table && feat && g_ && dfeat, DD_ERR_INVALID, "dd_recovery_bwd_u8: null pointer");
+    DD_REQUIRE(ws && ws_bytes >= recovery_bwd_ws_bytes(B, H, W), DD_ERR_WORKSPACE, "dd_recovery_bwd_u8: workspace %zu < %zu", ws_bytes,
+               recovery_bwd_ws_bytes(B, H, W));
+    DD_REQUIRE((W & 3) == 0 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)g_ & 15) == 0 && (!IcA || ((uintptr_t)IcA & 15) == 0), DD_ERR_INVALID,
+               "dd_recovery_bwd_u8: needs W %% 4 == 0, a 4-byte aligned source and 16-byte aligned g / IcA (got W = %d)", W);
+    const bool fast = !precise_mode();
+    float* w = reinterpret_cast<float*>(ws);
+    if (IcA)
+        return fast ? launch_bwd_u8<true, true>(src, dark_table, A, IcA, feat, g_, dfeat, B, H, W, w, st)
+                    : launch_bwd_u8<true, false>(src, dark_table, A, IcA, feat, g_, dfeat, B, H, W, w, st);
+    return fast ? launch_bwd_u8<false, true>(src, dark_table, A, nullptr, feat, g_, dfeat, B, H, W, w, st)
+                : launch_bwd_u8<false, false>(src, dark_table, A, nullptr, feat, g_, dfeat, B, H, W, w, st);
 }

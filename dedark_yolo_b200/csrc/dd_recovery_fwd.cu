@@ -36,12 +36,24 @@ constexpr int kXRP = 160;               // pitch (floats) of the TMA staging row
 // image, one row box per (reflected) image row for the blocks at its top and bottom -- issued by warp 0 one block ahead into a
 // staging tile and counted on an mbarrier: no register prefetch, no per-thread address arithmetic, and the stage phase never
 // waits for DRAM.
-template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA>
+// U8: x is the dataloader's uint8 batch (train.py:72) and `dark_tab` the 256-entry darkening table
+// pow(k/255, p) (dd_dark_table): the darkened fp32 batch is never materialised in HBM, the stage phase looks it up.  Needs
+// ALIGNED (W % 4 == 0: one 32-bit load per four pixels) and runs on the register-prefetch path (TMA = false).
+template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA, bool U8 = false>
 __global__ void __launch_bounds__(kThreads, 2)
 recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap xmap16,
                     const float* __restrict__ x, const float* __restrict__ A,
-                    const float* __restrict__ IcA, const float* __restrict__ feat, float* __restrict__ y, int B, int H, int W) {
+                    const float* __restrict__ IcA, const float* __restrict__ feat, float* __restrict__ y, int B, int H, int W,
+                    const float* __restrict__ dark_tab = nullptr) {
+    static_assert(!U8 || (ALIGNED && !TMA), "uint8 sources: aligned rows, register prefetch");
     pdl_begin();
+    __shared__ float s_tab[U8 ? 256 : 1];
+    if (U8) {
+        if (threadIdx.x < 256) s_tab[threadIdx.x] = __ldg(dark_tab + threadIdx.x);
+        __syncthreads();
+    }
+    const unsigned char* x8 = reinterpret_cast<const unsigned char*>(x);
+    auto lut4 = [&](unsigned w) { return make_float4(s_tab[w & 255u], s_tab[(w >> 8) & 255u], s_tab[(w >> 16) & 255u], s_tab[w >> 24]); };
     extern __shared__ __align__(128) float smem[];
     float* XR = smem;                                  // [32 rows][kXRP] raw x of the block being staged (TMA only)
     float* XS2 = smem + (TMA ? kRB * kXRP : 0);
@@ -73,6 +85,7 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
         const float pc = sp.c, pp = sp.p;
         const float* xp = x + (size_t)u.plane * H * W;
+        const unsigned char* xp8 = x8 + (size_t)u.plane * H * W;
         const float* ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
         float* yp = y + (size_t)u.plane * H * W;
 
@@ -107,7 +120,8 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                         const size_t ro = (size_t)row * W;
                         if (ALIGNED) {
                             if (gc >= 0 && gc < W) {
-                                pre[k][e] = __ldg(reinterpret_cast<const float4*>(xp + ro + gc));
+                                if (U8) pre[k][e].x = __uint_as_float(__ldg(reinterpret_cast<const unsigned*>(xp8 + ro + gc)));  // four source bytes
+                                else pre[k][e] = __ldg(reinterpret_cast<const float4*>(xp + ro + gc));
                                 if (HAS_ICA) prei[k][e] = __ldg(reinterpret_cast<const float4*>(ip + ro + gc));
                             }
                         } else {
@@ -133,7 +147,7 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                     const int row = reflect(u.r0 - kRadius + v, H);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        x0r[k][c] = __ldg(xp + (size_t)row * W + c);
+                        x0r[k][c] = U8 ? s_tab[__ldg(xp8 + (size_t)row * W + c)] : __ldg(xp + (size_t)row * W + c);
                         icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
                     }
                 }
@@ -170,7 +184,8 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const float m = MS[min(v0 + e, u.nU - 1)];
-                        const float4 in = TMA ? *reinterpret_cast<const float4*>(XR + (2 * rp + e) * kXRP + 4 * c4) : pre[k][e];
+                        const float4 in = TMA ? *reinterpret_cast<const float4*>(XR + (2 * rp + e) * kXRP + 4 * c4)
+                                          : U8 ? lut4(__float_as_uint(pre[k][e].x)) : pre[k][e];
                         const float4 ic = HAS_ICA ? prei[k][e] : make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
                         o[e][0] = chain_x3<HAS_ICA, FAST>(ck, in.x, ic.x) * m;
                         o[e][1] = chain_x3<HAS_ICA, FAST>(ck, in.y, ic.y) * m;
@@ -282,8 +297,23 @@ static int launch_fwd4(const CUtensorMap& xmap, const CUtensorMap& xmap16, const
                        int H, int W, const Sched& sc, cudaStream_t st) {
     constexpr size_t smem = TMA ? kFwdSmemTma : kFwdSmem;
     DD_ENSURE_SMEM((recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>), smem, "recovery kernel");
-    launch_pdl(recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>, dim3(sc.G), dim3(kThreads), smem, st, xmap, xmap16, x, A, IcA, feat, y, B, H, W);
+    launch_pdl(recovery_fwd_kernel<HAS_ICA, FAST, ALIGNED, TMA>, dim3(sc.G), dim3(kThreads), smem, st, xmap, xmap16, x, A, IcA, feat, y, B, H, W,
+               (const float*)nullptr);
     return DD_OK;
+}
+
+// the same kernel reading the uint8 batch through the darkening table
+template <bool HAS_ICA, bool FAST>
+static int launch_fwd_u8(const uint8_t* src, const float* tab, const float* A, const float* IcA, const float* feat, float* y, int B, int H, int W,
+                         cudaStream_t st) {
+    const Sched sc = make_sched(B, H, W);
+    CUtensorMap none;
+    memset(&none, 0, sizeof(none));
+    auto kern = recovery_fwd_kernel<HAS_ICA, FAST, true, false, true>;
+    DD_ENSURE_SMEM(kern, kFwdSmem, "recovery kernel (uint8 source)");
+    launch_pdl(kern, dim3(sc.G), dim3(kThreads), kFwdSmem, st, none, none, reinterpret_cast<const float*>(src), A, IcA, feat, y, B, H, W, tab);
+    count_launch();
+    return check_launch("dd_recovery_fwd_u8");
 }
 
 // tensor-core variant: 148 persistent CTAs, 3xTF32 (fp32 gate 1e-5)
@@ -394,4 +424,18 @@ extern "C" int dd_recovery_fwd(const float* x, const float* A, const float* IcA,
     const bool fast = !precise_mode();
     if (IcA) return fast ? launch_fwd2<true, true>(x, A, IcA, feat, y, B, H, W, st) : launch_fwd2<true, false>(x, A, IcA, feat, y, B, H, W, st);
     return fast ? launch_fwd2<false, true>(x, A, nullptr, feat, y, B, H, W, st) : launch_fwd2<false, false>(x, A, nullptr, feat, y, B, H, W, st);
+}
+
+// ---- uint8 batch -> filter chain without a darkened fp32 batch in HBM -------------------------------------
+extern "C" int dd_recovery_fwd_u8(const uint8_t* src, const float* dark_table, const float* A, const float* IcA, const float* feat, float* y,
+                                  int B, int H, int W, void* stream_) {
+    using namespace dd;
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (int e = check_recovery_shape("dd_recovery_fwd_u8", B, H, W)) return e;
+    DD_REQUIRE(src && dark_table && feat && y, DD_ERR_INVALID, "dd_recovery_fwd_u8: null pointer");
+    DD_REQUIRE((W & 3) == 0 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)y & 7) == 0 && (!IcA || ((uintptr_t)IcA & 15) == 0), DD_ERR_INVALID,
+               "dd_recovery_fwd_u8: needs W %% 4 == 0, a 4-byte aligned source and 16-byte aligned IcA (got W = %d)", W);
+    const bool fast = !precise_mode();
+    if (IcA) return fast ? launch_fwd_u8<true, true>(src, dark_table, A, IcA, feat, y, B, H, W, st) : launch_fwd_u8<true, false>(src, dark_table, A, IcA, feat, y, B, H, W, st);
+    return fast ? launch_fwd_u8<false, true>(src, dark_table, A, nullptr, feat, y, B, H, W, st) : launch_fwd_u8<false, false>(src, dark_table, A, nullptr, feat, y, B, H, W, st);
 }

@@ -230,6 +230,50 @@ def filters_backward(x, feat, g, A=None, IcA=None, need_dx: bool = False):
     return dfeat, dx
 
 
+# ---- the chain on the uint8 batch (no darkened fp32 batch in HBM) ----------------------------------------
+def dark_table(p: float, device, lut: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The 256 darkened values ``pow(k/255, p)`` as ``dd_synth_fwd`` produces them (``lut`` overrides, e.g. the reference's CPU bits)."""
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        t = torch.empty(256, dtype=torch.float32, device=dev)
+        lut = None if lut is None else _f32c(lut.to(dev))
+        check(lib.dd_dark_table(float(p), _ptr(lut), _ptr(t), _stream(dev)))
+    return t
+
+
+def _u8_batch(src):
+    _need_cuda(src)
+    if src.dtype != torch.uint8 or src.dim() != 4 or src.shape[1] != 3:
+        raise TypeError(f"uint8 [B,3,H,W] expected, got {src.dtype} {tuple(src.shape)}")
+    return src.contiguous()
+
+
+def filters_forward_u8(src_u8, table, feat, A=None, IcA=None) -> torch.Tensor:
+    """``filters_forward(table[src_u8], feat, A, IcA)`` without materialising the darkened batch (``dd_recovery_fwd_u8``)."""
+    src_u8 = _u8_batch(src_u8)
+    _need_cuda(table, feat, A, IcA)
+    B, _, H, W = src_u8.shape
+    y = torch.empty(src_u8.shape, dtype=torch.float32, device=src_u8.device)
+    with torch.cuda.device(src_u8.device):
+        check(lib.dd_recovery_fwd_u8(_ptr(src_u8), _ptr(table), _ptr(A), _ptr(IcA), _ptr(feat), _ptr(y), B, H, W, _stream(src_u8.device)))
+    return y
+
+
+def filters_backward_u8(src_u8, table, feat, g, A=None, IcA=None) -> torch.Tensor:
+    """dfeat of ``filters_backward(table[src_u8], ...)`` (``dd_recovery_bwd_u8``; a uint8 source has no dx)."""
+    src_u8 = _u8_batch(src_u8)
+    _need_cuda(table, feat, g, A, IcA)
+    B, _, H, W = src_u8.shape
+    dev = src_u8.device
+    dfeat = torch.empty(B, NUM_FEATURES, dtype=torch.float32, device=dev)
+    ws_bytes = _lib.workspace_bytes(_lib.WS_RECOVERY_BWD, B, H, W)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dd_recovery_bwd_u8(_ptr(src_u8), _ptr(table), _ptr(A), _ptr(IcA), _ptr(feat), _ptr(_f32c(g)), _ptr(dfeat), B, H, W,
+                                     _ptr(ws), ws_bytes, _stream(dev)))
+    return dfeat
+
+
 def debug_blur_tc(x: torch.Tensor, x3: bool = True) -> torch.Tensor:
     """Unit-test hook: the reflect-padded 25x25 Gaussian of ``x`` through the tensor-core engine (``dd_debug_blur_tc``)."""
     _need_cuda(x)

@@ -55,7 +55,7 @@ class _Range:
 class RecoveryPipeline:
     def __init__(self, module: lowlight_recovery, B: int, H: int, W: int, dark_param: float = 15.0,
                  src_dtype: torch.dtype = torch.float32, device=None, process_group=None, allreduce: bool = False,
-                 exchange=None, keep_clean: bool = False, io_dtype: torch.dtype = torch.float32):
+                 exchange=None, keep_clean: bool = False, io_dtype: torch.dtype = torch.float32, materialize_dark: bool = True):
         dev = torch.device(device if device is not None else next(module.parameters()).device)
         if dev.type != "cuda":
             raise RuntimeError("RecoveryPipeline needs a CUDA device (no CPU fallback)")
@@ -70,6 +70,7 @@ class RecoveryPipeline:
         # uint8 sources: the fp32 clean image (train.py:72, ``batch["clean_img"]``) is only an operand of the recovery loss, which
         # the synthesis pass has already reduced -- it is materialised (one more full-size write) only on request
         self.keep_clean = keep_clean
+        self.materialize_dark = bool(materialize_dark)   # validated below (needs fused_resize)
         self.params = [q.detach() for q in ordered_parameters(module.extractor)]
         for q in self.params:
             assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous()
@@ -100,18 +101,30 @@ class RecoveryPipeline:
         # shared memory) -- that pass is HBM bound and the fusion saves the re-read of the dark batch (e2e +7 %).  fp32 sources stay
         # on two passes: their synthesis is issue bound on the exact powf and the fused kernel measured 8 us slower than the pair.
         self.fused_resize = src_dtype == torch.uint8 and io_dtype == torch.float32 and bool(lib.dd_synth_resize_supported(H, W))
+        # uint8 batch -> synthesis -> filter chain without the darkened fp32 batch in HBM.  The fused
+        # synthesis pass then only produces r and the recovery loss, and the filter kernels read the uint8 batch through the
+        # 256-entry darkening table (y and the gradients are bit-identical).  The uint8 batch of a step must stay alive and
+        # unchanged until that step's backward has run (HostBatchPrefetcher holds a slot exactly that long).
+        if not self.materialize_dark:
+            if not self.fused_resize:
+                raise ValueError("materialize_dark=False needs a uint8 source, fp32 I/O and a size the fused synthesis + resize pass "
+                                 "supports (W % 4 == 0)")
+            self._dark_tab = torch.empty(256, **f32)
+            with torch.cuda.device(dev):
+                check(lib.dd_dark_table(self.p, None, _p(self._dark_tab), torch.cuda.current_stream(dev).cuda_stream))
         self.graphs = {}
 
     # -- per-batch buffers: what the synthesis writes and the rest of the step reads ---------------------
     class _Slot:
-        __slots__ = ("clean", "dark", "rec", "r", "ws_syn")
+        __slots__ = ("clean", "dark", "rec", "r", "ws_syn", "src")
 
     def _new_slot(self):
         f32 = dict(dtype=torch.float32, device=self.dev)
         B, H, W = self.B, self.H, self.W
         s = self._Slot()
         s.clean = torch.empty(B, 3, H, W, **f32) if (self.src_dtype == torch.uint8 and self.keep_clean) else None
-        s.dark = torch.empty(B, 3, H, W, dtype=self.io_dtype, device=self.dev)
+        s.dark = torch.empty(B, 3, H, W, dtype=self.io_dtype, device=self.dev) if self.materialize_dark else None
+        s.src = None   # materialize_dark=False: the uint8 batch this slot's step reads
         s.rec = torch.zeros((), **f32)
         s.r = torch.empty(B, 3, 256, 256, **f32)
         s.ws_syn = torch.empty(_lib.workspace_bytes(_lib.WS_SYNTH, B), dtype=torch.uint8, device=self.dev)
@@ -132,6 +145,8 @@ class RecoveryPipeline:
         s = self._slots[self._cur if slot is None else slot]
         is_u8 = src.dtype == torch.uint8
         if self.fused_resize:  # also produces r: forward() then skips dd_resize256
+            if not self.materialize_dark:
+                s.src = src
             check(lib.dd_synth_resize_fwd(_p(src), _lib.SRC_U8 if is_u8 else _lib.SRC_F32, self.p, None, None,
                                           _p(s.clean), _p(s.dark), _p(s.r), _p(s.rec), self.B, self.H,
                                           self.W, _p(s.ws_syn), s.ws_syn.numel(), st))
@@ -156,6 +171,9 @@ class RecoveryPipeline:
 
     def _filters_fwd(self, st, A, IcA):
         B, H, W = self.B, self.H, self.W
+        if not self.materialize_dark:
+            check(lib.dd_recovery_fwd_u8(_p(self._slots[self._cur].src), _p(self._dark_tab), _p(A), _p(IcA), _p(self.feat), _p(self.y), B, H, W, st))
+            return
         check(lib.dd_recovery_fwd_ex(_p(self.dark), self._dt, _p(A), _p(IcA), _p(self.feat), _p(self.y), self._dt, B, H, W, st))
 
     def backward_filters(self, g, st, A=None, IcA=None):
@@ -164,6 +182,10 @@ class RecoveryPipeline:
 
     def _filters_bwd(self, g, st, A=None, IcA=None):
         B, H, W = self.B, self.H, self.W
+        if not self.materialize_dark:
+            check(lib.dd_recovery_bwd_u8(_p(self._slots[self._cur].src), _p(self._dark_tab), _p(A), _p(IcA), _p(self.feat), _p(g), _p(self.dfeat),
+                                         B, H, W, _p(self._ws_rb), self._ws_rb.numel(), st))
+            return
         check(lib.dd_recovery_bwd_ex(_p(self.dark), self._dt, _p(A), _p(IcA), _p(self.feat), _p(g), self._dt, _p(self.dfeat), None, B, H, W,
                                      _p(self._ws_rb), self._ws_rb.numel(), st))
 

@@ -88,6 +88,18 @@ int dd_synth_resize_fwd(const void* src, int src_dtype, float p, const float* lu
                         float* clean_out, float* dark_out, float* r_out, float* rec_out, int B, int H, int W, void* ws,
                         size_t ws_bytes, void* stream);
 
+/* ---- uint8 batch -> filter chain in one pass, no darkened fp32 batch in HBM ---------------------
+ * (models/yolo/detect/train.py:72-109: the dataloader hands uint8 NCHW, data/dataset.py:172-188.)  dd_dark_table writes the 256
+ * darkened values dark[k] = pow(k/255, p) -- the same bits dd_synth_fwd produces; lut256 overrides as there -- and
+ * dd_recovery_fwd_u8 / dd_recovery_bwd_u8 are dd_recovery_fwd / dd_recovery_bwd reading `src` (uint8 [B,3,H,W]) through that
+ * table in their stage phase: y and dfeat are bit-identical to the fp32-source calls on the materialised batch.  Needs
+ * W % 4 == 0.  dd_synth_resize_fwd with dark_out == NULL then only produces r and the recovery loss.  No dx (x is data). */
+int dd_dark_table(float p, const float* lut256, float* table_out, void* stream);
+int dd_recovery_fwd_u8(const uint8_t* src, const float* dark_table, const float* A, const float* IcA, const float* feat, float* y,
+                       int B, int H, int W, void* stream);
+int dd_recovery_bwd_u8(const uint8_t* src, const float* dark_table, const float* A, const float* IcA, const float* feat, const float* g,
+                       float* dfeat, int B, int H, int W, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- the dark-channel prior on the GPU ------------------------------------------
  * Replaces the per-batch D2H + numpy loop of DetectionTrainer.preprocess_batch (models/yolo/detect/train.py:81-97:
  * DarkChannel :42-45, AtmLight :47-61, DarkIcA :63-67) that produces batch['dedark_A'] / batch['IcA'].  Works on the
