@@ -17,11 +17,16 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 m = dd.lowlight_recovery(3).to(dev).train()
 U8 = os.environ.get("PROF_SRC", "f32") == "u8"  # the e2e path: uint8 batch, synthesis fused with the resize
-pipe = dd.RecoveryPipeline(m, B, H, W, dark_param=15.0, src_dtype=torch.uint8 if U8 else torch.float32)
+BF16 = os.environ.get("PROF_IO", "f32") == "bf16"  # bf16 I/O mode: tensor-core filter kernels
+N2 = os.environ.get("PROF_N2", "0") == "1"         # uint8 batch read by the filter kernels (no dark batch)
+pipe = dd.RecoveryPipeline(m, B, H, W, dark_param=15.0, src_dtype=torch.uint8 if U8 else torch.float32,
+                           io_dtype=torch.bfloat16 if BF16 else torch.float32, materialize_dark=not N2)
 gen = torch.Generator(device=dev).manual_seed(1234)
 clean = (torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, device=dev) if U8
          else torch.rand(B, 3, H, W, generator=gen, device=dev))
 g = torch.randn(B, 3, H, W, generator=gen, device=dev)
+if BF16:
+    g = g.bfloat16()
 n0 = dd.launch_count()
 for _ in range(steps):
     pipe.step(clean, g)
