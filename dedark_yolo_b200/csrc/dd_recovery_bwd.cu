@@ -127,15 +127,23 @@ namespace dd {
 // TMA: the g halo tile of every row-block arrives as two 16-row x 156-column boxes (cp.async.bulk.tensor through a tensor
 // map of the [planes][H][W] cotangent; everything outside the image is zero-filled by the copy engine), issued by one
 // thread and counted on an mbarrier: no per-thread address arithmetic, no staging instructions at all.
-// U8: x is the uint8 source batch, read through the 256-entry darkening table `dark_tab` (one 32-bit load
-// per four pixels; needs ALIGNED); no dx (x is data).
-template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA, bool U8 = false>
+// XT: element type of x -- 0 fp32; 1 uint8: the source batch, read through the 256-entry darkening table
+// `dark_tab` (one 32-bit load per four pixels); 2 bf16 (the bf16 I/O mode).  GB: the cotangent g is bf16 -- it
+// is converted to fp32 on its way into the ring (register prefetch one block ahead; TMA moves bytes, it cannot widen them).
+// The arithmetic is fp32 throughout.  XT != 0 and GB need ALIGNED; no dx for a uint8 source.
+constexpr int kXF32 = 0, kXU8 = 1, kXBF16 = 2;
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 q) {
+    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xFFFF0000u), __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xFFFF0000u));
+}
+template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA, int XT = kXF32, bool GB = false>
 __global__ void __launch_bounds__(kThreads, 2)
 recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __restrict__ x, const float* __restrict__ A,
                     const float* __restrict__ IcA, const float* __restrict__ feat, const float* __restrict__ g,
                     float* __restrict__ part, float* __restrict__ Spart, float* __restrict__ dx, int B, int H, int W,
                     const float* __restrict__ dark_tab = nullptr) {
-    static_assert(!U8 || ALIGNED, "uint8 sources need 4-byte aligned rows");
+    constexpr bool U8 = XT == kXU8, XB = XT == kXBF16;
+    static_assert((XT == kXF32 && !GB) || ALIGNED, "uint8 / bf16 operands need aligned rows");
+    static_assert(!(GB && TMA), "a bf16 cotangent is staged through registers");
     pdl_begin();
     __shared__ float s_tab[U8 ? 256 : 1];
     if (U8) {
@@ -143,6 +151,8 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         __syncthreads();
     }
     const unsigned char* x8 = reinterpret_cast<const unsigned char*>(x);
+    const unsigned short* xb = reinterpret_cast<const unsigned short*>(x);
+    const unsigned short* gb = reinterpret_cast<const unsigned short*>(g);
     auto lut4 = [&](unsigned w) { return make_float4(s_tab[w & 255u], s_tab[(w >> 8) & 255u], s_tab[(w >> 16) & 255u], s_tab[w >> 24]); };
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t tma_bar;
@@ -198,11 +208,53 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         const float pc = sp.c, pp = sp.p;
         const float* xp = x + (size_t)u.plane * H * W;
         const unsigned char* xp8 = x8 + (size_t)u.plane * H * W;
+        const unsigned short* xpb = xb + (size_t)u.plane * H * W;
+        const unsigned short* gpb = gb + (size_t)u.plane * H * W;
         const float* gp = g + (size_t)u.plane * H * W;
         const float* ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
 
         // g block n -> ring XS (rows outside the image and columns outside [0, W) are zero)
+        uint2 gpre[GB ? kStage4 : 1];   // GB: the bf16 rows of the next block, in flight between stage(n) and stage_commit(n)
+        // GB: a thread's items of a block are the same (row, column chunk) pairs in every block -- their offsets are computed once per
+        // segment, a block then costs one ring-row wrap test and one bounds test per item
+        int g_rr[GB ? kStage4 : 1], g_soff[GB ? kStage4 : 1];
+        unsigned g_goff[GB ? kStage4 : 1];
+        bool g_colok[GB ? kStage4 : 1];
+        if (GB) {
+#pragma unroll
+            for (int k = 0; k < kStage4; ++k) {
+                const int f = tid + k * kThreads;
+                const int rr = f / kXW4, c4 = f - rr * kXW4, gc = u.c0 - kRadius + 4 * c4;
+                g_rr[k] = f < kRB * kXW4 ? rr : -1;
+                g_soff[k] = 4 * c4;
+                g_colok[k] = gc >= 0 && gc < W;
+                g_goff[k] = (unsigned)(rr * W + gc);   // + (first row of the block) * W; only used when the row and column are inside
+            }
+        }
+        auto stage_commit = [&](int n) {  // GB only: widen and store block n into the ring (its rows are free since the last barrier)
+            if (!GB) return;
+            const int rb = (n * kRB) % kXRingB;
+#pragma unroll
+            for (int k = 0; k < kStage4; ++k) {
+                if (g_rr[GB ? k : 0] >= 0) {
+                    int ring = rb + g_rr[GB ? k : 0];
+                    ring = ring >= kXRingB ? ring - kXRingB : ring;
+                    *reinterpret_cast<float4*>(XS + ring * kXP + g_soff[GB ? k : 0]) = bf16x4_to_float4(gpre[GB ? k : 0]);
+                }
+            }
+        };
         auto stage = [&](int n) {
+            if (GB) {
+                const int row0 = u.r0 - kRadius + n * kRB;
+                const unsigned short* base = gpb + (ptrdiff_t)row0 * W;
+#pragma unroll
+                for (int k = 0; k < kStage4; ++k) {
+                    const int row = row0 + g_rr[GB ? k : 0];
+                    const bool ok = g_rr[GB ? k : 0] >= 0 && g_colok[GB ? k : 0] && row >= 0 && row < H;
+                    gpre[GB ? k : 0] = ok ? __ldg(reinterpret_cast<const uint2*>(base + g_goff[GB ? k : 0])) : make_uint2(0u, 0u);
+                }
+                return;
+            }
             if (TMA) {
                 if (tid == 0) {
                     mbar_arrive_expect_tx(&tma_bar, 2u * 16u * kXP * 4u);
@@ -253,7 +305,8 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                 if (v < u.nU && row >= 0 && row < H) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        x0r[k][c] = U8 ? s_tab[__ldg(xp8 + (size_t)row * W + c)] : __ldg(xp + (size_t)row * W + c);
+                        x0r[k][c] = U8 ? s_tab[__ldg(xp8 + (size_t)row * W + c)]
+                                       : XB ? __uint_as_float((unsigned)__ldg(xpb + (size_t)row * W + c) << 16) : __ldg(xp + (size_t)row * W + c);
                         icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
                     }
                 }
@@ -284,7 +337,9 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         for (int n = 0; n <= u.nB; ++n) {
             const bool have = n < u.nB;
             if (have) {
-                if (TMA) {
+                if (GB) {
+                    stage_commit(n);
+                } else if (TMA) {
                     mbar_wait(&tma_bar, tma_phase);
                     tma_phase ^= 1u;
                 } else {
@@ -308,7 +363,8 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                         const float4 g5 = *reinterpret_cast<const float4*>(XS + (o % kXRingB) * kXP + 4 * c4 + kRadius);
                         const float4 bt = *reinterpret_cast<const float4*>(BT + rr * kBP + 4 * c4);
                         const float m = MSm[o], q1 = MSq[o];
-                        const float4 x0 = U8 ? lut4(__float_as_uint(x0p[k].x)) : x0p[k];
+                        const float4 x0 = U8 ? lut4(__float_as_uint(x0p[k].x))
+                                          : XB ? bf16x4_to_float4(make_uint2(__float_as_uint(x0p[k].x), __float_as_uint(x0p[k].y))) : x0p[k];
                         const size_t off = (size_t)jr * W + gc;
                         float4 ic = make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
                         if (HAS_ICA) {
@@ -387,6 +443,10 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                         const float* rp = xp + (size_t)(u.r0 + o - kRadius) * W + gc;
                         if (U8) {
                             x0p[k].x = __uint_as_float(__ldg(reinterpret_cast<const unsigned*>(xp8 + (size_t)(u.r0 + o - kRadius) * W + gc)));
+                        } else if (XB) {
+                            const uint2 q = __ldg(reinterpret_cast<const uint2*>(xpb + (size_t)(u.r0 + o - kRadius) * W + gc));
+                            x0p[k].x = __uint_as_float(q.x);
+                            x0p[k].y = __uint_as_float(q.y);
                         } else if (ALIGNED) {
                             x0p[k] = __ldg(reinterpret_cast<const float4*>(rp));
                         } else {
@@ -604,11 +664,11 @@ static int launch_bwd_u8(const uint8_t* src, const float* tab, const float* A, c
     const bool tma = W >= kXP && H >= 16 && make_tensor_map_3d(&gmap, g, B * 3, H, W, kXP, 16);
     const float* xf = reinterpret_cast<const float*>(src);
     if (tma) {
-        auto kern = recovery_bwd_kernel<HAS_ICA, FAST, true, true, true>;
+        auto kern = recovery_bwd_kernel<HAS_ICA, FAST, true, true, kXU8>;
         DD_ENSURE_SMEM(kern, kBwdSmem, "recovery kernel (uint8 source)");
         launch_pdl(kern, dim3(sc.G), dim3(kThreads), kBwdSmem, st, gmap, xf, A, IcA, feat, g, part, Spart, (float*)nullptr, B, H, W, tab);
     } else {
-        auto kern = recovery_bwd_kernel<HAS_ICA, FAST, true, false, true>;
+        auto kern = recovery_bwd_kernel<HAS_ICA, FAST, true, false, kXU8>;
         DD_ENSURE_SMEM(kern, kBwdSmem, "recovery kernel (uint8 source)");
         launch_pdl(kern, dim3(sc.G), dim3(kThreads), kBwdSmem, st, gmap, xf, A, IcA, feat, g, part, Spart, (float*)nullptr, B, H, W, tab);
     }
@@ -617,6 +677,38 @@ static int launch_bwd_u8(const uint8_t* src, const float* tab, const float* A, c
                        sc.strips, tab);
     count_launch(2);
     return check_launch("dd_recovery_bwd_u8");
+}
+
+// bf16 I/O mode on the CUDA-core kernel (no dx): x and / or g are bf16, fp32 arithmetic and FFMA2 blur.  Measured on B200
+// (16x3x640x640, both bf16): this kernel ~135 us against 232 us for the tensor-core backward, whose lane <-> column epilogue pays
+// one warp reduction per 32 pixels and scalar loads (profiles/r02_ncu_full_filters_bf16_tc.md) -- so it is the default.
+template <bool HAS_ICA, typename TX, typename TG>
+static int launch_bwd_cc_io(const TX* x, const float* A, const float* IcA, const float* feat, const TG* g, float* dfeat, int B, int H, int W, float* ws,
+                            cudaStream_t st) {
+    constexpr int XT = sizeof(TX) == 2 ? kXBF16 : kXF32;
+    constexpr bool GB = sizeof(TG) == 2;
+    const Sched sc = make_sched(B, H, W);
+    float* part = ws;
+    float* Spart = part + (size_t)(sc.G + sc.nPS) * kBwdSums;
+    CUtensorMap gmap;
+    memset(&gmap, 0, sizeof(gmap));
+    const float* xf = reinterpret_cast<const float*>(x);
+    const float* gf = reinterpret_cast<const float*>(g);
+    bool tma = false;
+    if (!GB) tma = W >= kXP && H >= 16 && make_tensor_map_3d(&gmap, gf, B * 3, H, W, kXP, 16);
+    if (tma) {
+        auto kern = recovery_bwd_kernel<HAS_ICA, true, true, !GB, XT, false>;
+        DD_ENSURE_SMEM(kern, kBwdSmem, "recovery kernel (bf16 I/O)");
+        launch_pdl(kern, dim3(sc.G), dim3(kThreads), kBwdSmem, st, gmap, xf, A, IcA, feat, gf, part, Spart, (float*)nullptr, B, H, W, (const float*)nullptr);
+    } else {
+        auto kern = recovery_bwd_kernel<HAS_ICA, true, true, false, XT, GB>;
+        DD_ENSURE_SMEM(kern, kBwdSmem, "recovery kernel (bf16 I/O)");
+        launch_pdl(kern, dim3(sc.G), dim3(kThreads), kBwdSmem, st, gmap, xf, A, IcA, feat, gf, part, Spart, (float*)nullptr, B, H, W, (const float*)nullptr);
+    }
+    launch_pdl_cluster(recovery_bwd_finalize_kernel<HAS_ICA, true, TX>, dim3(B * kFinCluster), dim3(kFinThreads), 0, st, kFinCluster, x, A, IcA, feat,
+                       (const float*)part, (const float*)Spart, dfeat, (TX*)nullptr, B, H, W, sc.G, sc.strips, (const float*)nullptr);
+    count_launch(2);
+    return check_launch("dd_recovery_bwd_ex");
 }
 
 // tensor-core variant: 148 persistent CTAs, 3xTF32 (fp32 gates).  Same workspace, same finalize kernel.
@@ -709,6 +801,16 @@ extern "C" int dd_recovery_bwd_ex(const void* x, int x_dtype, const float* A, co
     DD_REQUIRE((W & 3) == 0 && H > kRadius + 1 && W > kRadius + 1 && (((uintptr_t)x | (uintptr_t)g_ | (uintptr_t)dx) & 15) == 0, DD_ERR_INVALID,
                "dd_recovery_bwd_ex: the bf16 I/O mode needs W %% 4 == 0, H and W >= 14 and 16-byte aligned x / g / dx (got %d x %d)", H, W);
     float* w = reinterpret_cast<float*>(ws);
+    // no dx wanted (training: x is data) -> the CUDA-core kernel with bf16 loads (faster); DEDARK_BLUR=tc keeps the tensor-core backward
+    if (!dx && !blur_on_tensor_cores()) {
+#define DD_BWD_CC(TX, TG)                                                                                                                       \
+    return IcA ? launch_bwd_cc_io<true, TX, TG>(reinterpret_cast<const TX*>(x), A, IcA, feat, reinterpret_cast<const TG*>(g_), dfeat, B, H, W, w, st) \
+               : launch_bwd_cc_io<false, TX, TG>(reinterpret_cast<const TX*>(x), A, nullptr, feat, reinterpret_cast<const TG*>(g_), dfeat, B, H, W, w, st)
+        if (x_dtype == DD_BF16 && g_dtype == DD_BF16) { DD_BWD_CC(bf16, bf16); }
+        if (x_dtype == DD_BF16) { DD_BWD_CC(bf16, float); }
+        DD_BWD_CC(float, bf16);
+#undef DD_BWD_CC
+    }
 #define DD_BWD_IO(TX, TG)                                                                                                                       \
     return IcA ? launch_bwd_tc_io<true, TX, TG>(reinterpret_cast<const TX*>(x), A, IcA, feat, reinterpret_cast<const TG*>(g_), dfeat,              \
                                                 reinterpret_cast<TX*>(dx), B, H, W, w, st)                                                        \
