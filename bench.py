@@ -483,6 +483,18 @@ def run_ours(args):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
 
+    # the same loop with module.use_cuda_graphs = True: forward and backward launch sequences replayed as CUDA graphs
+    module.use_cuda_graphs = True
+    for i in range(8):   # first sightings run eagerly, second sightings capture
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_graph_s = max_over_ranks(time.perf_counter() - t0, dev)
+    module.use_cuda_graphs = False
+
     # same loop with the host reading each step's result one step late (the D2H of step i is awaited while step i+1 is
     # already enqueued): host-side launch work then overlaps the kernels of the previous step.  Reported beside the
     # synchronous number, which stays the headline.
@@ -620,8 +632,11 @@ def run_ours(args):
                   + " + stream sync, every step",
            "module_api": {"value": world * B * e2e_steps / e2e_s, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                           "api": "HostBatchPrefetcher -> preprocess_batch -> lowlight_recovery(nn.Module) fwd -> autograd bwd -> "
-                                 "D2H(recovery loss, grad norm) + stream sync every step (eager; bound by ~0.7 ms of Python/autograd "
-                                 "host work per step, not by the GPU)"},
+                                 "D2H(recovery loss, grad norm) + stream sync every step (eager launches; host-bound: ~0.4 ms of "
+                                 "Python / autograd / launch work per step)"},
+           "module_api_cuda_graphs": {"value": world * B * e2e_steps / e2e_graph_s, "ms_per_step": 1e3 * e2e_graph_s / e2e_steps,
+                                      "api": "the same loop with lowlight_recovery.use_cuda_graphs = True (the module replays its forward "
+                                             "and backward launch sequences as CUDA graphs keyed by the buffers' addresses)"},
            "module_api_result_read_one_step_late": {"value": world * B * e2e_steps / e2e_lag_s, "ms_per_step": 1e3 * e2e_lag_s / e2e_steps},
            "no_dark_batch_n2": n2,
            "h2d_gbs_measured": h2d_gbs, "h2d_ms_per_step_alone": B * 3 * H * W / (h2d_gbs * 1e9) * 1e3}

@@ -47,7 +47,13 @@ def preprocess_batch(batch: dict, device, dark_param: float = 15.0, lowlight_FLA
         batch["img"] = clean
         batch["recovery_loss_batch"] = torch.zeros((), dtype=torch.float32, device=src.device)
         return batch
-    clean, dark, _, rec = ops.synth_forward(src, dark_param, lut=lut, clean_lut=clean_lut)
+    if src.dim() == 4 and src.shape[1] == 3 and ops.synth_resize_supported(src.shape[2], src.shape[3]):
+        # one pass: darkening + recovery loss + the 256x256 resize the module applies first (llie.py:43); the resized batch rides
+        # on the darkened tensor and lowlight_recovery.forward picks it up instead of re-reading the full-size batch
+        clean, dark, r, rec = ops.synth_resize_forward(src, dark_param, lut=lut, clean_lut=clean_lut)
+        dark._dd_resize256 = (r, dark._version)
+    else:
+        clean, dark, _, rec = ops.synth_forward(src, dark_param, lut=lut, clean_lut=clean_lut)
     if dedark_FLAG:
         batch["clean_img"] = dark
         batch["img"] = dark

@@ -112,6 +112,9 @@ class RecoveryPipeline:
             self._dark_tab = torch.empty(256, **f32)
             with torch.cuda.device(dev):
                 check(lib.dd_dark_table(self.p, None, _p(self._dark_tab), torch.cuda.current_stream(dev).cuda_stream))
+        # experiment switch (profiles/debug/fork_probe.py): fork the next batch's synthesis before the filter backward instead of
+        # behind it
+        self.fork_before_filters_bwd = False
         self.graphs = {}
 
     # -- per-batch buffers: what the synthesis writes and the rest of the step reads ---------------------
@@ -264,7 +267,9 @@ class RecoveryPipeline:
             cur = self._cur
             rec = self._slots[cur].rec
             self.forward(st, resize=False)
-            self.backward_filters(g, st)
+            early = self.fork_before_filters_bwd and src_next is not None
+            if not early:
+                self.backward_filters(g, st)
             if src_next is not None:
                 assert src_next.shape == (self.B, 3, self.H, self.W)
                 self._ev_fork.record(main)
@@ -273,6 +278,8 @@ class RecoveryPipeline:
                 self.synth(src_next, sst, slot=cur ^ 1)
                 self.resize(sst, slot=cur ^ 1)
                 self._ev_join.record(self._side)
+            if early:
+                self.backward_filters(g, st)
             bucketed = self.allreduce and self.exchange is None
             if bucketed:
                 # two buckets: the fc gradients are reduced over the ranks while the convolution backward (and the synthesis
