@@ -450,7 +450,25 @@ def run_ours(args):
 
     # ---- e2e: user-facing API, uint8 batch in pinned host memory, H2D + D2H inside the timed region
     cpu_gen = torch.Generator().manual_seed(4321 + rank)
-    host_u8 = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=cpu_gen).pin_memory() for _ in range(2)]
+    host_u8 = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=cpu_gen) for _ in range(2)]
+    host_kind = "pinned (torch pin_memory)"
+    if os.environ.get("DEDARK_HOST_WC", "0") == "1":
+        # experiment: write-combined pinned staging buffers (cudaHostAllocWriteCombined): the DMA engine's reads
+        # of uncached memory need no snoop of the CPU caches
+        import ctypes as _C
+        _rt = _C.CDLL("libcudart.so.12")
+        wc = []
+        for t in host_u8:
+            ptr = _C.c_void_p()
+            rc = _rt.cudaHostAlloc(_C.byref(ptr), _C.c_size_t(t.numel()), _C.c_uint(0x04))
+            assert rc == 0, f"cudaHostAlloc(write-combined) failed: {rc}"
+            buf = torch.frombuffer((_C.c_uint8 * t.numel()).from_address(ptr.value), dtype=torch.uint8).view(t.shape)
+            buf.copy_(t)
+            wc.append(buf)
+        host_u8 = wc
+        host_kind = "pinned, write-combined (cudaHostAllocWriteCombined)"
+    else:
+        host_u8 = [t.pin_memory() for t in host_u8]
     host_out = torch.empty(2, dtype=torch.float32).pin_memory()
     params = [p for p in module.parameters()]
 
@@ -639,6 +657,7 @@ def run_ours(args):
                                              "and backward launch sequences as CUDA graphs keyed by the buffers' addresses)"},
            "module_api_result_read_one_step_late": {"value": world * B * e2e_steps / e2e_lag_s, "ms_per_step": 1e3 * e2e_lag_s / e2e_steps},
            "no_dark_batch_n2": n2,
+           "host_buffers": host_kind,
            "h2d_gbs_measured": h2d_gbs, "h2d_ms_per_step_alone": B * 3 * H * W / (h2d_gbs * 1e9) * 1e3}
 
     if rank == 0:

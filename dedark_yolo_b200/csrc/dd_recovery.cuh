@@ -321,10 +321,11 @@ inline int set_smem(K kernel, size_t bytes) {
 }
 
 // Which blur engine the fp32 entry points use.  DEDARK_BLUR=tc: the tensor-core kernels (dd_blur_tc.cuh, 3xTF32) whenever the
-// rows are 16-byte aligned (W % 4 == 0); DEDARK_BLUR=cc or unset: the CUDA-core (FFMA2) kernels, which are still the faster
-// ones at fp32 precision (measured on B200, 16x3x640x640: forward 82 us vs 91 us, backward 135 us vs 260 us -- the operand
-// split of 3xTF32 costs as many CUDA-core instructions as the FFMA2 passes it replaces).  The bf16 entry points always run
-// on the tensor cores (plain TF32, no split).  Read on every call so that tests can compare the two paths in one process.
+// rows are 16-byte aligned (W % 4 == 0); DEDARK_BLUR=cc or unset: the CUDA-core (FFMA2) kernels, which are the faster ones at
+// fp32 precision (B200, 16x3x640x640, kernel time: forward 82 us vs 115 us, backward 135 us vs 256 us -- DESIGN.md section 4.5).
+// The bf16 I/O mode runs its forward on the tensor cores (plain TF32, 81 us) and its backward on the CUDA-core kernel with bf16
+// loads (151 us; 232 us on the tensor cores, which DEDARK_BLUR=tc and a requested dx still select).  Read on every call so that
+// tests can compare the engines in one process.
 inline bool blur_on_tensor_cores() {
     const char* e = getenv("DEDARK_BLUR");
     return e && e[0] == 't' && e[1] == 'c';
