@@ -204,7 +204,10 @@ __device__ __forceinline__ void hpass8(const float* __restrict__ xrow, float out
     // even window positions: the aligned input pairs E[i] = (in[2i], in[2i+1]) exactly as LDS.128 delivered them, one FFMA2
     // with an immediate tap.  Odd positions would need the shifted pairs (in[2i+1], in[2i+2]) -- two register moves each, ~80
     // moves per call once the compiler has satisfied the pair alignment -- so they are two scalar FFMAs on the halves
-    // instead: the same FMA-pipe time, a quarter fewer instructions.
+    // instead: the same FMA-pipe time, a quarter fewer instructions.  (Round 2 tried the all-FFMA2 form -- odd taps on the aligned
+    // pairs into a swapped accumulator (-> out[t+1], -> out[t]) with tap pairs (k_{m-1}, k_{m+1}) from uniform registers, 26 FFMA2
+    // per output pair and bit-identical sums: 135.3 -> 140.3 us for the backward.  These passes are bound by the FMA pipe, not by
+    // issue slots, and the packed form spends two more lane-FMAs per pair on zero taps.)
 #pragma unroll
     for (int t = 0; t < 8; t += 2) {
         u64 acc = pk(0.f, 0.f);
