@@ -632,6 +632,41 @@ def run_ours(args):
     except Exception as e:  # noqa: BLE001  (reported, not fatal: the headline does not depend on this leg)
         n2 = {"error": repr(e)}
 
+    # bf16 I/O mode (north_star "fp32/bf16 batch"): the same plain captured step with the darkened batch, y and the
+    # cotangent in bf16 (forward: 1xTF32 tensor-core blur; backward: CUDA-core kernel with bf16 loads), and its filter kernels alone
+    bf = {}
+    try:
+        pb = dd.RecoveryPipeline(module, B, H, W, dark_param=DARK_PARAM, io_dtype=torch.bfloat16, allreduce=False)
+        gb = [gs[k].bfloat16() for k in range(2)]
+        for k in range(2):
+            pb.capture(("bf", k), cleans[k], gb[k])
+        for i in range(6):
+            pb.graphs[("bf", i % 2)].replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(40):
+            pb.graphs[("bf", i % 2)].replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        bf["ms_per_step_plain"] = e0.elapsed_time(e1) / 40
+        stq = torch.cuda.current_stream(dev).cuda_stream
+        for name, fn in (("filters_fwd_us", lambda k: pb._filters_fwd(stq, None, None)), ("filters_bwd_us", lambda k: pb._filters_bwd(gb[k], stq))):
+            for i in range(3):
+                fn(i % 2)
+            e0.record()
+            for i in range(12):      # back-to-back launches: the queue stays full, host overhead does not enter
+                fn(i % 2)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            bf[name] = 1e3 * e0.elapsed_time(e1) / 12
+        nb = B * 3 * H * W * (2 + 2)   # bf16 in + bf16 out (forward); bf16 g + bf16 x (backward)
+        bf["algorithmic_bytes_per_kernel"] = nb
+        bf["frac_of_hbm_peak"] = {"filters_fwd": nb / (bf["filters_fwd_us"] * 1e-6) / 1e9 / peak, "filters_bwd": nb / (bf["filters_bwd_us"] * 1e-6) / 1e9 / peak}
+        bf["note"] = "half the bytes of the fp32 mode at about the same kernel times: the filter kernels are FMA-pipe bound, not HBM bound (DESIGN.md 4.5, 4.6)"
+        del pb
+    except Exception as e:  # noqa: BLE001
+        bf = {"error": repr(e)}
+
     # the pinned-host -> device copy alone (what bounds the overlapped pipeline): 5 copies of one batch, CUDA events
     h2d0, h2d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dev_u8 = torch.empty_like(host_u8[0], device=dev)
@@ -657,6 +692,7 @@ def run_ours(args):
                                              "and backward launch sequences as CUDA graphs keyed by the buffers' addresses)"},
            "module_api_result_read_one_step_late": {"value": world * B * e2e_steps / e2e_lag_s, "ms_per_step": 1e3 * e2e_lag_s / e2e_steps},
            "no_dark_batch_n2": n2,
+           "bf16_io_mode": bf,
            "host_buffers": host_kind,
            "h2d_gbs_measured": h2d_gbs, "h2d_ms_per_step_alone": B * 3 * H * W / (h2d_gbs * 1e9) * 1e3}
 
