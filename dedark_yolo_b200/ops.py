@@ -320,7 +320,7 @@ class _Plan:
     backward costs a handful of C-ABI calls and two allocations (y and the flat gradient) of host work.  ``version``
     counts the forwards that have written the activation buffers: a backward whose forward is no longer the latest one
     (two forwards before a backward) recomputes resize + predictor forward first -- correctness never depends on the cache."""
-    __slots__ = ("r", "acts", "feat", "dfeat", "ws_pb", "ws_rb", "version", "wkey", "w", "tick", "graphs", "seen", "cap_stream")
+    __slots__ = ("r", "acts", "feat", "dfeat", "ws_pb", "ws_rb", "version", "wkey", "w", "tick", "graphs", "seen", "cap_stream", "captures", "replays", "graphs_off")
 
     def __init__(self, dev, B, H, W):
         f32 = dict(dtype=torch.float32, device=dev)
@@ -333,6 +333,8 @@ class _Plan:
         self.wkey, self.w = None, None
         self.tick = 0
         self.graphs, self.seen, self.cap_stream = {}, {}, None   # CUDA-graph replay of the launch sequences (module.use_cuda_graphs)
+        self.captures = self.replays = 0
+        self.graphs_off = False   # set when captures do not pay off (addresses that do not recur)
 
 
 _PLANS = weakref.WeakKeyDictionary()   # module instance -> {(device index, B, H, W): _Plan}
@@ -389,11 +391,18 @@ def _launch(pl: _Plan, device, key, fn, use_graphs: bool):
     """Run ``fn()`` (a fixed sequence of C-ABI launches on the current stream) -- directly, or, with ``use_graphs``, as the replay
     of a CUDA graph captured the second time the same ``key`` (every pointer and shape the launches depend on) is seen.  One
     replay costs the host ~10 us where the 9-10 launches of a forward or backward cost ~40.  Nothing in ``fn`` allocates."""
-    if not use_graphs or torch.cuda.is_current_stream_capturing():
+    if not use_graphs or pl.graphs_off or torch.cuda.is_current_stream_capturing():
         fn()
         return
     g = pl.graphs.get(key)
     if g is None:
+        if pl.captures >= 8 and pl.replays < 2 * pl.captures:
+            # a capture costs about a millisecond; when the buffers' addresses do not recur (a caller that allocates fresh tensors
+            # from a growing pool every step) replaying never amortises it: go back to plain launches for this call shape
+            pl.graphs_off = True
+            pl.graphs.clear()
+            fn()
+            return
         n = pl.seen.get(key, 0)
         if n == 0:                                   # first sighting: plain launches (also sets the kernels' attributes)
             if len(pl.seen) > 4 * _MAX_GRAPHS:
@@ -416,6 +425,9 @@ def _launch(pl: _Plan, device, key, fn, use_graphs: bool):
                 g.capture_end()
         cur.wait_stream(pl.cap_stream)
         pl.graphs[key] = g
+        pl.captures += 1
+    else:
+        pl.replays += 1
     g.replay()
 
 
