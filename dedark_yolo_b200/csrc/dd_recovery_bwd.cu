@@ -15,6 +15,14 @@
 //   2. V adjoint pass (FFMA2) -> B^T g5 for 32 rows x 128 columns                                   -> tile BT
 //   3. pointwise: one warp per output row (float4 per lane): chain recompute, the five parameter sums in registers,
 //      the row sum S = sum_w g4 x3 (the rgb2lum quirk couples every pixel of a row to columns 0..2) by warp shuffle.
+// Reflect borders (round 2): the adjoint of the reflect-padded blur equals the PLAIN 25-tap pass over the mirror-extended cotangent
+// g^ (g^[-i] = g[i], the image-border row / column doubled) with the border outputs halved (dd_blur_tc.cuh derives it; it holds
+// when the two borders are more than one radius apart, H, W >= 14).  The g ring is completed in place right after a block's rows
+// have landed -- mirrored halo columns, doubled border column, mirrored rows above / below the image, doubled border rows, spread
+// over all 256 threads -- and both passes then run without any border code.  The previous form (zero-filled halo + the fold-back
+// gather hfold8 / vfold on the outputs within 12 of a border) put several hundred serial instructions on one or two warps of every
+// block of a border strip while the other warps waited at the barrier: 135 us against 98 us without it (profiles/r02_*), i.e. the
+// per-SM busy time ranged from 156 k to 247 k cycles.  Images with H or W = 13 keep the fold-back form.
 // Per (CTA, plane-strip) partial sums and per-row S go to the workspace; a fixed-order finalize kernel (one CTA per
 // image, no float atomics) adds them up, applies the column 0..2 fix-up and the regressor Jacobians.
 #include <cooperative_groups.h>
@@ -296,6 +304,63 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         };
         stage(0);
 
+        // ---- mirror extension of the cotangent ring (see the header) -------------------------------------------------------------
+        const bool mirror = H > kRadius + 1 && W > kRadius + 1;
+        const bool col_fix = mirror && (u.c0 == 0 || u.c0 + kStripW + kRadius > W);   // the tile holds columns < 0 or >= W
+        const int tc_last = W - 1 - u.c0 + kRadius;                                    // tile column of image column W - 1
+        float fxc[4];                                                                  // pointwise phase: this thread's four columns
+        bool edge_col = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gcol = u.c0 + 4 * (tid & 31) + i;
+            fxc[i] = (gcol == 0 || gcol == W - 1) ? 0.5f : 1.f;
+            edge_col = edge_col || gcol == 0 || gcol == W - 1;
+        }
+        auto mirror_fixup = [&](int n) {   // block n's rows are in the ring and visible to this thread's CTA
+            const int row_first = u.r0 - kRadius + n * kRB;                           // image row of the block's first ring row
+            const bool row_fix = row_first < 0 || row_first + kRB > H - 1;            // rows outside the image, or a border row
+            if (!col_fix && !row_fix) return;                                         // (CTA-uniform)
+            if (!TMA) __syncthreads();                                                // rows staged by other threads
+            if (col_fix) {   // in-image rows: 8 threads per row, 26 independent items (12 + 12 mirrored columns, 2 doubled ones)
+                const int rr = tid >> 3, jr = row_first + rr;
+                if (jr >= 0 && jr < H) {
+                    float* xr = XS + ((n * kRB + rr) % kXRingB) * kXP;
+#pragma unroll
+                    for (int k0 = 0; k0 < 32; k0 += 8) {
+                        const int k = k0 + (tid & 7);
+                        if (k < kRadius) {                                            // column -(k+1) <- column k+1   (strip 0 only)
+                            if (u.c0 == 0) xr[kRadius - 1 - k] = xr[kRadius + 1 + k];
+                        } else if (k < 2 * kRadius) {                                 // column W-1+i <- column W-1-i
+                            const int i = k - kRadius + 1, td = tc_last + i, ts = tc_last - i;
+                            if (td >= 0 && td < kXW && ts >= 0) xr[td] = xr[ts];
+                        } else if (k == 2 * kRadius) {                                // g^[0] = 2 g[0]
+                            if (u.c0 == 0) xr[kRadius] *= 2.f;
+                        } else if (k == 2 * kRadius + 1) {                            // g^[W-1] = 2 g[W-1]
+                            if (tc_last >= 0 && tc_last < kXW) xr[tc_last] *= 2.f;
+                        }
+                    }
+                }
+            }
+            if (row_fix) {   // rows above / below the image <- their mirror rows (already column-complete); border rows doubled
+                __syncthreads();
+                for (int it = tid; it < kRB * kXW4; it += kThreads) {
+                    const int rr = it / kXW4, c4 = it - rr * kXW4, jr = row_first + rr;
+                    float4* dst = reinterpret_cast<float4*>(XS + ((n * kRB + rr) % kXRingB) * kXP) + c4;
+                    if (jr < 0 || jr >= H) {
+                        const int js = jr < 0 ? -jr : 2 * (H - 1) - jr;               // reflect
+                        if (js >= 0 && js < H && (jr >= -kRadius && jr < H + kRadius)) {
+                            const int vs = js - (u.r0 - kRadius);                     // ring row of the source (an earlier or the same block)
+                            *dst = *(reinterpret_cast<const float4*>(XS + (vs % kXRingB) * kXP) + c4);
+                        }
+                    } else if (jr == 0 || jr == H - 1) {
+                        float4 v = *dst;
+                        v.x *= 2.f; v.y *= 2.f; v.z *= 2.f; v.w *= 2.f;
+                        *dst = v;
+                    }
+                }
+            }
+        };
+
         {   // per-row contrast scalars of the segment: all loads first (<= 3 rows per thread), then the arithmetic
             constexpr int kPer = (kMaxU + kThreads - 1) / kThreads;
             float x0r[kPer][3], icr[kPer][3];
@@ -345,6 +410,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                 } else {
                     cp_async_wait_all();
                 }
+                if (mirror) mirror_fixup(n);
             }
             __syncthreads();  // g block n visible; BT of block n-1 complete; the H ring rows block n overwrites are no longer read
             if (n > 0) {
@@ -360,8 +426,8 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                     const int gc = u.c0 + 4 * c4;
                     float srow = 0.f;
                     if (gc < W) {
-                        const float4 g5 = *reinterpret_cast<const float4*>(XS + (o % kXRingB) * kXP + 4 * c4 + kRadius);
-                        const float4 bt = *reinterpret_cast<const float4*>(BT + rr * kBP + 4 * c4);
+                        float4 g5 = *reinterpret_cast<const float4*>(XS + (o % kXRingB) * kXP + 4 * c4 + kRadius);
+                        float4 bt = *reinterpret_cast<const float4*>(BT + rr * kBP + 4 * c4);
                         const float m = MSm[o], q1 = MSq[o];
                         const float4 x0 = U8 ? lut4(__float_as_uint(x0p[k].x))
                                           : XB ? bf16x4_to_float4(make_uint2(__float_as_uint(x0p[k].x), __float_as_uint(x0p[k].y))) : x0p[k];
@@ -375,6 +441,11 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                         }
                         // columns beyond W - 1 (only when W % 4 != 0): g5 and bt are zero-padded there, but bt is not
                         // (it is a blur of real data), so mask their cotangents explicitly
+                        if (mirror && (edge_col || jr == 0 || jr == H - 1)) {   // border row / column: g^ was doubled there, B^T g^ is twice B^T g
+                            const float fr = (jr == 0 || jr == H - 1) ? 0.5f : 1.f;
+                            g5.x *= fr * fxc[0]; g5.y *= fr * fxc[1]; g5.z *= fr * fxc[2]; g5.w *= fr * fxc[3];
+                            bt.x *= fr * fxc[0]; bt.y *= fr * fxc[1]; bt.z *= fr * fxc[2]; bt.w *= fr * fxc[3];
+                        }
                         float4 d;
                         d.x = px_bwd<HAS_ICA, FAST>(x0.x, ic.x, g5.x, bt.x, m, q1, ck, pp, acc, srow);
                         if (ALIGNED) {  // W % 4 == 0: a float4 that starts inside the image ends inside it
@@ -414,7 +485,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                         float o[8];
                         hpass8(xrow + cb, o);
                         const int j0 = u.c0 + cb;  // global column of o[0]
-                        if (j0 <= kRadius || j0 + 7 >= W - 1 - kRadius) {  // reflect fold-back (image borders only)
+                        if (!mirror && (j0 <= kRadius || j0 + 7 >= W - 1 - kRadius)) {  // reflect fold-back (H or W = 13 only)
                             float tmp[8];
     #pragma unroll
                             for (int t = 0; t < 8; ++t) tmp[t] = o[t];
@@ -468,7 +539,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                         for (int r = 0; r < 8; ++r) {
                             const int o = o_first + r;
                             const int jr = u.r0 + o - kRadius;  // image row
-                            if (jr <= kRadius || jr >= H - 1 - kRadius) {  // reflect fold-back (top / bottom rows only)
+                            if (!mirror && (jr <= kRadius || jr >= H - 1 - kRadius)) {  // reflect fold-back (H or W = 13 only)
                                 const float2 bt = vfold(upk(bt2[r]), HS, col2, jr, u.r0, H);
                                 bt2[r] = pk(bt.x, bt.y);
                             }
