@@ -57,13 +57,17 @@ BYTES_RESIZE_TAPS = 3 * 256 * 256 * 4 * 4
 
 def load_traffic(kernel: str):
     """Measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture,
-    profiles/r01_traffic.json, written from the committed ncu summaries); None when no capture exists."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(path) as f:
-            return json.load(f)["dram_bytes_per_launch"].get(kernel)
-    except Exception:
-        return None
+    profiles/r02_traffic.json -- r01_traffic.json as second choice --, written from the committed ncu summaries); None when no
+    capture exists."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                v = json.load(f)["dram_bytes_per_launch"].get(kernel)
+            if v is not None:
+                return v
+        except Exception:
+            continue
+    return None
 
 
 def load_peaks():
