@@ -308,6 +308,9 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         const bool mirror = H > kRadius + 1 && W > kRadius + 1;
         const bool col_fix = mirror && (u.c0 == 0 || u.c0 + kStripW + kRadius > W);   // the tile holds columns < 0 or >= W
         const int tc_last = W - 1 - u.c0 + kRadius;                                    // tile column of image column W - 1
+        const int wrow = tid >> 5, lane4 = 4 * lane;                                   // pointwise phase: this thread's row offset / column chunk
+        const int gc = u.c0 + lane4;                                                   // ... and its first image column
+        const ptrdiff_t w8 = 8 * (ptrdiff_t)W;                                         // eight image rows (elements)
         float fxc[4];                                                                  // pointwise phase: this thread's four columns
         bool edge_col = false;
 #pragma unroll
@@ -414,24 +417,30 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
             }
             __syncthreads();  // g block n visible; BT of block n-1 complete; the H ring rows block n overwrites are no longer read
             if (n > 0) {
-                // pointwise phase: warp <-> output row, lane <-> float4
+                // pointwise phase: warp <-> output row, lane <-> float4.  A thread's four items of a block are rows ob, ob + 8, ob + 16,
+                // ob + 24 of one column chunk: every index is a per-block base plus a constant step (no per-item multiplications)
+                const int ob = (n - 1) * kRB - kRadius + wrow;             // virtual row of item 0
+                int ring = ob % kXRingB;                                   // ring row of item 0 (rows with ob < 0 are skipped below)
+                ring = ring < 0 ? ring + kXRingB : ring;
+                const ptrdiff_t row_off0 = (ptrdiff_t)(u.r0 + ob - kRadius) * W + gc;   // image offset of item 0 (element units)
+                float* sp_ptr = Spart + ((ptrdiff_t)u.plane * H + (u.r0 + ob - kRadius)) * sc.strips + u.strip;
     #pragma unroll
                 for (int k = 0; k < kPW4; ++k) {
-                    const int f = tid + k * kThreads;
-                    const int rr = f >> 5, c4 = f & 31;
-                    const int o = (n - 1) * kRB - kRadius + rr;
-                    const bool row_ok = o >= kRadius && o < kRadius + u.seg_len;  // warp-uniform
+                    const int rr = wrow + 8 * k;
+                    const int o = ob + 8 * k;
+                    const bool row_ok = (unsigned)(o - kRadius) < (unsigned)u.seg_len;  // warp-uniform
+                    int rk = ring + 8 * k;
+                    rk = rk >= kXRingB ? rk - kXRingB : rk;
                     if (!row_ok) continue;
                     const int jr = u.r0 + o - kRadius;
-                    const int gc = u.c0 + 4 * c4;
                     float srow = 0.f;
                     if (gc < W) {
-                        float4 g5 = *reinterpret_cast<const float4*>(XS + (o % kXRingB) * kXP + 4 * c4 + kRadius);
-                        float4 bt = *reinterpret_cast<const float4*>(BT + rr * kBP + 4 * c4);
+                        float4 g5 = *reinterpret_cast<const float4*>(XS + rk * kXP + lane4 + kRadius);
+                        float4 bt = *reinterpret_cast<const float4*>(BT + rr * kBP + lane4);
                         const float m = MSm[o], q1 = MSq[o];
                         const float4 x0 = U8 ? lut4(__float_as_uint(x0p[k].x))
                                           : XB ? bf16x4_to_float4(make_uint2(__float_as_uint(x0p[k].x), __float_as_uint(x0p[k].y))) : x0p[k];
-                        const size_t off = (size_t)jr * W + gc;
+                        const ptrdiff_t off = row_off0 + (ptrdiff_t)k * w8;
                         float4 ic = make_float4(kDefaultIcA, kDefaultIcA, kDefaultIcA, kDefaultIcA);
                         if (HAS_ICA) {
                             ic.x = __ldg(ip + off);
@@ -471,7 +480,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                         }
                     }
                     srow = warp_sum(srow);
-                    if (lane == 0) Spart[((size_t)u.plane * H + jr) * sc.strips + u.strip] = srow;
+                    if (lane == 0) sp_ptr[(ptrdiff_t)k * 8 * sc.strips] = srow;
                 }
             }
             if (have) {
@@ -502,29 +511,31 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
             __syncthreads();  // H ring rows of block n visible; BT, the g centre rows and x0p of block n-1 consumed
             if (have) {
                 if (n + 1 < u.nB) stage(n + 1);
-                // prefetch x0 for this block's output rows (issued after the H pass to keep its register footprint down; consumed after the V pass)
+                // prefetch x0 for this block's output rows (issued after the H pass to keep its register footprint down; consumed after the
+                // V pass): one 64-bit base per block, a constant step of 8 rows between the four items
+                {
+                    const int ob = n * kRB - kRadius + wrow;
+                    const ptrdiff_t off0 = (ptrdiff_t)(u.r0 + ob - kRadius) * W + gc;
     #pragma unroll
-                for (int k = 0; k < kPW4; ++k) {
-                    const int f = tid + k * kThreads;
-                    const int rr = f >> 5, c4 = f & 31;
-                    const int o = n * kRB - kRadius + rr;
-                    const int gc = u.c0 + 4 * c4;
-                    x0p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (o >= kRadius && o < kRadius + u.seg_len && gc < W) {
-                        const float* rp = xp + (size_t)(u.r0 + o - kRadius) * W + gc;
-                        if (U8) {
-                            x0p[k].x = __uint_as_float(__ldg(reinterpret_cast<const unsigned*>(xp8 + (size_t)(u.r0 + o - kRadius) * W + gc)));
-                        } else if (XB) {
-                            const uint2 q = __ldg(reinterpret_cast<const uint2*>(xpb + (size_t)(u.r0 + o - kRadius) * W + gc));
-                            x0p[k].x = __uint_as_float(q.x);
-                            x0p[k].y = __uint_as_float(q.y);
-                        } else if (ALIGNED) {
-                            x0p[k] = __ldg(reinterpret_cast<const float4*>(rp));
-                        } else {
-                            x0p[k].x = __ldg(rp);
-                            if (gc + 1 < W) x0p[k].y = __ldg(rp + 1);
-                            if (gc + 2 < W) x0p[k].z = __ldg(rp + 2);
-                            if (gc + 3 < W) x0p[k].w = __ldg(rp + 3);
+                    for (int k = 0; k < kPW4; ++k) {
+                        x0p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if ((unsigned)(ob + 8 * k - kRadius) < (unsigned)u.seg_len && gc < W) {
+                            const ptrdiff_t off = off0 + (ptrdiff_t)k * w8;
+                            if (U8) {
+                                x0p[k].x = __uint_as_float(__ldg(reinterpret_cast<const unsigned*>(xp8 + off)));
+                            } else if (XB) {
+                                const uint2 q = __ldg(reinterpret_cast<const uint2*>(xpb + off));
+                                x0p[k].x = __uint_as_float(q.x);
+                                x0p[k].y = __uint_as_float(q.y);
+                            } else if (ALIGNED) {
+                                x0p[k] = __ldg(reinterpret_cast<const float4*>(xp + off));
+                            } else {
+                                const float* rp = xp + off;
+                                x0p[k].x = __ldg(rp);
+                                if (gc + 1 < W) x0p[k].y = __ldg(rp + 1);
+                                if (gc + 2 < W) x0p[k].z = __ldg(rp + 2);
+                                if (gc + 3 < W) x0p[k].w = __ldg(rp + 3);
+                            }
                         }
                     }
                 }
