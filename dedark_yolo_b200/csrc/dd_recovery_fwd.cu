@@ -31,6 +31,12 @@ constexpr int kXP2 = 308;               // XS2 pitch (floats per row pair): 2*15
 constexpr int kHRows = kHRing + 24;     // HS rows: 64-row ring + the first 24 rows mirrored behind it
 constexpr int kStage2 = (16 * kXW4 + kThreads - 1) / kThreads;  // (row pair, float4 column) items per thread per block (3)
 constexpr int kXRP = 160;               // pitch (floats) of the TMA staging rows: 640 B, a multiple of the 128 B TMA alignment
+// "mixed" schedule (the TMA instantiation, round 2): two barriers per row-block, the pointwise stage of block n+1 shares an interval
+// with the horizontal pass of block n (half of the warps run them in the other order, so MUFU / issue-bound and FMA-bound code meet
+// in time), the vertical pass of block n has the other interval -- the structure of the backward kernel.  It needs the x4 rows of
+// block n+1 beside the centre rows the vertical pass of block n still reads: an 80-row x4 ring; the H ring gives its mirrored
+// rows back (the vertical pass walks four 8-row groups that never wrap): 20 + 49.3 + 33.8 + 2.6 KB, still two CTAs per SM.
+constexpr int kPairsM = 40;             // x4 ring of the mixed schedule, in row pairs
 
 // TMA: the raw x rows of every row-block arrive by cp.async.bulk.tensor -- two 16-row x 160-column boxes for a block inside the
 // image, one row box per (reflected) image row for the blocks at its top and bottom -- issued by warp 0 one block ahead into a
@@ -55,10 +61,14 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     const unsigned char* x8 = reinterpret_cast<const unsigned char*>(x);
     auto lut4 = [&](unsigned w) { return make_float4(s_tab[w & 255u], s_tab[(w >> 8) & 255u], s_tab[(w >> 16) & 255u], s_tab[w >> 24]); };
     extern __shared__ __align__(128) float smem[];
+    constexpr bool MIXED = TMA;                        // see kPairsM
+    constexpr int P = MIXED ? kPairsM : kPairs;        // x4 ring depth in row pairs
+    constexpr int HR = MIXED ? kHRing : kHRows;        // H ring rows (mixed: no mirrored copy behind the ring)
     float* XR = smem;                                  // [32 rows][kXRP] raw x of the block being staged (TMA only)
     float* XS2 = smem + (TMA ? kRB * kXRP : 0);
-    float* HS = XS2 + kPairs * kXP2;
-    float* MS = HS + kHRows * kHP;  // per virtual row: m = (1-c) + c*q
+    float* HS = XS2 + P * kXP2;
+    float* MS = HS + HR * kHP;  // per virtual row: m = (1-c) + c*q
+    auto xs2_row = [&](int pair) { return XS2 + (MIXED ? pair % P : (pair & (P - 1))) * kXP2; };
     __shared__ ImgParams sp;
     __shared__ __align__(8) uint64_t tma_bar;
     uint32_t tma_phase = 0;
@@ -167,12 +177,7 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 
         if (!TMA) stage(0);
 
-        for (int n = 0; n < u.nB; ++n) {
-            __syncthreads();  // MS ready (n == 0); ring slots of block n no longer read by the previous V pass
-            if (TMA) {
-                mbar_wait(&tma_bar, tma_phase);
-                tma_phase ^= 1u;
-            }
+        auto stage_compute = [&](int n) {   // raw x rows of block n (staging tile / prefetch registers) -> pointwise chain -> x4 ring
 #pragma unroll
             for (int k = 0; k < kStage2; ++k) {
                 const int f = tid + k * kThreads;
@@ -192,7 +197,7 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                         o[e][2] = chain_x3<HAS_ICA, FAST>(ck, in.z, ic.z) * m;
                         o[e][3] = chain_x3<HAS_ICA, FAST>(ck, in.w, ic.w) * m;
                     }
-                    float* xrow = XS2 + ((v0 >> 1) & (kPairs - 1)) * kXP2;  // element (row e, staged col c) at xrow[2c + e]
+                    float* xrow = xs2_row(v0 >> 1);  // element (row e, staged col c) at xrow[2c + e]
                     float4* dst = reinterpret_cast<float4*>(xrow + 8 * c4);
                     dst[0] = make_float4(o[0][0], o[1][0], o[0][1], o[1][1]);
                     dst[1] = make_float4(o[0][2], o[1][2], o[0][3], o[1][3]);
@@ -218,14 +223,13 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                     }
                 }
             }
-            if (!TMA && n + 1 < u.nB) stage(n + 1);
-            __syncthreads();
-            if (TMA && n + 1 < u.nB) stage(n + 1);  // the staging tile has been consumed by everyone
+        };
+        auto hpass = [&](int n) {
             {   // horizontal pass: thread = row pair x 8 columns; lanes 0..15 -> row pairs
                 const int rp = tid & 15, cg = tid >> 4;
                 const int v0 = n * kRB + 2 * rp;
                 u64 acc[8];
-                blur8_pairs<2>(XS2 + ((v0 >> 1) & (kPairs - 1)) * kXP2 + 16 * cg, acc);
+                blur8_pairs<2>(xs2_row(v0 >> 1) + 16 * cg, acc);
                 float lo[8], hi[8];
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
@@ -239,7 +243,7 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                 *reinterpret_cast<float4*>(h0 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
                 *reinterpret_cast<float4*>(h0 + kHP) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<float4*>(h0 + kHP + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-                if (s0 < 24) {  // mirrored copy behind the ring: a 32-row window starting at slot <= 56 never wraps
+                if (!MIXED && s0 < 24) {  // mirrored copy behind the ring: a 32-row window starting at slot <= 56 never wraps
                     float* h1 = h0 + kHRing * kHP;
                     *reinterpret_cast<float4*>(h1) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     *reinterpret_cast<float4*>(h1 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
@@ -247,13 +251,15 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                     *reinterpret_cast<float4*>(h1 + kHP + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
                 }
             }
-            __syncthreads();
+        };
+        auto vpass = [&](int n) {
             {   // vertical pass + USM epilogue: lanes -> column pairs, 8 rows per thread
                 const int col2 = 2 * (tid & 63), rg = tid >> 6;
                 const int o_first = n * kRB - kRadius + 8 * rg;  // virtual row of the first output (even)
                 if (o_first >= kRadius && o_first < kRadius + u.seg_len) {
                     u64 bl[8];
-                    blur8_pairs<kHP>(HS + ((o_first - kRadius) & (kHRing - 1)) * kHP + col2, bl);
+                    if (MIXED) vpass8x2(HS, (o_first - kRadius) & (kHRing - 1), col2, bl);   // four 8-row groups, no mirrored rows
+                    else blur8_pairs<kHP>(HS + ((o_first - kRadius) & (kHRing - 1)) * kHP + col2, bl);
                     const int gc = u.c0 + col2;
                     if (gc < W) {
                         const u64 p2 = pk(pp, pp), m1 = pk(-1.f, -1.f);
@@ -262,8 +268,7 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 #pragma unroll
                         for (int r = 0; r < 8; r += 2) {
                             // centre x4 of rows (o, o+1), columns (c, c+1): one LDS.128 from the interleaved ring
-                            const float4 c4v = *reinterpret_cast<const float4*>(
-                                XS2 + (((o_first + r) >> 1) & (kPairs - 1)) * kXP2 + 2 * (col2 + kRadius));
+                            const float4 c4v = *reinterpret_cast<const float4*>(xs2_row((o_first + r) >> 1) + 2 * (col2 + kRadius));
                             const u64 xa = pk(c4v.x, c4v.z), xb = pk(c4v.y, c4v.w);
                             const u64 ya = fma2(fma2(bl[r], m1, xa), p2, xa);      // (x4 - blur) * p + x4
                             const u64 yb = fma2(fma2(bl[r + 1], m1, xb), p2, xb);
@@ -285,12 +290,52 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                     }
                 }
             }
+        };
+
+        if (MIXED) {
+            // two barriers per row-block: [H pass of block n | stage of block n+1] , [V pass of block n]
+            __syncthreads();                       // MS ready; the rings of the previous segment are no longer read
+            mbar_wait(&tma_bar, tma_phase);        // block 0's rows (requested before the per-row scalars)
+            tma_phase ^= 1u;
+            stage_compute(0);
+            __syncthreads();                       // x4 rows of block 0 visible, staging tile consumed
+            if (u.nB > 1) stage(1);
+            const bool stage_first = (tid >> 7) & 1;   // warps 4..7 stage first, warps 0..3 blur first: one of each on every scheduler (warp % 4)
+            for (int n = 0; n < u.nB; ++n) {
+                const bool more = n + 1 < u.nB;
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    if ((pass == 0) == stage_first) {
+                        if (more) {
+                            mbar_wait(&tma_bar, tma_phase);
+                            tma_phase ^= 1u;
+                            stage_compute(n + 1);
+                        }
+                    } else {
+                        hpass(n);
+                    }
+                }
+                __syncthreads();                   // H rows of block n and x4 rows of block n+1 visible; staging tile consumed
+                if (n + 2 < u.nB) stage(n + 2);
+                vpass(n);
+                __syncthreads();                   // the centre rows block n+2's stage overwrites and the H rows block n+1 overwrites are free
+            }
+        } else {
+            for (int n = 0; n < u.nB; ++n) {
+                __syncthreads();  // MS ready (n == 0); ring slots of block n no longer read by the previous V pass
+                stage_compute(n);
+                if (n + 1 < u.nB) stage(n + 1);
+                __syncthreads();
+                hpass(n);
+                __syncthreads();
+                vpass(n);
+            }
         }
     }
 }
 
 constexpr size_t kFwdSmem = (size_t)(kPairs * kXP2 + kHRows * kHP + kMaxU) * sizeof(float);
-constexpr size_t kFwdSmemTma = kFwdSmem + (size_t)kRB * kXRP * sizeof(float);
+constexpr size_t kFwdSmemTma = (size_t)(kRB * kXRP + kPairsM * kXP2 + kHRing * kHP + kMaxU) * sizeof(float);   // mixed schedule (kPairsM)
 
 template <bool HAS_ICA, bool FAST, bool ALIGNED, bool TMA>
 static int launch_fwd4(const CUtensorMap& xmap, const CUtensorMap& xmap16, const float* x, const float* A, const float* IcA, const float* feat, float* y, int B,

@@ -21,9 +21,18 @@ pipe.prime(cleans[0])
 for i in range(6):
     pipe.step_overlapped(cleans[(i + 1) % 4], gs[i % 4])
 torch.cuda.synchronize()
+GRAPH = os.environ.get("GRAPH") == "1"   # plain steps as CUDA-graph replays: the gaps between the kernels of a captured step
+if GRAPH:
+    for k in range(4):
+        pipe.capture(k, cleans[k], gs[k])
+    for i in range(8):
+        pipe.replay(i % 4)
+    torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for i in range(6, 9):
-        if PLAIN:
+        if GRAPH:
+            pipe.replay(i % 4)
+        elif PLAIN:
             pipe.step(cleans[i % 4], gs[i % 4])
         else:
             pipe.step_overlapped(cleans[(i + 1) % 4], gs[i % 4])
@@ -31,5 +40,9 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
 t0 = evs[0].time_range.start
+prev_end = None
 for e in evs:
+    gap = "" if prev_end is None else f" gap {e.time_range.start - prev_end:6.1f}"
+    prev_end = max(prev_end or 0, e.time_range.end)
+    print(gap, end=" ")
     print(f"{e.time_range.start - t0:9.1f} +{e.time_range.end - e.time_range.start:7.1f} us  stream? {getattr(e, 'device_resource_id', '?')!s:4}  {e.name[:70]}")
