@@ -547,3 +547,28 @@ def test_synth_resize_fused_equals_separate_passes(ops, shape, dtype):
     rec64 = float(torch.nn.functional.mse_loss(dark_b.double(), clean64))
     assert abs(float(rec_b) - rec64) <= 1e-6 * rec64 and abs(float(rec_a) - rec64) <= 1e-6 * rec64
     assert not ops.synth_resize_supported(640, 641)  # W % 4 != 0 stays on the two-pass path
+
+
+# ---- reflect borders of the backward by mirror extension: shapes where both borders share a block / strip -----
+@pytest.mark.parametrize("B,H,W", [(2, 14, 14), (1, 14, 40), (2, 20, 24), (1, 31, 33), (2, 45, 140), (1, 70, 132), (1, 33, 300), (1, 160, 156),
+                                   (1, 13, 40), (1, 40, 13)])
+def test_backward_border_shapes_vs_fp64_oracle(dd, ops, B, H, W):
+    """Every combination the mirror extension distinguishes: top and bottom mirror rows in one block (H < 32), left and right
+    mirror columns in one strip (W < 128), a strip whose right halo lies outside the image (W = 132, 140), the TMA path
+    (W >= 156), unaligned widths (register staging), and 13-pixel images, which keep the fold-back form.  dfeat and dx against
+    the fp64 oracle (autograd through the reflect-padded dense-equivalent blur)."""
+    gen = torch.Generator().manual_seed(100 * H + W)
+    x = torch.rand(B, 3, H, W, generator=gen)
+    g = torch.randn(B, 3, H, W, generator=gen)
+    feat = torch.randn(B, 15, generator=gen) * 0.8
+    x64 = x.double().requires_grad_(True)
+    f64 = feat.double().requires_grad_(True)
+    y64 = O.filter_chain(x64, f64, dense_blur=False)
+    y64.backward(g.double())
+    y = ops.filters_forward(x.cuda(), feat.cuda())
+    dfeat, dx = ops.filters_backward(x.cuda(), feat.cuda(), g.cuda(), need_dx=True)
+    report(f"border fwd {H}x{W}", y, y64, FWD_TOL)
+    report(f"border dfeat {H}x{W}", dfeat, f64.grad, GRAD_TOL)
+    report(f"border dx {H}x{W}", dx, x64.grad, 2 * GRAD_TOL)
+    d2, dx2 = ops.filters_backward(x.cuda(), feat.cuda(), g.cuda(), need_dx=True)
+    assert torch.equal(dfeat, d2) and torch.equal(dx, dx2), "backward must be bit-reproducible"
