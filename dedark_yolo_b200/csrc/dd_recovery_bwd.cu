@@ -210,16 +210,32 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         if (cur_ps >= 0 && u.ps != cur_ps) flush();
         cur_ps = u.ps;
         __syncthreads();
-        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
-        __syncthreads();
-        const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
-        const float pc = sp.c, pp = sp.p;
         const float* xp = x + (size_t)u.plane * H * W;
         const unsigned char* xp8 = x8 + (size_t)u.plane * H * W;
         const unsigned short* xpb = xb + (size_t)u.plane * H * W;
         const unsigned short* gpb = gb + (size_t)u.plane * H * W;
         const float* gp = g + (size_t)u.plane * H * W;
         const float* ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
+        // columns 0..2 of every row of the segment (the per-row contrast scalars below): requested before the regressors are
+        // evaluated -- they do not depend on them, and one warp's tanhf / expf calls then run in the shadow of these loads
+        constexpr int kPer = (kMaxU + kThreads - 1) / kThreads;
+        float x0r[kPer][3], icr[kPer][3];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int v = tid + k * kThreads, row = u.r0 - kRadius + v;
+            if (v < u.nU && row >= 0 && row < H) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    x0r[k][c] = U8 ? s_tab[__ldg(xp8 + (size_t)row * W + c)]
+                                   : XB ? __uint_as_float((unsigned)__ldg(xpb + (size_t)row * W + c) << 16) : __ldg(xp + (size_t)row * W + c);
+                    icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
+                }
+            }
+        }
+        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
+        __syncthreads();
+        const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
+        const float pc = sp.c, pp = sp.p;
 
         // g block n -> ring XS (rows outside the image and columns outside [0, W) are zero)
         uint2 gpre[GB ? kStage4 : 1];   // GB: the bf16 rows of the next block, in flight between stage(n) and stage_commit(n)
@@ -364,21 +380,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
             }
         };
 
-        {   // per-row contrast scalars of the segment: all loads first (<= 3 rows per thread), then the arithmetic
-            constexpr int kPer = (kMaxU + kThreads - 1) / kThreads;
-            float x0r[kPer][3], icr[kPer][3];
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) {
-                const int v = tid + k * kThreads, row = u.r0 - kRadius + v;
-                if (v < u.nU && row >= 0 && row < H) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        x0r[k][c] = U8 ? s_tab[__ldg(xp8 + (size_t)row * W + c)]
-                                       : XB ? __uint_as_float((unsigned)__ldg(xpb + (size_t)row * W + c) << 16) : __ldg(xp + (size_t)row * W + c);
-                        icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
-                    }
-                }
-            }
+        {   // per-row contrast scalars of the segment (the rows' first three columns were loaded at the top of the segment)
 #pragma unroll
             for (int k = 0; k < kPer; ++k) {
                 const int v = tid + k * kThreads, row = u.r0 - kRadius + v;

@@ -90,14 +90,29 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         const Seg u = next_seg(blk, blk_end, sc, H);
         blk += seg_blocks(u);
         __syncthreads();  // previous segment fully consumed (rings, MS, sp)
-        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
-        __syncthreads();
-        const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
-        const float pc = sp.c, pp = sp.p;
         const float* xp = x + (size_t)u.plane * H * W;
         const unsigned char* xp8 = x8 + (size_t)u.plane * H * W;
         const float* ip = HAS_ICA ? IcA + (size_t)u.b * H * W : nullptr;
         float* yp = y + (size_t)u.plane * H * W;
+        // columns 0..2 of every row of the segment (per-row contrast scalars): requested before the regressors are evaluated
+        constexpr int kPer = (kMaxU + kThreads - 1) / kThreads;
+        float x0r[kPer][3], icr[kPer][3];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int v = tid + k * kThreads;
+            if (v < u.nU) {
+                const int row = reflect(u.r0 - kRadius + v, H);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    x0r[k][c] = U8 ? s_tab[__ldg(xp8 + (size_t)row * W + c)] : __ldg(xp + (size_t)row * W + c);
+                    icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
+                }
+            }
+        }
+        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
+        __syncthreads();
+        const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
+        const float pc = sp.c, pp = sp.p;
 
         // item (k) of a thread: row pair rp (2 rows) x float4 column c4; fixed across blocks
         float4 pre[kStage2][2], prei[kStage2][2];
@@ -147,21 +162,7 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             }
         };
         if (TMA) stage(0);  // the first block's rows fly while the per-row scalars below are computed
-        {   // per-row contrast scalars of the segment: all loads first (<= 3 rows per thread), then the arithmetic
-            constexpr int kPer = (kMaxU + kThreads - 1) / kThreads;
-            float x0r[kPer][3], icr[kPer][3];
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) {
-                const int v = tid + k * kThreads;
-                if (v < u.nU) {
-                    const int row = reflect(u.r0 - kRadius + v, H);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        x0r[k][c] = U8 ? s_tab[__ldg(xp8 + (size_t)row * W + c)] : __ldg(xp + (size_t)row * W + c);
-                        icr[k][c] = HAS_ICA ? __ldg(ip + (size_t)row * W + c) : kDefaultIcA;
-                    }
-                }
-            }
+        {   // per-row contrast scalars of the segment (the rows' first three columns were loaded at the top of the segment)
 #pragma unroll
             for (int k = 0; k < kPer; ++k) {
                 const int v = tid + k * kThreads;
