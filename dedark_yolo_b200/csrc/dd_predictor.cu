@@ -19,6 +19,7 @@
 #include "dd_conv_tc.cuh"
 #include "dd_conv_tiled.cuh"
 #include "dd_layout.cuh"
+#include "dd_predictor_tail.cuh"
 
 namespace dd {
 
@@ -425,6 +426,15 @@ extern "C" int dd_predictor_fwd(const float* r, const dd_predictor_tensors* w, f
     }
     if (int e = launch_tc_fwd<16, 32, 128>(a[0], prep + pred_prep_offset(1), w->conv_b[1], a[1], B, st)) return e;
     if (int e = launch_tc_fwd<32, 32, 64>(a[1], prep + pred_prep_offset(2), w->conv_b[2], a[2], B, st)) return e;
+    if (tail_fused()) {  // experiment: conv4, conv5, fc1, fc2 of one image per cluster of 8 CTAs (dd_predictor_tail.cuh)
+        static const cudaError_t attr = cudaFuncSetAttribute(predictor_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmem);
+        DD_REQUIRE(attr == cudaSuccess, DD_ERR_CUDA, "dd_predictor_fwd: shared memory opt-in failed: %s", cudaGetErrorString(attr));
+        launch_pdl_cluster(predictor_tail_kernel, dim3(B * kTailCluster), dim3(256), kTailSmem, st, kTailCluster, (const float*)a[2],
+                           (const float*)w->conv_w[3], (const float*)w->conv_b[3], (const float*)w->conv_w[4], (const float*)w->conv_b[4],
+                           (const float*)w->fc1_w, (const float*)w->fc1_b, (const float*)w->fc2_w, (const float*)w->fc2_b, a[3], a[4], a[5], feat);
+        count_launch();
+        return check_launch("dd_predictor_fwd");
+    }
     if (int e = launch_tc_fwd<32, 32, 32>(a[2], prep + pred_prep_offset(3), w->conv_b[3], a[3], B, st)) return e;
     if (int e = launch_tc_fwd<32, 32, 16>(a[3], prep + pred_prep_offset(4), w->conv_b[4], a[4], B, st)) return e;
     launch_pdl_cluster(fc_fwd_kernel, dim3(B * kFcCluster), dim3(256), 0, st, kFcCluster, (const float*)a[4], (const float*)w->fc1_w, (const float*)w->fc1_b,
