@@ -164,51 +164,79 @@ conv_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, c
 // fully connected layers
 // -------------------------------------------------------------------------------------------------
 // fc1 + fc2 of one image per CLUSTER of 4 CTAs: CTA r computes h[b][16r .. 16r+15] = leaky(flat[b] . W1[o] + b1[o])
-// (warp w: outputs 16r+2w, 16r+2w+1; all 32 weight loads of a lane in flight at once), the four quarters meet through
-// distributed shared memory, and CTA 0 finishes feat[b][j] = h[b] . W2[j] + b2[j].
+// (warp w: outputs 16r+2w, 16r+2w+1; all weight loads of a lane in flight at once, requested BEFORE the grid dependency is
+// resolved -- the weights are parameters, no kernel of this library writes them), every CTA stores its quarter straight into
+// CTA 0's shared memory (distributed shared memory), and CTA 0 finishes feat[b][j] = h[b] . W2[j] + b2[j] with 16 lanes per
+// output (W2 staged in shared memory before the wait as well).  In the stream this kernel is pure latency: the serial
+// 64-load fc2 loop and a second cluster barrier of the first version cost 5 of its 9 us.
 constexpr int kFcCluster = 4;
+// A COHERENT ld.global in a volatile asm stays where it is written relative to griddepcontrol.wait.  ld.global.nc does not: ptxas
+// reschedules it freely in BOTH directions (__ldg builtin and inline PTX alike).  When this kernel first read its weights
+// before the wait and the producer's data behind it, both with __ldg, the producer's loads were hoisted ABOVE the wait -- a
+// stale read.  Rule (checked on the SASS of every kernel by tests/test_sass_pdl.py): no global access in front of ACQBULK,
+// except here, where weights are read with ldg_pinned and the producer's data with __ldcg (ld.global.cg, never hoisted).
+__device__ __forceinline__ float4 ldg_pinned(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
 __global__ void __launch_bounds__(256)
 fc_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w1, const float* __restrict__ b1,
               const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ h, float* __restrict__ feat) {
-    pdl_begin();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int PER_CTA = kFc1Out / kFcCluster;  // 16
-    __shared__ float s_h[PER_CTA];
-    __shared__ float s_all[kFc1Out];
+    constexpr int NV = kFc1In / 128;               // float4 per lane and row
+    __shared__ __align__(16) float s_all[kFc1Out];
+    __shared__ __align__(16) float s_w2[kFeat * kFc1Out];
     const int b = blockIdx.x / kFcCluster, r = (int)cluster.block_rank(), lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const float4* f = reinterpret_cast<const float4*>(flat + (size_t)b * kFc1In);
     const int o0 = r * PER_CTA + 2 * wid;
-    const float4* wa = reinterpret_cast<const float4*>(w1 + (size_t)o0 * kFc1In);
-    const float4* wb = wa + kFc1In / 4;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // first half of a split cluster barrier: CTA 0 must have started before a peer stores into its shared memory; the wait
+    // (below, in front of those stores) is free by then
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    float4 c0[NV], c1[NV];
+    {
+        const float4* wa = reinterpret_cast<const float4*>(w1 + (size_t)o0 * kFc1In);
+        const float4* wb = wa + kFc1In / 4;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { c0[i] = ldg_pinned(wa + lane + 32 * i); c1[i] = ldg_pinned(wb + lane + 32 * i); }
+    }
+    const float bias0 = __ldg(b1 + o0), bias1 = __ldg(b1 + o0 + 1);
+    if (r == 0 && threadIdx.x < kFeat * kFc1Out / 4)
+        reinterpret_cast<float4*>(s_w2)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(w2) + threadIdx.x);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const float4* f = reinterpret_cast<const float4*>(flat + (size_t)b * kFc1In);
+    float4 x[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) x[i] = __ldcg(f + lane + 32 * i);   // NOT __ldg: the compiler hoists ld.global.nc above the wait
     float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kFc1In / 128; ++i) {
-        const float4 x = __ldg(f + lane + 32 * i), c0 = __ldg(wa + lane + 32 * i), c1 = __ldg(wb + lane + 32 * i);
-        acc0 = fmaf(x.x, c0.x, acc0); acc0 = fmaf(x.y, c0.y, acc0); acc0 = fmaf(x.z, c0.z, acc0); acc0 = fmaf(x.w, c0.w, acc0);
-        acc1 = fmaf(x.x, c1.x, acc1); acc1 = fmaf(x.y, c1.y, acc1); acc1 = fmaf(x.z, c1.z, acc1); acc1 = fmaf(x.w, c1.w, acc1);
+    for (int i = 0; i < NV; ++i) {
+        acc0 = fmaf(x[i].x, c0[i].x, acc0); acc0 = fmaf(x[i].y, c0[i].y, acc0); acc0 = fmaf(x[i].z, c0[i].z, acc0); acc0 = fmaf(x[i].w, c0[i].w, acc0);
+        acc1 = fmaf(x[i].x, c1[i].x, acc1); acc1 = fmaf(x[i].y, c1[i].y, acc1); acc1 = fmaf(x[i].z, c1[i].z, acc1); acc1 = fmaf(x[i].w, c1[i].w, acc1);
     }
     acc0 = warp_sum(acc0);
     acc1 = warp_sum(acc1);
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
     if (lane == 0) {
-        const float v0 = leaky(acc0 + __ldg(b1 + o0)), v1 = leaky(acc1 + __ldg(b1 + o0 + 1));
-        s_h[2 * wid] = v0;
-        s_h[2 * wid + 1] = v1;
+        const float v0 = leaky(acc0 + bias0), v1 = leaky(acc1 + bias1);
+        float* dst = cluster.map_shared_rank(s_all, 0);   // CTA 0's copy
+        dst[o0] = v0;
+        dst[o0 + 1] = v1;
         h[b * kFc1Out + o0] = v0;
         h[b * kFc1Out + o0 + 1] = v1;
     }
-    cluster.sync();
+    cluster.sync();   // the only barrier: the peers' stores into CTA 0 are complete and visible; nobody reads the peers' memory
     if (r == 0) {
-        if (threadIdx.x < kFc1Out) s_all[threadIdx.x] = cluster.map_shared_rank(s_h, threadIdx.x / PER_CTA)[threadIdx.x % PER_CTA];
-        __syncthreads();
-        if (threadIdx.x < kFeat) {
-            const int j = threadIdx.x;
-            float acc = 0.f;
-            for (int o = 0; o < kFc1Out; ++o) acc = fmaf(s_all[o], __ldg(w2 + j * kFc1Out + o), acc);
-            feat[b * kFeat + j] = acc + __ldg(b2 + j);
-        }
+        const int j = threadIdx.x >> 4, p = threadIdx.x & 15;   // 16 lanes per output, 4 products each, xor-tree in a fixed order
+        const int jj = j < kFeat ? j : kFeat - 1;               // (the 16th group only keeps the shuffles full-warp)
+        const float4 hv = reinterpret_cast<const float4*>(s_all)[p], wv = reinterpret_cast<const float4*>(s_w2)[jj * 16 + p];
+        float acc = fmaf(hv.w, wv.w, fmaf(hv.z, wv.z, fmaf(hv.y, wv.y, hv.x * wv.x)));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (p == 0 && j < kFeat) feat[b * kFeat + j] = acc + __ldg(b2 + j);
     }
-    cluster.sync();  // keep the peers' shared memory alive until CTA 0 has read it
 }
 
 // The whole FC backward in ONE launch.  dhpre[b][o] = leaky'(h[b][o]) * sum_j dfeat[b][j] W2[j][o] is so cheap (15 MACs)
@@ -239,9 +267,16 @@ fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, cons
                 s_dh[tid] = leaky_grad(__ldg(h + b * kFc1Out + o), v);
             }
             __syncthreads();
-            for (int bb = 0; bb < nb; ++bb) {
-                acc = fmaf(s_dh[bb], __ldg(flat + (size_t)(b0 + bb) * kFc1In + i), acc);
-                bsum += s_dh[bb];
+            for (int c0 = 0; c0 < nb; c0 += 16) {   // 16 loads in flight, then the same serial FMA order (zeros pad the tail)
+                float fv[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) fv[k] = c0 + k < nb ? __ldg(flat + (size_t)(b0 + c0 + k) * kFc1In + i) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float d = c0 + k < nb ? s_dh[c0 + k] : 0.f;
+                    acc = fmaf(d, fv[k], acc);
+                    bsum += d;
+                }
             }
             __syncthreads();
         }
@@ -262,14 +297,27 @@ fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, cons
         __syncthreads();
         if (b >= B) return;
         float acc = 0.f;
-#pragma unroll 8
-        for (int o = 0; o < kFc1Out; ++o) acc = fmaf(s_dh[o], __ldg(w1 + (size_t)o * kFc1In + i), acc);
+        float wv[kFc1Out];   // all 64 weight loads of the column in flight at once
+#pragma unroll
+        for (int o = 0; o < kFc1Out; ++o) wv[o] = __ldg(w1 + (size_t)o * kFc1In + i);
+#pragma unroll
+        for (int o = 0; o < kFc1Out; ++o) acc = fmaf(s_dh[o], wv[o], acc);
         dpre5[t] = leaky_grad(flat[t], acc);
     } else {
         for (int t = tid; t < kFeat * kFc1Out; t += 256) {
             const int j = t / kFc1Out, o = t % kFc1Out;
             float acc = 0.f;
-            for (int b = 0; b < B; ++b) acc = fmaf(__ldg(dfeat + b * kFeat + j), __ldg(h + b * kFc1Out + o), acc);
+            for (int b0 = 0; b0 < B; b0 += 16) {   // 32 loads in flight, then the same serial FMA order
+                float dv[16], hv[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const bool ok = b0 + k < B;
+                    dv[k] = ok ? __ldg(dfeat + (b0 + k) * kFeat + j) : 0.f;
+                    hv[k] = ok ? __ldg(h + (b0 + k) * kFc1Out + o) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc = fmaf(dv[k], hv[k], acc);
+            }
             dw2[t] = acc;
             if (px.world > 1) push_grad(px, tag, kGradOffFc2W + t, acc);
         }

@@ -87,7 +87,7 @@ predictor_tail_kernel(const float* __restrict__ a2, const float* __restrict__ w4
         for (int i = tid; i < 32 * 5 * 8; i += 256) {
             const int c4 = i & 7, t = i >> 3, lr = t % 5, ci = t / 5, row = 4 * q - 1 + lr;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row >= 0) v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)ci * 32 + row) * 32) + c4);
+            if (row >= 0) v = __ldcg(reinterpret_cast<const float4*>(src + ((size_t)ci * 32 + row) * 32) + c4);  // producer data: never __ldg behind a wait
             float* d = s_in + (ci * 5 + lr) * kTailInP + 1 + 4 * c4;
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }

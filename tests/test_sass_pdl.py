@@ -1,0 +1,53 @@
+"""Static check of the built library: programmatic dependent launch is only safe when NO global-memory access of a kernel is
+scheduled in front of its griddepcontrol.wait (SASS: ACQBULK).  The source puts pdl_begin() first in every kernel, but ptxas is
+free to move non-coherent loads (ld.global.nc / __ldg) across the wait -- it did, once (dd_predictor.cu, fc_fwd_kernel) -- so the
+rule is checked on the machine code.  Two kernels read PARAMETERS ahead of the wait on purpose (no kernel of the library writes
+them): there every load in front of the wait must be a weight load, and the producer's data is read with ld.global.cg behind it.
+"""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from dedark_yolo_b200 import _lib
+
+ALLOWED_EARLY = {   # kernel-name fragment -> SASS opcodes allowed in front of ACQBULK
+    "fc_fwd_kernel": {"LDG.E.128", "LDG.E.128.CONSTANT"},
+    "predictor_tail_kernel": {"LDG.E.CONSTANT"},
+}
+GLOBAL_OP = re.compile(r"\*/\s+(?:@!?U?P\d+\s+)?((?:LDG|LD\.E|LDGSTS|UTMALDG|UBLKCP|ATOMG|ATOM\.|RED\.|REDG|STG|ST\.E|UTMASTG)\S*)")
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not installed")
+def test_no_global_access_in_front_of_griddepcontrol_wait():
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    kernels, fn = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            kernels[fn] = {"wait": False, "early": []}
+            continue
+        if fn is None:
+            continue
+        k = kernels[fn]
+        if "ACQBULK" in line:
+            k["wait"] = True
+        elif not k["wait"]:
+            g = GLOBAL_OP.search(line)
+            if g:
+                k["early"].append(g.group(1).rstrip(";"))
+    assert len(kernels) > 50
+    bad = {}
+    for name, k in kernels.items():
+        assert k["wait"], f"{name}: no griddepcontrol.wait (every kernel of the library starts with pdl_begin)"
+        allowed = next((ops for frag, ops in ALLOWED_EARLY.items() if frag in name), set())
+        extra = [op for op in k["early"] if op not in allowed]
+        if extra:
+            bad[name] = sorted(set(extra))
+    assert not bad, f"global-memory access scheduled in front of griddepcontrol.wait: {bad}"
+    # the two exceptions read the producer's data with ld.global.cg (STRONG.GPU in SASS), which is never hoisted
+    for frag in ALLOWED_EARLY:
+        names = [n for n in kernels if frag in n]
+        assert names, frag
