@@ -267,16 +267,9 @@ fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, cons
                 s_dh[tid] = leaky_grad(__ldg(h + b * kFc1Out + o), v);
             }
             __syncthreads();
-            for (int c0 = 0; c0 < nb; c0 += 16) {   // 16 loads in flight, then the same serial FMA order (zeros pad the tail)
-                float fv[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) fv[k] = c0 + k < nb ? __ldg(flat + (size_t)(b0 + c0 + k) * kFc1In + i) : 0.f;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float d = c0 + k < nb ? s_dh[c0 + k] : 0.f;
-                    acc = fmaf(d, fv[k], acc);
-                    bsum += d;
-                }
+            for (int bb = 0; bb < nb; ++bb) {
+                acc = fmaf(s_dh[bb], __ldg(flat + (size_t)(b0 + bb) * kFc1In + i), acc);
+                bsum += s_dh[bb];
             }
             __syncthreads();
         }
@@ -297,27 +290,14 @@ fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, cons
         __syncthreads();
         if (b >= B) return;
         float acc = 0.f;
-        float wv[kFc1Out];   // all 64 weight loads of the column in flight at once
-#pragma unroll
-        for (int o = 0; o < kFc1Out; ++o) wv[o] = __ldg(w1 + (size_t)o * kFc1In + i);
-#pragma unroll
-        for (int o = 0; o < kFc1Out; ++o) acc = fmaf(s_dh[o], wv[o], acc);
+#pragma unroll 8
+        for (int o = 0; o < kFc1Out; ++o) acc = fmaf(s_dh[o], __ldg(w1 + (size_t)o * kFc1In + i), acc);
         dpre5[t] = leaky_grad(flat[t], acc);
     } else {
         for (int t = tid; t < kFeat * kFc1Out; t += 256) {
             const int j = t / kFc1Out, o = t % kFc1Out;
             float acc = 0.f;
-            for (int b0 = 0; b0 < B; b0 += 16) {   // 32 loads in flight, then the same serial FMA order
-                float dv[16], hv[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const bool ok = b0 + k < B;
-                    dv[k] = ok ? __ldg(dfeat + (b0 + k) * kFeat + j) : 0.f;
-                    hv[k] = ok ? __ldg(h + (b0 + k) * kFc1Out + o) : 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < 16; ++k) acc = fmaf(dv[k], hv[k], acc);
-            }
+            for (int b = 0; b < B; ++b) acc = fmaf(__ldg(dfeat + b * kFeat + j), __ldg(h + b * kFc1Out + o), acc);
             dw2[t] = acc;
             if (px.world > 1) push_grad(px, tag, kGradOffFc2W + t, acc);
         }

@@ -29,3 +29,30 @@ for mode in ("fused", "tc", "fused", "tc"):  # DEDARK_TAIL: "fused" = the experi
     out[mode] = feat.clone()
     print(f"tail {mode}: predictor fwd median {ts[len(ts)//2]:.1f} us (best {ts[0]:.1f})", flush=True)
 print("max |feat fused - feat tc| =", (out["fused"] - out["tc"]).abs().max().item())
+
+# ---- the predictor backward (all launches of dd_predictor_bwd): 12 calls captured in one CUDA graph (no host time between them)
+os.environ.pop("DEDARK_TAIL", None)
+feat, acts = ops.predictor_forward(r, params)
+dfeat = torch.randn(B, 15, device="cuda")
+flat = torch.empty(sum(p.numel() for p in params), device="cuda")
+side = torch.cuda.Stream()
+with torch.cuda.stream(side):
+    for _ in range(3):
+        ops.predictor_backward(r, params, acts, dfeat, flat_grad=flat)
+    side.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for _ in range(12):
+            ops.predictor_backward(r, params, acts, dfeat, flat_grad=flat)
+    for _ in range(3):
+        g.replay()
+    side.synchronize()
+    ts = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(side)
+        g.replay()
+        b.record(side); b.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3 / 12)
+ts.sort()
+print(f"predictor bwd (graph of 12) median {ts[len(ts)//2]:.1f} us (best {ts[0]:.1f})", flush=True)
