@@ -95,6 +95,13 @@ __device__ __forceinline__ void pdl_begin() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The two halves separately, for kernels whose prologue touches no global memory (barrier initialisation, TMEM allocation, the
+// first __syncthreads): pdl_launch(); prologue; pdl_wait(); -- the prologue then runs while the predecessor is still working.
+// Kernels that allocate TMEM call pdl_launch() AFTER the allocation: a dependent CTA that shares the SM must not be able to take
+// the columns first (it would hold them while waiting for this grid, which waits for the columns).
+// tests/test_sass_pdl.py checks on the SASS that no global access ends up in front of the wait.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};

@@ -139,7 +139,6 @@ template <int CIN, int COUT, int HIN>
 __global__ void __launch_bounds__(288, 1)
 conv_tc_fwd(const float* __restrict__ in, const float* __restrict__ wprep, const float* __restrict__ bias,
             float* __restrict__ out, int total_px) {
-    pdl_begin();
     constexpr int HO = HIN / 2, NST = CIN / 8;
     constexpr int B_STAGE = 18 * 2 * COUT * 4;      // floats: [18 slots][hi rows | lo rows][4]
     constexpr uint32_t TMEM_COLS = 512, A_COL0 = 64, A_BUF = 144, A_LO = 72;
@@ -162,6 +161,8 @@ conv_tc_fwd(const float* __restrict__ in, const float* __restrict__ wprep, const
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    pdl_launch();   // after the TMEM allocation (dd_common.cuh); everything above ran beside the predecessor
+    pdl_wait();
     const uint32_t tmem = ctl.tmem_base;
     DD_TC_STAMP(1);
 
@@ -670,7 +671,6 @@ template <int CIN, int COUT, int HIN>
 __global__ void __launch_bounds__(288, 1)
 conv_tc_bwd(const float* __restrict__ in, const float* __restrict__ dpre, const float* __restrict__ wprep_dgrad,
             const float* __restrict__ act_in, float* __restrict__ partial, float* __restrict__ din, int n_w, int total_px) {
-    pdl_begin();
     extern __shared__ __align__(128) float smem_tc[];
     __shared__ BwdCtl ctl;
     const int t = threadIdx.x, warp = t >> 5;
@@ -687,6 +687,8 @@ conv_tc_bwd(const float* __restrict__ in, const float* __restrict__ dpre, const 
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    pdl_launch();   // after the TMEM allocation (dd_common.cuh)
+    pdl_wait();
     if ((int)blockIdx.x < n_w)
         conv_tc_wgrad_body<CIN, COUT, HIN>(blockIdx.x, n_w, in, dpre, partial, total_px, smem_tc, &ctl);
     else

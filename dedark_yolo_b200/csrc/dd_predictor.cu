@@ -329,7 +329,7 @@ static void launch_conv_dgrad(const float* dpre, const float* w, const float* ac
 __global__ void __launch_bounds__(256)
 conv1_fwd_prep_kernel(const __grid_constant__ CUtensorMap rmap, const float* __restrict__ w, const float* __restrict__ bias,
                       float* __restrict__ out, int ntiles, int n_conv, const tc::PrepJobs jobs) {
-    pdl_begin();
+    pdl_launch();
     extern __shared__ __align__(128) unsigned char smem_c1f[];
     __shared__ __align__(8) uint64_t full[2];
     if ((int)blockIdx.x < n_conv) {
@@ -339,8 +339,10 @@ conv1_fwd_prep_kernel(const __grid_constant__ CUtensorMap rmap, const float* __r
             fence_mbar_init();
         }
         __syncthreads();
+        pdl_wait();
         conv1_fwd_body(blockIdx.x, n_conv, &rmap, w, bias, out, ntiles, smem_c1f, full);
     } else {
+        pdl_wait();
         tc::prep_weights_body(jobs, (int)blockIdx.x - n_conv);
     }
 }

@@ -152,12 +152,8 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
     constexpr bool U8 = XT == kXU8, XB = XT == kXBF16;
     static_assert((XT == kXF32 && !GB) || ALIGNED, "uint8 / bf16 operands need aligned rows");
     static_assert(!(GB && TMA), "a bf16 cotangent is staged through registers");
-    pdl_begin();
+    pdl_launch();   // the wait follows the barrier set-up below: nothing in front of it touches global memory
     __shared__ float s_tab[U8 ? 256 : 1];
-    if (U8) {
-        if (threadIdx.x < 256) s_tab[threadIdx.x] = __ldg(dark_tab + threadIdx.x);
-        __syncthreads();
-    }
     const unsigned char* x8 = reinterpret_cast<const unsigned char*>(x);
     const unsigned short* xb = reinterpret_cast<const unsigned short*>(x);
     const unsigned short* gb = reinterpret_cast<const unsigned short*>(g);
@@ -170,6 +166,11 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
             mbar_init(&tma_bar, 1);
             fence_mbar_init();
         }
+        __syncthreads();
+    }
+    pdl_wait();
+    if (U8) {
+        if (threadIdx.x < 256) s_tab[threadIdx.x] = __ldcg(dark_tab + threadIdx.x);   // not __ldg: ptxas hoists ld.global.nc above the wait
         __syncthreads();
     }
     float* XS = smem;                   // g, zero outside the image

@@ -52,12 +52,8 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                     const float* __restrict__ IcA, const float* __restrict__ feat, float* __restrict__ y, int B, int H, int W,
                     const float* __restrict__ dark_tab = nullptr) {
     static_assert(!U8 || (ALIGNED && !TMA), "uint8 sources: aligned rows, register prefetch");
-    pdl_begin();
+    pdl_launch();   // the wait follows the barrier set-up below: nothing in front of it touches global memory
     __shared__ float s_tab[U8 ? 256 : 1];
-    if (U8) {
-        if (threadIdx.x < 256) s_tab[threadIdx.x] = __ldg(dark_tab + threadIdx.x);
-        __syncthreads();
-    }
     const unsigned char* x8 = reinterpret_cast<const unsigned char*>(x);
     auto lut4 = [&](unsigned w) { return make_float4(s_tab[w & 255u], s_tab[(w >> 8) & 255u], s_tab[(w >> 16) & 255u], s_tab[w >> 24]); };
     extern __shared__ __align__(128) float smem[];
@@ -77,6 +73,11 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             mbar_init(&tma_bar, 1);
             fence_mbar_init();
         }
+        __syncthreads();
+    }
+    pdl_wait();
+    if (U8) {
+        if (threadIdx.x < 256) s_tab[threadIdx.x] = __ldcg(dark_tab + threadIdx.x);   // not __ldg: ptxas hoists ld.global.nc above the wait
         __syncthreads();
     }
 
