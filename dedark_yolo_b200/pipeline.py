@@ -115,6 +115,7 @@ class RecoveryPipeline:
         # experiment switch (profiles/debug/fork_probe.py): fork the next batch's synthesis before the filter backward instead of
         # behind it
         self.fork_before_filters_bwd = False
+        self.capture_stream = None   # stream the overlapped step is captured on (None: torch's capture stream); see enable_overlap
         self.graphs = {}
 
     # -- per-batch buffers: what the synthesis writes and the rest of the step reads ---------------------
@@ -315,7 +316,7 @@ class RecoveryPipeline:
             torch.cuda.synchronize(self.dev)
             self._cur = slot
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self.capture_stream):
                 out = self.step_overlapped(src_next, g)
                 if epilogue is not None:
                     epilogue(*out)

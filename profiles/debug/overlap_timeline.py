@@ -28,9 +28,20 @@ if GRAPH:
     for i in range(8):
         pipe.replay(i % 4)
     torch.cuda.synchronize()
+OVL_GRAPH = os.environ.get("OVL_GRAPH") == "1"   # the headline configuration of bench.py: the pipelined step as one graph per step
+if OVL_GRAPH:
+    for k in range(4):
+        pipe.capture_overlapped(("ovl", k), cleans[(k + 1) % 4], gs[k], slot=k % 2)
+    pipe._cur = 0
+    pipe.prime(cleans[0])
+    for i in range(8):
+        pipe.replay_overlapped(("ovl", i % 4))
+    torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for i in range(6, 9):
-        if GRAPH:
+    for i in range(8, 11):
+        if OVL_GRAPH:
+            pipe.replay_overlapped(("ovl", i % 4))
+        elif GRAPH:
             pipe.replay(i % 4)
         elif PLAIN:
             pipe.step(cleans[i % 4], gs[i % 4])
