@@ -35,6 +35,15 @@ def init_from_env(backend: str = "nccl"):
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
             kw["device_id"] = torch.device("cuda", local_rank)
+            if os.environ.get("DEDARK_NCCL_HIGH_PRIORITY", "1") == "1":
+                # the collectives of the bucketed step are small and latency-bound and start beside kernels that fill the GPU
+                # (the next batch's synthesis): their CTAs must not queue behind those
+                try:
+                    opts = dist.ProcessGroupNCCL.Options()
+                    opts.is_high_priority_stream = True
+                    kw["pg_options"] = opts
+                except Exception:  # pragma: no cover - older torch
+                    pass
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, local_rank, world
 

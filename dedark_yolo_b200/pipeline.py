@@ -115,6 +115,10 @@ class RecoveryPipeline:
         # experiment switch (profiles/debug/fork_probe.py): fork the next batch's synthesis before the filter backward instead of
         # behind it
         self.fork_before_filters_bwd = False
+        # bucketed data-parallel step, experiment switch: DEDARK_DDP_SCHEDULE=behind synthesises the next batch BEHIND the
+        # convolution backward (three graphs per step; the synthesis then runs beside the last all-reduce) instead of beside it
+        # (two graphs, the default).  Same step time at 2 GPUs (0.4003 ms either way).
+        self.synth_behind_conv_bwd = os.environ.get("DEDARK_DDP_SCHEDULE", "beside") == "behind"
         self.capture_stream = None   # stream the overlapped step is captured on (None: torch's capture stream); see enable_overlap
         self.graphs = {}
 
@@ -326,14 +330,24 @@ class RecoveryPipeline:
         return graph
 
     def _step_halves(self, src_next, g, half: int):
-        """The overlapped step in two halves around the point where the fc gradients are final: half 0 = forward, filter
-        backward, fc backward; half 1 = convolution backward with the synthesis of the next batch beside it."""
+        """The overlapped step in pieces around the points where a gradient bucket is final: half 0 = forward, filter
+        backward, fc backward; then either half 1 = convolution backward with the synthesis of the next batch forked beside it
+        (the default; the synthesis fills the GPU, so that fork overlaps little -- DESIGN.md section 6 (xxix) -- and the last
+        all-reduce is exposed at the end of the step), or (``synth_behind_conv_bwd``) half 1 = convolution backward and half 2 =
+        synthesis + resize of the next batch, which then runs beside the all-reduce of the convolution bucket."""
         main = torch.cuda.current_stream(self.dev)
         st = main.cuda_stream
         if half == 0:
             self.forward(st, resize=False)
             self.backward_filters(g, st)
             self.backward_predictor_part(st, 1)
+            return
+        if self.synth_behind_conv_bwd:
+            if half == 1:
+                self.backward_predictor_part(st, 2)
+            else:
+                self.synth(src_next, st, slot=self._cur ^ 1)
+                self.resize(st, slot=self._cur ^ 1)
             return
         self._ev_fork.record(main)
         self._side.wait_event(self._ev_fork)
@@ -349,7 +363,7 @@ class RecoveryPipeline:
         between them (collectives stay outside the graphs: capturing them hung at teardown)."""
         with torch.cuda.device(self.dev):
             graphs = []
-            for half in (0, 1):
+            for half in ((0, 1, 2) if self.synth_behind_conv_bwd else (0, 1)):
                 self._cur = slot
                 self._step_halves(src_next, g, half)  # warm-up outside capture
                 torch.cuda.synchronize(self.dev)
@@ -369,6 +383,8 @@ class RecoveryPipeline:
             w1 = self.allreduce_fc_async()
             graph[1].replay()
             w2 = self.allreduce_conv_async()
+            if len(graph) > 2:
+                graph[2].replay()   # the next batch's synthesis, beside the all-reduce of the convolution bucket
             w1.wait()
             w2.wait()
         else:
