@@ -430,6 +430,31 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     stage_us = {s: 1e3 * statistics.mean(ev[i][k].elapsed_time(ev[i][k + 1]) for i in range(args.steps))
                 for k, s in enumerate(stages)}
+    # the two filter kernels alone: bursts of 12 back-to-back launches (the queue stays full, so neither the host's launch work nor
+    # the event records of the eager loop above enter), inputs rotating over RING x 78.6 MB buffers (> L2).  dd_recovery_bwd is two
+    # launches (main kernel + finalize): its time covers both.
+    burst_us = {}
+    if cleans[0].dtype == torch.float32:
+        def _fwd(k):
+            _lib.check(_lib.lib.dd_recovery_fwd(_p(cleans[k]), None, None, _p(pipe.feat), _p(pipe.y), B, H, W, st))
+
+        def _bwd(k):
+            _lib.check(_lib.lib.dd_recovery_bwd(_p(cleans[k]), None, None, _p(pipe.feat), _p(gs[k]), _p(pipe.dfeat), None, B, H, W,
+                                                _p(pipe._ws_rb), pipe._ws_rb.numel(), st))
+
+        for name, fn in (("filters_fwd", _fwd), ("filters_bwd", _bwd)):
+            for i in range(4):
+                fn(i % RING)
+            ts = []
+            for rep in range(5):
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
+                for i in range(12):
+                    fn(i % RING)
+                b1.record()
+                b1.synchronize()
+                ts.append(1e3 * b0.elapsed_time(b1) / 12)
+            burst_us[name] = statistics.median(ts)
     peak, peak_src = load_peaks()
     alg = {"filters_fwd": BYTES_FWD * B, "filters_bwd": BYTES_BWD * B, "synth": BYTES_SYNTH * B}
     # whole-step fraction: the quantity the north star targets (22 806 528 B per image fwd+bwd at
@@ -437,15 +462,20 @@ def run_ours(args):
     step_bytes = (BYTES_FWD + BYTES_RESIZE_TAPS + BYTES_BWD) * B
     step_s = ms_per_step * 1e-3
     dominant = max(("filters_fwd", "filters_bwd"), key=lambda s: stage_us[s])
-    achieved = alg[dominant] / (stage_us[dominant] * 1e-6) / 1e9
+    kernel_us = burst_us.get(dominant, stage_us[dominant])   # the launch(es) alone; the eager stage time is reported beside it
+    achieved = alg[dominant] / (kernel_us * 1e-6) / 1e9
     roofline = {
         "bound": "hbm", "kernel": {"filters_fwd": "recovery_fwd_kernel", "filters_bwd": "recovery_bwd_kernel (+finalize)"}[dominant],
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": load_traffic({"filters_fwd": "recovery_fwd_kernel", "filters_bwd": "recovery_bwd_kernel"}[dominant]),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dominant],
-        "kernel_us": stage_us[dominant],
+        "kernel_us": kernel_us,
+        "kernel_us_how": ("median of 5 bursts of 12 back-to-back launches, CUDA events on the launching stream, inputs rotating over "
+                          f"{RING} x {B * 3 * H * W * 4 / 1e6:.1f} MB (> L2)") if dominant in burst_us else "eager stage time",
+        "kernel_us_by_kernel": burst_us,
+        "frac_eager_stage": alg[dominant] / (stage_us[dominant] * 1e-6) / 1e9 / peak,
         "all_stages_us": stage_us,
-        "frac_by_stage": {s: alg[s] / (stage_us[s] * 1e-6) / 1e9 / peak for s in alg},
+        "frac_by_stage": {s: alg[s] / (burst_us.get(s, stage_us[s]) * 1e-6) / 1e9 / peak for s in alg},
         "frac_vs_nominal_8TBs": achieved / 8000.0,
         "step_frac": step_bytes / step_s / 1e9 / peak,
         "step_frac_with_synthesis_bytes": (step_bytes + BYTES_SYNTH * B) / step_s / 1e9 / peak,
