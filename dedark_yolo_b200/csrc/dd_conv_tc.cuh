@@ -161,8 +161,17 @@ conv_tc_fwd(const float* __restrict__ in, const float* __restrict__ wprep, const
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    pdl_launch();   // after the TMEM allocation (dd_common.cuh); everything above ran beside the predecessor
+    // The prepared weights are written by conv1_fwd_prep_kernel at the head of the forward.  For conv3..conv5 (CIN == 32) that
+    // kernel is at least the predecessor's predecessor, and every tensor-core kernel releases its dependents only AFTER its own
+    // wait has returned (below: wait, then launch), so when this CTA runs, the predecessor is past its wait and the weights are
+    // final: their 74 KB copy starts ahead of the grid dependency.  conv2 (CIN == 16) directly follows the producer and waits.
+    constexpr bool EARLY_W = CIN == 32;
+    if (EARLY_W && warp < 8) {
+        for (int i = t; i < NST * B_STAGE / 4; i += 256) cp_async16(sB + 4 * i, wprep + 4 * i);
+        cp_async_commit();
+    }
     pdl_wait();
+    pdl_launch();   // after the TMEM allocation (dd_common.cuh) and after the wait (see above)
     const uint32_t tmem = ctl.tmem_base;
     DD_TC_STAMP(1);
 
@@ -170,8 +179,10 @@ conv_tc_fwd(const float* __restrict__ in, const float* __restrict__ wprep, const
         // ================================ producers + epilogue ================================
         const int m = t & 127, h = t >> 7, q = warp & 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        for (int i = t; i < NST * B_STAGE / 4; i += 256) cp_async16(sB + 4 * i, wprep + 4 * i);
-        cp_async_commit();
+        if (!EARLY_W) {
+            for (int i = t; i < NST * B_STAGE / 4; i += 256) cp_async16(sB + 4 * i, wprep + 4 * i);
+            cp_async_commit();
+        }
 
         // im2col gather of one stage (4 channels x 3x3 window) into registers: per window row one aligned 64-bit load
         // (columns 2*ow, 2*ow+1); the left neighbour (column 2*ow-1) comes from the previous lane's load
@@ -322,10 +333,22 @@ constexpr uint32_t kBwdTmemCols = 512;
 template <int CIN, int COUT>
 constexpr size_t conv_tc_dgrad_smem() { return (size_t)((COUT / 8) * 8 * 2 * 4 * CIN * 4) * sizeof(float); }
 
+// the data-gradient weights (prepared in the forward pass of the same step: final long before any backward kernel starts) into
+// shared memory; called ahead of griddepcontrol.wait
+template <int CIN, int COUT>
+__device__ __forceinline__ void conv_tc_dgrad_preload(const float* __restrict__ wprep, float* smem) {
+    constexpr int NST = COUT / 8, N = 4 * CIN, B_STAGE = 8 * 2 * N * 4;
+    const int t = threadIdx.x;
+    if (t < 256) {
+        for (int i = t; i < NST * B_STAGE / 4; i += 256) cp_async16(smem + 4 * i, wprep + 4 * i);
+        cp_async_commit();
+    }
+}
 template <int CIN, int COUT, int HIN>
 __device__ __forceinline__ void conv_tc_dgrad_body(const int cta, const int nctas, const float* __restrict__ dpre,
                                                    const float* __restrict__ wprep, const float* __restrict__ act_in,
                                                    float* __restrict__ din, int total_q, float* smem, BwdCtl* ctl) {
+    // (the prepared weights were requested by conv_tc_bwd ahead of the grid dependency: conv_tc_dgrad_preload)
     constexpr int HO = HIN / 2, NST = COUT / 8, N = 4 * CIN;
     constexpr int B_STAGE = 8 * 2 * N * 4;  // floats: [8 slots][hi rows | lo rows][4]
     constexpr uint32_t A_COL0 = 2 * N, A_BUF = 64, A_LO = 32;
@@ -339,8 +362,6 @@ __device__ __forceinline__ void conv_tc_dgrad_body(const int cta, const int ncta
     if (warp < 8) {
         const int m = t & 127, h = t >> 7, q = warp & 3, half = warp >> 2;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        for (int i = t; i < NST * B_STAGE / 4; i += 256) cp_async16(sB + 4 * i, wprep + 4 * i);
-        cp_async_commit();
 
         struct Raw { float v[16]; };  // [channel e][nb = da*2 + dc]
         auto gather = [&](Raw& r, int tile, int c) {
@@ -687,8 +708,9 @@ conv_tc_bwd(const float* __restrict__ in, const float* __restrict__ dpre, const 
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    pdl_launch();   // after the TMEM allocation (dd_common.cuh)
+    if ((int)blockIdx.x >= n_w) conv_tc_dgrad_preload<CIN, COUT>(wprep_dgrad, smem_tc);
     pdl_wait();
+    pdl_launch();   // after the TMEM allocation (dd_common.cuh) and after the wait (conv_tc_fwd explains why)
     if ((int)blockIdx.x < n_w)
         conv_tc_wgrad_body<CIN, COUT, HIN>(blockIdx.x, n_w, in, dpre, partial, total_px, smem_tc, &ctl);
     else

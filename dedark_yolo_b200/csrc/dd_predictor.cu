@@ -249,7 +249,8 @@ fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, cons
               const float* __restrict__ flat, const float* __restrict__ w1, float* __restrict__ dw2, float* __restrict__ db2,
               float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dpre5, int B, int n_w, int n_d,
               const PushCtx px) {
-    pdl_begin();
+    pdl_wait();     // wait, then launch: the tensor-core kernel behind this one copies its (forward-pass) weights ahead of its own wait
+    pdl_launch();
     static_assert(kFc1In % 256 == 0, "a CTA never straddles two rows of W1");
     const unsigned int tag = push_tag(px);
     __shared__ float s_dh[256];

@@ -1,8 +1,8 @@
 """Static check of the built library: programmatic dependent launch is only safe when NO global-memory access of a kernel is
 scheduled in front of its griddepcontrol.wait (SASS: ACQBULK).  The source puts pdl_begin() first in every kernel, but ptxas is
 free to move non-coherent loads (ld.global.nc / __ldg) across the wait -- it did, once (dd_predictor.cu, fc_fwd_kernel) -- so the
-rule is checked on the machine code.  Two kernels read PARAMETERS ahead of the wait on purpose (no kernel of the library writes
-them): there every load in front of the wait must be a weight load, and the producer's data is read with ld.global.cg behind it.
+rule is checked on the machine code.  A few kernels read PARAMETERS or data that is final at least two kernels earlier ahead of the
+wait on purpose: there every access in front of the wait must be one of those loads (the producer's data is read behind it).
 """
 import re
 import shutil
@@ -15,6 +15,10 @@ from dedark_yolo_b200 import _lib
 ALLOWED_EARLY = {   # kernel-name fragment -> SASS opcodes allowed in front of ACQBULK
     "fc_fwd_kernel": {"LDG.E.128", "LDG.E.128.CONSTANT"},
     "predictor_tail_kernel": {"LDG.E.CONSTANT"},
+    # the prepared weights of the tensor-core convolutions (written by conv1_fwd_prep_kernel, at least two kernels earlier in
+    # the stream; every tensor-core kernel and fc_bwd release their dependents only after their own wait) are copied early
+    "conv_tc_fwdILi32E": {"LDGSTS.E.BYPASS.128", "LDGDEPBAR"},
+    "conv_tc_bwd": {"LDGSTS.E.BYPASS.128", "LDGDEPBAR"},
 }
 GLOBAL_OP = re.compile(r"\*/\s+(?:@!?U?P\d+\s+)?((?:LDG|LD\.E|LDGSTS|UTMALDG|UBLKCP|ATOMG|ATOM\.|RED\.|REDG|STG|ST\.E|UTMASTG)\S*)")
 
