@@ -734,34 +734,41 @@ struct ReduceJob {
 struct ReduceJobs {
     ReduceJob j[5];
 };
-constexpr int kReduceOut = 128;  // outputs per CTA: four per lane (one 128-bit load per slice): 257 CTAs, one wave
-__global__ void __launch_bounds__(1024, 2)  // 2 CTAs per SM: this kernel is a latency chain, occupancy is its throughput
+constexpr int kReduceOut = 128;     // outputs per CTA: four per lane (one 128-bit load per slice)
+constexpr int kReduceWarps = 8;     // 256-thread CTAs (32 registers): two of them fit on an SM BESIDE a conv1_wgrad CTA
+// The slices of the tensor-core layers (jobs 1..4) were written by kernels that are at least the predecessor's predecessor, and
+// the predecessor (conv1_wgrad_kernel) releases its dependents only after its own wait: those CTAs -- 253 of 257 -- do not wait
+// for the grid dependency at all and run beside conv1_wgrad; only the four CTAs of conv1's own slices (job 0) wait for it.
+// (With the peer exchange every CTA waits: its pushes must not overtake the previous exchange.)
+__global__ void __launch_bounds__(kReduceWarps * 32)
 wgrad_reduce_kernel(const ReduceJobs jobs, const PushCtx px) {
-    pdl_begin();
-    __shared__ float s_part[32][kReduceOut + 1];
-    const unsigned int tag = push_tag(px);
+    pdl_launch();
+    __shared__ float s_part[kReduceWarps][kReduceOut + 1];
     int ji = 0;
 #pragma unroll
     for (int k = 1; k < 5; ++k)
         if ((int)blockIdx.x >= jobs.j[k].block0) ji = k;
+    if (ji == 0 || px.world > 1) pdl_wait();
+    const unsigned int tag = push_tag(px);
     const ReduceJob jb = jobs.j[ji];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int base = ((int)blockIdx.x - jb.block0) * kReduceOut;
-    {   // warp `wid` sums slices wid, wid + 32, ... for outputs base + 4*lane .. + 3 (n and stride are multiples of 4)
+    {   // warp `wid` sums slices wid, wid + 8, ... for outputs base + 4*lane .. + 3 (n and stride are multiples of 4)
+        constexpr int NW = kReduceWarps;
         const int i = base + 4 * lane;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
         auto add = [](float4& a, const float4 v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
         if (i < jb.n) {
             const float* p0 = jb.partial + i;
             int s = wid;
-            for (; s + 96 < jb.nslices; s += 128) {
-                const float4 v0 = __ldg(reinterpret_cast<const float4*>(p0 + (size_t)s * jb.stride));
-                const float4 v1 = __ldg(reinterpret_cast<const float4*>(p0 + (size_t)(s + 32) * jb.stride));
-                const float4 v2 = __ldg(reinterpret_cast<const float4*>(p0 + (size_t)(s + 64) * jb.stride));
-                const float4 v3 = __ldg(reinterpret_cast<const float4*>(p0 + (size_t)(s + 96) * jb.stride));
+            for (; s + 3 * NW < jb.nslices; s += 4 * NW) {
+                const float4 v0 = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)s * jb.stride));
+                const float4 v1 = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)(s + NW) * jb.stride));
+                const float4 v2 = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)(s + 2 * NW) * jb.stride));
+                const float4 v3 = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)(s + 3 * NW) * jb.stride));
                 add(a0, v0); add(a1, v1); add(a2, v2); add(a3, v3);
             }
-            for (; s < jb.nslices; s += 32) add(a0, __ldg(reinterpret_cast<const float4*>(p0 + (size_t)s * jb.stride)));
+            for (; s < jb.nslices; s += NW) add(a0, __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)s * jb.stride)));
         }
         s_part[wid][4 * lane] = (a0.x + a1.x) + (a2.x + a3.x);
         s_part[wid][4 * lane + 1] = (a0.y + a1.y) + (a2.y + a3.y);
@@ -773,7 +780,7 @@ wgrad_reduce_kernel(const ReduceJobs jobs, const PushCtx px) {
     if (wid < kReduceOut / 32 && i < jb.n) {
         float r = 0.f;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) r += s_part[k][wid * 32 + lane];
+        for (int k = 0; k < kReduceWarps; ++k) r += s_part[k][wid * 32 + lane];
         int off;  // canonical flat offset of this output
         if (jb.cin == 0) {
             if (i < jb.nw) { jb.dw[i] = r; off = jb.off_w + i; } else { jb.db[i - jb.nw] = r; off = jb.off_b + i - jb.nw; }

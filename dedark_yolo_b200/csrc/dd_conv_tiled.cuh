@@ -110,7 +110,6 @@ constexpr size_t conv1_wgrad_smem() { return (size_t)2 * (c1_tile_bytes(kC1WgTH)
 __global__ void __launch_bounds__(256, 1)
 conv1_wgrad_kernel(const __grid_constant__ CUtensorMap rmap, const __grid_constant__ CUtensorMap dmap, float* __restrict__ partial,
                    int ntiles) {
-    pdl_launch();
     constexpr int TH = kC1WgTH, TX = kC1HOut / kC1TW, TY = kC1HOut / TH, ROWS = 2 * TH + 1, NW = kC1Out * kC1In * 9;
     constexpr int IN_B = c1_tile_bytes(TH), BUF_B = IN_B + kC1DTileB;
     extern __shared__ __align__(128) unsigned char smem_c1[];
@@ -123,6 +122,7 @@ conv1_wgrad_kernel(const __grid_constant__ CUtensorMap rmap, const __grid_consta
     }
     __syncthreads();
     pdl_wait();
+    pdl_launch();   // wait, then launch: most CTAs of the slice reduction behind this kernel do not wait for it (dd_conv_tc.cuh)
     auto issue = [&](int it) {
         const int tl = blockIdx.x + it * gridDim.x, tile = tl % (TX * TY), b = tl / (TX * TY);
         const int oh0 = (tile / TX) * TH, ow0 = (tile % TX) * kC1TW;

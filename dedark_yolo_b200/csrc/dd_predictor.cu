@@ -538,7 +538,7 @@ static int predictor_bwd_impl(const float* r, const dd_predictor_tensors* w, con
                                       l == 0 ? 0 : pred_cin(l), 432, block0, grad_off_conv_w(l), grad_off_conv_b(l)};
             block0 += (n + tc::kReduceOut - 1) / tc::kReduceOut;
         }
-        launch_pdl(tc::wgrad_reduce_kernel, dim3(block0), dim3(1024), 0, st, jobs, px);
+        launch_pdl(tc::wgrad_reduce_kernel, dim3(block0), dim3(tc::kReduceWarps * 32), 0, st, jobs, px);
     }
     count_launch(2);
     if (px.world > 1) {
