@@ -100,6 +100,10 @@ __device__ __forceinline__ void pdl_begin() {
 // Kernels that allocate TMEM call pdl_launch() AFTER the allocation: a dependent CTA that shares the SM must not be able to take
 // the columns first (it would hold them while waiting for this grid, which waits for the columns).
 // tests/test_sass_pdl.py checks on the SASS that no global access ends up in front of the wait.
+// For kernels that PRODUCE image-sized tensors (the synthesis passes, the dark-channel prior): wait, and never release the
+// dependents early -- they start when this grid has completed and flushed.  That is what allows the filter kernels to prefetch
+// the batch ahead of their own grid dependency whatever the caller's launch order is.
+__device__ __forceinline__ void pdl_wait_only() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 template <typename... KArgs, typename... Args>

@@ -108,7 +108,8 @@ __device__ inline void regress_warp(const float* __restrict__ f, ImgParams& P) {
         const bool wb = lane >= kSlotWb && lane < kSlotWb + 3;
         const bool live = lane == kSlotDedark || wb || lane == kSlotGamma || lane == kSlotContrast || lane == kSlotUsm;
         float t = 0.f;
-        if (live) t = tanhf(wb ? f[lane] * (lane == kSlotWb ? 0.f : 1.f) : f[lane]);
+        const float fv = live ? __ldcg(f + lane) : 0.f;   // the predictor's output: ld.global.cg, never moved across griddepcontrol.wait
+        if (live) t = tanhf(wb ? fv * (lane == kSlotWb ? 0.f : 1.f) : fv);
         P.t[lane] = t;
         if (wb) P.cs[lane - kSlotWb] = expf(t * 1.0f / 2.0f);
         if (lane == kSlotGamma) P.gamma = expf(t * kLn3);

@@ -168,8 +168,14 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         }
         __syncthreads();
     }
-    pdl_wait();
+    // As in the forward kernel: the batch and the cotangent (x, IcA, A, g) are inputs of the step -- no kernel of the library that
+    // writes image-sized tensors releases its dependents early -- so the first segment requests its per-row columns and its first
+    // cotangent tile BEFORE the wait, which sits in front of the regressors (feat is the only operand a predecessor may still be
+    // writing).  uint8 sources wait here (the table).
+    bool waited = false;
     if (U8) {
+        pdl_wait();
+        waited = true;
         if (threadIdx.x < 256) s_tab[threadIdx.x] = __ldcg(dark_tab + threadIdx.x);   // not __ldg: ptxas hoists ld.global.nc above the wait
         __syncthreads();
     }
@@ -233,11 +239,6 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
                 }
             }
         }
-        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
-        __syncthreads();
-        const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
-        const float pc = sp.c, pp = sp.p;
-
         // g block n -> ring XS (rows outside the image and columns outside [0, W) are zero)
         uint2 gpre[GB ? kStage4 : 1];   // GB: the bf16 rows of the next block, in flight between stage(n) and stage_commit(n)
         // GB: a thread's items of a block are the same (row, column chunk) pairs in every block -- their offsets are computed once per
@@ -320,6 +321,14 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
             cp_async_commit();
         };
         stage(0);
+        if (!waited) {
+            pdl_wait();
+            waited = true;
+        }
+        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
+        __syncthreads();
+        const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
+        const float pc = sp.c, pp = sp.p;
 
         // ---- mirror extension of the cotangent ring (see the header) -------------------------------------------------------------
         const bool mirror = H > kRadius + 1 && W > kRadius + 1;

@@ -75,8 +75,15 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         }
         __syncthreads();
     }
-    pdl_wait();
+    // The grid dependency of this kernel is the predictor's output (feat).  The batch itself (x, IcA, A) is an input of the step:
+    // the kernels of this library that write image-sized tensors (synthesis, dark-channel prior) never release their dependents
+    // early (pdl_wait_only, dd_common.cuh), so whatever runs behind them sees them complete.  The first segment therefore requests
+    // its per-row columns and its first tile BEFORE the wait, which sits in front of the regressors below.  (uint8 sources wait
+    // here: the table.)
+    bool waited = false;
     if (U8) {
+        pdl_wait();
+        waited = true;
         if (threadIdx.x < 256) s_tab[threadIdx.x] = __ldcg(dark_tab + threadIdx.x);   // not __ldg: ptxas hoists ld.global.nc above the wait
         __syncthreads();
     }
@@ -110,11 +117,6 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                 }
             }
         }
-        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
-        __syncthreads();
-        const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
-        const float pc = sp.c, pp = sp.p;
-
         // item (k) of a thread: row pair rp (2 rows) x float4 column c4; fixed across blocks
         float4 pre[kStage2][2], prei[kStage2][2];
         auto stage = [&](int n) {
@@ -162,7 +164,15 @@ recovery_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                 }
             }
         };
-        if (TMA) stage(0);  // the first block's rows fly while the per-row scalars below are computed
+        if (TMA) stage(0);  // the first block's rows fly while the regressors and the per-row scalars below are computed
+        if (!waited) {
+            pdl_wait();
+            waited = true;
+        }
+        if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
+        __syncthreads();
+        const ChainK ck = make_chain(sp, u.ch, A ? __ldg(A + u.b * 3 + u.ch) : kDefaultA);
+        const float pc = sp.c, pp = sp.p;
         {   // per-row contrast scalars of the segment (the rows' first three columns were loaded at the top of the segment)
 #pragma unroll
             for (int k = 0; k < kPer; ++k) {

@@ -13,7 +13,14 @@ import pytest
 from dedark_yolo_b200 import _lib
 
 ALLOWED_EARLY = {   # kernel-name fragment -> SASS opcodes allowed in front of ACQBULK
-    "fc_fwd_kernel": {"LDG.E.128", "LDG.E.128.CONSTANT"},
+    "fc_fwd_kernel": {"LDG.E.128", "LDG.E.128.CONSTANT", "LDG.E.CONSTANT"},   # weights and biases; the activations use ld.global.cg
+    # the batch (x, IcA, A: inputs of the step, older than fc_fwd_kernel, which waits before it releases this kernel): the first
+    # segment's per-row columns and first tile; the predictor's output (feat) is read with ld.global.cg behind the wait
+    "recovery_fwd_kernel": {"LDG.E.CONSTANT", "LDG.E.128.CONSTANT", "LDG.E.64.CONSTANT", "UTMALDG.3D"},
+    # the same in the backward (x, IcA, A and the cotangent g).  Its wait sits inside the segment loop, so in the linear listing the
+    # loop-carried flush of the per-plane-strip sums (STG.E, executed from the second segment on) is laid out in front of it.
+    "recovery_bwd_kernel": {"LDG.E.CONSTANT", "LDG.E.128.CONSTANT", "LDG.E.64.CONSTANT", "LDG.E.U16.CONSTANT", "UTMALDG.3D",
+                            "LDGSTS.E.BYPASS.128.ZFILL", "LDGDEPBAR", "STG.E"},
     "predictor_tail_kernel": {"LDG.E.CONSTANT"},
     # the prepared weights of the tensor-core convolutions (written by conv1_fwd_prep_kernel, at least two kernels earlier in
     # the stream; every tensor-core kernel and fc_bwd release their dependents only after their own wait) are copied early
