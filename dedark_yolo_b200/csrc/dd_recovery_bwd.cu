@@ -27,6 +27,7 @@
 // image, no float atomics) adds them up, applies the column 0..2 fix-up and the regressor Jacobians.
 #include <cooperative_groups.h>
 #include <cstring>
+#include <type_traits>
 
 #include "dd_async.cuh"
 #include "dd_recovery.cuh"
@@ -152,7 +153,6 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
     constexpr bool U8 = XT == kXU8, XB = XT == kXBF16;
     static_assert((XT == kXF32 && !GB) || ALIGNED, "uint8 / bf16 operands need aligned rows");
     static_assert(!(GB && TMA), "a bf16 cotangent is staged through registers");
-    pdl_launch();   // the wait follows the barrier set-up below: nothing in front of it touches global memory
     __shared__ float s_tab[U8 ? 256 : 1];
     const unsigned char* x8 = reinterpret_cast<const unsigned char*>(x);
     const unsigned short* xb = reinterpret_cast<const unsigned short*>(x);
@@ -172,9 +172,11 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
     // writes image-sized tensors releases its dependents early -- so the first segment requests its per-row columns and its first
     // cotangent tile BEFORE the wait, which sits in front of the regressors (feat is the only operand a predecessor may still be
     // writing).  uint8 sources wait here (the table).
+    // (wait, THEN launch_dependents: the finalize kernel behind this one reads x and feat ahead of its own wait)
     bool waited = false;
     if (U8) {
         pdl_wait();
+        pdl_launch();
         waited = true;
         if (threadIdx.x < 256) s_tab[threadIdx.x] = __ldcg(dark_tab + threadIdx.x);   // not __ldg: ptxas hoists ld.global.nc above the wait
         __syncthreads();
@@ -323,6 +325,7 @@ recovery_bwd_kernel(const __grid_constant__ CUtensorMap gmap, const float* __res
         stage(0);
         if (!waited) {
             pdl_wait();
+            pdl_launch();
             waited = true;
         }
         if (tid < 32) regress_warp(feat + u.b * kFeat, sp);
@@ -581,8 +584,16 @@ template <typename TX>
 __device__ __forceinline__ float load_x0(const TX* x, size_t i, const float*) { return btc::Elem<TX>::load1(x + i); }
 template <>
 __device__ __forceinline__ float load_x0<unsigned char>(const unsigned char* x, size_t i, const float* tab) { return __ldg(tab + __ldg(x + i)); }
+// dx was written by the main kernel (the grid dependency): read it with ld.global.cg, which is never moved across the wait
 template <typename TX>
-__device__ __forceinline__ void add_dx(TX* dx, size_t i, float v) { btc::Elem<TX>::store1(dx + i, btc::Elem<TX>::load1(dx + i) + v); }
+__device__ __forceinline__ void add_dx(TX* dx, size_t i, float v);
+template <>
+__device__ __forceinline__ void add_dx<float>(float* dx, size_t i, float v) { dx[i] = __ldcg(dx + i) + v; }
+template <>
+__device__ __forceinline__ void add_dx<__nv_bfloat16>(__nv_bfloat16* dx, size_t i, float v) {
+    const float old = __uint_as_float((unsigned)__ldcg(reinterpret_cast<const unsigned short*>(dx + i)) << 16);
+    dx[i] = __float2bfloat16_rn(old + v);
+}
 template <>
 __device__ __forceinline__ void add_dx<unsigned char>(unsigned char*, size_t, float) {}   // a uint8 source has no gradient
 
@@ -597,7 +608,12 @@ recovery_bwd_finalize_kernel(const TX* __restrict__ x, const float* __restrict__
                              const float* __restrict__ part, const float* __restrict__ Spart,
                              float* __restrict__ dfeat, TX* __restrict__ dx, int B, int H, int W, int ctas, int nsp,
                              const float* __restrict__ dark_tab = nullptr) {
-    pdl_begin();
+    // The main kernel in front releases this one only after its own wait has returned, so x, IcA, A and feat are final when a CTA
+    // of this kernel starts: the regressors and the rows' first three columns are requested AHEAD of the grid dependency, the
+    // main kernel's partial sums (part, Spart) behind it, with ld.global.cg.  (uint8 sources wait first: the table.)
+    pdl_launch();
+    constexpr bool kEarly = !std::is_same<TX, unsigned char>::value;
+    if (!kEarly) pdl_wait();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ ImgParams sp;
@@ -616,16 +632,24 @@ recovery_bwd_finalize_kernel(const TX* __restrict__ x, const float* __restrict__
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = i0 + e * kFinThreads + tid;
-            S[e] = 0.f;
             if (i < row_hi) {
                 const int ch = i / H, row = i - ch * H, plane = 3 * b + ch;
-                for (int st = 0; st < nsp; ++st) S[e] += Spart[((size_t)plane * H + row) * nsp + st];
                 const size_t off = ((size_t)plane * H + row) * W;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     x0[e][k] = load_x0(x, off + k, dark_tab);
                     ica[e][k] = HAS_ICA ? __ldg(IcA + ((size_t)b * H + row) * W + k) : kDefaultIcA;
                 }
+            }
+        }
+        if (kEarly && i0 == row_lo) pdl_wait();
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = i0 + e * kFinThreads + tid;
+            S[e] = 0.f;
+            if (i < row_hi) {
+                const int ch = i / H, row = i - ch * H, plane = 3 * b + ch;
+                for (int st = 0; st < nsp; ++st) S[e] += __ldcg(Spart + ((size_t)plane * H + row) * nsp + st);
             }
         }
         if (i0 == row_lo) __syncthreads();  // sp
@@ -678,7 +702,8 @@ recovery_bwd_finalize_kernel(const TX* __restrict__ x, const float* __restrict__
         const float wk = HAS_ICA ? 1.f : ((1.f - sp.w * kDefaultIcA >= kTxMin) ? kDefaultIcA / (txc * txc) : 0.f);
         const ChainK ckp = make_chain(sp, ch, A ? __ldg(A + b * 3 + ch) : kDefaultA);
         for (int c = c_first; c <= c_last; ++c) {
-            const float* q = part + (size_t)(c + ps) * kBwdSums;
+            const float* qp = part + (size_t)(c + ps) * kBwdSums;
+            const float q[kBwdSums] = {__ldcg(qp), __ldcg(qp + 1), __ldcg(qp + 2), __ldcg(qp + 3), __ldcg(qp + 4)};
             dp += q[0]; dc += q[1]; dg += (double)q[2] * 0.69314718055994530942;
             if (HAS_ICA) {
                 ds[ch] += q[3];

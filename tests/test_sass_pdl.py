@@ -19,6 +19,10 @@ ALLOWED_EARLY = {   # kernel-name fragment -> SASS opcodes allowed in front of A
     "recovery_fwd_kernel": {"LDG.E.CONSTANT", "LDG.E.128.CONSTANT", "LDG.E.64.CONSTANT", "UTMALDG.3D"},
     # the same in the backward (x, IcA, A and the cotangent g).  Its wait sits inside the segment loop, so in the linear listing the
     # loop-carried flush of the per-plane-strip sums (STG.E, executed from the second segment on) is laid out in front of it.
+    # the finalize kernel behind it (the main kernel waits before it releases it): feat (ld.global.cg, first in program order) and
+    # the rows' first three columns of x / IcA; the main kernel's partial sums and dx are ld.global.cg behind the wait (volatile
+    # asm statements keep their order)
+    "recovery_bwd_finalize_kernel": {"LDG.E.CONSTANT", "LDG.E.U16.CONSTANT", "LDG.E.STRONG.GPU"},
     "recovery_bwd_kernel": {"LDG.E.CONSTANT", "LDG.E.128.CONSTANT", "LDG.E.64.CONSTANT", "LDG.E.U16.CONSTANT", "UTMALDG.3D",
                             "LDGSTS.E.BYPASS.128.ZFILL", "LDGDEPBAR", "STG.E"},
     "predictor_tail_kernel": {"LDG.E.CONSTANT"},
