@@ -561,6 +561,10 @@ __device__ __forceinline__ void conv_tc_wgrad_body(const int cta, const int nsli
             float own[12];
             float dv[NDV][4];
         };
+        // `in` is an activation of the forward pass (final long before any backward kernel), dpre the gradient the predecessor
+        // just wrote: the first gather of a CTA requests its `in` window, THEN waits for the grid dependency, then reads dpre
+        // (ld.global.cg: ptxas moves ld.global.nc across the wait)
+        bool waited = false;
         auto gather = [&](Raw& v, int tile) {
             const int gp = tile * PXT + p;
             const bool valid = gp < total_px;
@@ -576,6 +580,10 @@ __device__ __forceinline__ void conv_tc_wgrad_body(const int cta, const int nsli
                     v.x[e * 3 + kh] = ok ? __ldg(reinterpret_cast<const float2*>(rp)) : make_float2(0.f, 0.f);
                     v.own[e * 3 + kh] = (ok && lane == 0 && ow > 0) ? __ldg(rp - 1) : 0.f;
                 }
+            if (!waited) {
+                pdl_wait();
+                waited = true;
+            }
 #pragma unroll
             for (int u = 0; u < NDV; ++u) {
                 const int idx = t + u * 256, pp = idx % PXT, gch = idx / PXT;
@@ -583,7 +591,7 @@ __device__ __forceinline__ void conv_tc_wgrad_body(const int cta, const int nsli
                 const int bb = gpp / (HO * HO), rr = gpp % (HO * HO);
                 const float* d = dpre + ((size_t)bb * COUT + 4 * gch) * HO * HO + rr;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v.dv[u][e] = gpp < total_px ? __ldg(d + (size_t)e * HO * HO) : 0.f;
+                for (int e = 0; e < 4; ++e) v.dv[u][e] = gpp < total_px ? __ldcg(d + (size_t)e * HO * HO) : 0.f;
             }
         };
         int g = 0;
@@ -629,6 +637,7 @@ __device__ __forceinline__ void conv_tc_wgrad_body(const int cta, const int nsli
         Raw v0, v1;
         if (t0 < t1) gather(v0, t0);
         if (t0 + 1 < t1) gather(v1, t0 + 1);
+        if (!waited) pdl_wait();   // a CTA without tiles still zeroes its slice below
 #pragma unroll 1
         for (int tile = t0; tile < t1; tile += 2) {
             stage(v0, tile);
@@ -708,13 +717,18 @@ conv_tc_bwd(const float* __restrict__ in, const float* __restrict__ dpre, const 
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if ((int)blockIdx.x >= n_w) conv_tc_dgrad_preload<CIN, COUT>(wprep_dgrad, smem_tc);
-    pdl_wait();
-    pdl_launch();   // after the TMEM allocation (dd_common.cuh) and after the wait (conv_tc_fwd explains why)
-    if ((int)blockIdx.x < n_w)
+    if ((int)blockIdx.x < n_w) {
+        // weight-gradient CTAs wait inside their first gather (behind the loads of the forward activations).  They may release the
+        // dependents right away: the data-gradient CTAs of the same grid do so only after the wait, and the dependent grid starts
+        // when EVERY CTA has, i.e. when the predecessor of this grid has completed.
+        pdl_launch();
         conv_tc_wgrad_body<CIN, COUT, HIN>(blockIdx.x, n_w, in, dpre, partial, total_px, smem_tc, &ctl);
-    else
+    } else {
+        conv_tc_dgrad_preload<CIN, COUT>(wprep_dgrad, smem_tc);
+        pdl_wait();
+        pdl_launch();   // after the TMEM allocation (dd_common.cuh) and after the wait (conv_tc_fwd explains why)
         conv_tc_dgrad_body<CIN, COUT, HIN>(blockIdx.x - n_w, gridDim.x - n_w, dpre, wprep_dgrad, act_in, din, total_px, smem_tc, &ctl);
+    }
     fence_before_sync();
     __syncthreads();
     DD_TC_CTA_END();
