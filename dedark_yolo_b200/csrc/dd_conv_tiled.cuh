@@ -120,19 +120,23 @@ conv1_wgrad_kernel(const __grid_constant__ CUtensorMap rmap, const __grid_consta
         mbar_init(&full[1], 1);
         fence_mbar_init();
     }
-    __syncthreads();
-    pdl_wait();
-    pdl_launch();   // wait, then launch: most CTAs of the slice reduction behind this kernel do not wait for it (dd_conv_tc.cuh)
-    auto issue = [&](int it) {
+    // part 1 of a tile: the window of the resized batch r (an input of the forward pass); part 2: the cotangent tile the predecessor
+    // (conv_tc_bwd<16, 32, 128>, which waits before it releases this kernel) has just written.  Both land on the same barrier.
+    auto issue = [&](int it, int part) {
         const int tl = blockIdx.x + it * gridDim.x, tile = tl % (TX * TY), b = tl / (TX * TY);
         const int oh0 = (tile / TX) * TH, ow0 = (tile % TX) * kC1TW;
         unsigned char* buf = smem_c1 + (it & 1) * BUF_B;
-        mbar_arrive_expect_tx(&full[it & 1], kC1In * ROWS * kC1BoxW * 4 + kC1DTileB);
-        tma_load_3d(buf, &rmap, 2 * ow0 - 4, 2 * oh0 - 1, b * kC1In, &full[it & 1]);
-        tma_load_3d(buf + IN_B, &dmap, ow0, oh0, b * kC1Out, &full[it & 1]);
+        if (part & 1) {
+            mbar_arrive_expect_tx(&full[it & 1], kC1In * ROWS * kC1BoxW * 4 + kC1DTileB);
+            tma_load_3d(buf, &rmap, 2 * ow0 - 4, 2 * oh0 - 1, b * kC1In, &full[it & 1]);
+        }
+        if (part & 2) tma_load_3d(buf + IN_B, &dmap, ow0, oh0, b * kC1Out, &full[it & 1]);
     };
     const int my = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    if (tid == 0 && my > 0) issue(0);
+    if (tid == 0 && my > 0) issue(0, 1);   // r of the first tile: ahead of the grid dependency
+    pdl_wait();
+    pdl_launch();   // wait, then launch: most CTAs of the slice reduction behind this kernel do not wait for it (dd_conv_tc.cuh)
+    if (tid == 0 && my > 0) issue(0, 2);
 
     float acc[4][27], accb[4];
 #pragma unroll
@@ -142,7 +146,7 @@ conv1_wgrad_kernel(const __grid_constant__ CUtensorMap rmap, const __grid_consta
         for (int k = 0; k < 27; ++k) acc[t][k] = 0.f;
     }
     for (int it = 0; it < my; ++it) {
-        if (tid == 0 && it + 1 < my) issue(it + 1);
+        if (tid == 0 && it + 1 < my) issue(it + 1, 3);
         mbar_wait(&full[it & 1], (uint32_t)(it >> 1) & 1u);
         const float* s_in = reinterpret_cast<const float*>(smem_c1 + (it & 1) * BUF_B);
         const float* s_d = reinterpret_cast<const float*>(smem_c1 + (it & 1) * BUF_B + IN_B);

@@ -28,6 +28,8 @@ ALLOWED_EARLY = {   # kernel-name fragment -> SASS opcodes allowed in front of A
     "predictor_tail_kernel": {"LDG.E.CONSTANT"},
     # the prepared weights of the tensor-core convolutions (written by conv1_fwd_prep_kernel, at least two kernels earlier in
     # the stream; every tensor-core kernel and fc_bwd release their dependents only after their own wait) are copied early
+    # the resized batch r (an input of the forward pass) of the first tile; the cotangent tile follows behind the wait
+    "conv1_wgrad_kernel": {"UTMALDG.3D"},
     "conv_tc_fwdILi32E": {"LDGSTS.E.BYPASS.128", "LDGDEPBAR"},
     "conv_tc_bwd": {"LDGSTS.E.BYPASS.128", "LDGDEPBAR"},
 }
