@@ -243,7 +243,8 @@ fc_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w1, cons
 // that every CTA recomputes the few values it needs in shared memory instead of waiting for a separate kernel:
 //   CTAs [0, n_w)         dW1[o][i] = sum_b dhpre[b][o] flat[b][i]  (256 consecutive i of ONE o per CTA), db1[o]
 //   CTAs [n_w, n_w + n_d) dpre5[b][i] = leaky'(a5[b][i]) * sum_o dhpre[b][o] W1[o][i]  (256 consecutive i of ONE image)
-//   last CTA              dW2[j][o] = sum_b dfeat[b][j] h[b][o],  db2[j] = sum_b dfeat[b][j]
+//   last 4 CTAs           dW2[j][o] = sum_b dfeat[b][j] h[b][o] (one element per thread),  db2[j] = sum_b dfeat[b][j]
+constexpr int kFc2Ctas = (kFeat * kFc1Out + 255) / 256;   // 4
 __global__ void __launch_bounds__(256)
 fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, const float* __restrict__ w2,
               const float* __restrict__ flat, const float* __restrict__ w1, float* __restrict__ dw2, float* __restrict__ db2,
@@ -294,15 +295,16 @@ fc_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ h, cons
 #pragma unroll 8
         for (int o = 0; o < kFc1Out; ++o) acc = fmaf(s_dh[o], __ldg(w1 + (size_t)o * kFc1In + i), acc);
         dpre5[t] = leaky_grad(flat[t], acc);
-    } else {
-        for (int t = tid; t < kFeat * kFc1Out; t += 256) {
+    } else {   // the last kFc2Ctas CTAs: one dW2 element per thread (one CTA looping four times was the longest chain of the kernel)
+        const int t = (bid - n_w - n_d) * 256 + tid;
+        if (t < kFeat * kFc1Out) {
             const int j = t / kFc1Out, o = t % kFc1Out;
             float acc = 0.f;
             for (int b = 0; b < B; ++b) acc = fmaf(__ldg(dfeat + b * kFeat + j), __ldg(h + b * kFc1Out + o), acc);
             dw2[t] = acc;
             if (px.world > 1) push_grad(px, tag, kGradOffFc2W + t, acc);
         }
-        if (tid < kFeat) {
+        if (bid == n_w + n_d && tid < kFeat) {
             float acc = 0.f;
             for (int b = 0; b < B; ++b) acc += __ldg(dfeat + b * kFeat + tid);
             db2[tid] = acc;
@@ -501,7 +503,7 @@ static int predictor_bwd_impl(const float* r, const dd_predictor_tensors* w, con
 
     if (part != 2) {
         const int n_w = kFc1Out * kFc1In / 256, n_d = (B * kFc1In + 255) / 256;
-        launch_pdl(fc_bwd_kernel, dim3(n_w + n_d + 1), dim3(256), 0, st, dfeat, a[5], (const float*)w->fc2_w, a[4], (const float*)w->fc1_w,
+        launch_pdl(fc_bwd_kernel, dim3(n_w + n_d + kFc2Ctas), dim3(256), 0, st, dfeat, a[5], (const float*)w->fc2_w, a[4], (const float*)w->fc1_w,
                    g->fc2_w, g->fc2_b, g->fc1_w, g->fc1_b, d[4], B, n_w, n_d, px);
         count_launch();
         if (part == 1) return check_launch("dd_predictor_bwd_part(fc)");
