@@ -86,23 +86,33 @@ inline int sm_count() {  // SMs of the current device (all GPUs of a node are th
 }
 
 // ---- programmatic dependent launch ---------------------------------------------------------------
-// Every kernel of the library is launched with the programmatic-stream-serialization attribute and starts with
-// pdl_begin(): the next kernel in the stream may be scheduled as soon as all CTAs of this one have started (its CTAs
-// then wait in griddepcontrol.wait until this grid has completed and its memory is visible), which hides the launch
-// latency between the ~20 dependent kernels of a step.  Safe by construction: nothing touches global memory before
-// the wait, and a grid cannot complete before its predecessors (its working CTAs waited for them).
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute: the next kernel in the stream may
+// be scheduled as soon as all CTAs of this one have executed griddepcontrol.launch_dependents (or exited); its CTAs run until
+// their own griddepcontrol.wait, which returns when this grid has completed and its memory is visible.  That hides the launch
+// latency, the prologues and the first loads of the ~20 dependent kernels of a step.  The rules that keep it correct:
+//   1. Default (pdl_begin): release, then wait, first thing in the kernel -- nothing touches global memory before the wait.  A grid
+//      cannot complete before its predecessors (its working CTAs waited for them).
+//   2. Prologues that touch no global memory (barrier initialisation, TMEM allocation, the first __syncthreads) may sit in front
+//      of the wait: pdl_launch(); prologue; pdl_wait().  Kernels that allocate TMEM release their dependents AFTER the
+//      allocation: a dependent CTA sharing the SM must not take the columns first (it would hold them while waiting for this
+//      grid, which waits for the columns).
+//   3. A kernel may READ ahead of its wait only what its predecessor cannot be writing:
+//      - parameters (no kernel of the library writes them);
+//      - image-sized inputs of the step (x, IcA, A, g, r): the kernels that PRODUCE such tensors (synthesis, dark-channel prior)
+//        never release their dependents early (pdl_wait_only), so whatever runs behind them sees them complete;
+//      - data written two or more kernels earlier, IF the predecessor waits before it releases (pdl_wait(); pdl_launch();):
+//        a dependent CTA then only runs once the predecessor is past its own wait, i.e. once everything older has completed.
+//        (When only some CTAs of the predecessor do so, that is enough: the dependent grid starts when EVERY CTA has released.)
+//   4. Nothing is WRITTEN to global memory ahead of the wait, except by CTAs whose inputs and outputs are covered by 3 and that
+//      never wait at all (the slice reduction of the tensor-core layers, dd_conv_tc.cuh).
+//   5. ptxas moves ld.global.nc (__ldg, const __restrict__ loads) across griddepcontrol.wait in BOTH directions.  Data of the
+//      predecessor that is read right behind a wait uses ld.global.cg (__ldcg, a volatile asm); loads that must stay in front of
+//      it use a coherent ld.global in a volatile asm (ldg_pinned, dd_predictor.cu) or cp.async / TMA.
+// tests/test_sass_pdl.py checks the machine code of every kernel: no global access in front of ACQBULK except the listed ones.
 __device__ __forceinline__ void pdl_begin() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
-// The two halves separately, for kernels whose prologue touches no global memory (barrier initialisation, TMEM allocation, the
-// first __syncthreads): pdl_launch(); prologue; pdl_wait(); -- the prologue then runs while the predecessor is still working.
-// Kernels that allocate TMEM call pdl_launch() AFTER the allocation: a dependent CTA that shares the SM must not be able to take
-// the columns first (it would hold them while waiting for this grid, which waits for the columns).
-// tests/test_sass_pdl.py checks on the SASS that no global access ends up in front of the wait.
-// For kernels that PRODUCE image-sized tensors (the synthesis passes, the dark-channel prior): wait, and never release the
-// dependents early -- they start when this grid has completed and flushed.  That is what allows the filter kernels to prefetch
-// the batch ahead of their own grid dependency whatever the caller's launch order is.
 __device__ __forceinline__ void pdl_wait_only() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
