@@ -98,7 +98,7 @@ inline int sm_count() {  // SMs of the current device (all GPUs of a node are th
 //      grid, which waits for the columns).
 //   3. A kernel may READ ahead of its wait only what its predecessor cannot be writing:
 //      - parameters (no kernel of the library writes them);
-//      - image-sized inputs of the step (x, IcA, A, g, r): the kernels that PRODUCE such tensors (synthesis, dark-channel prior)
+//      - image-sized inputs of the step (x, IcA, A, g): the kernels that PRODUCE such tensors (synthesis, dark-channel prior)
 //        never release their dependents early (pdl_wait_only), so whatever runs behind them sees them complete;
 //      - data written two or more kernels earlier, IF the predecessor waits before it releases (pdl_wait(); pdl_launch();):
 //        a dependent CTA then only runs once the predecessor is past its own wait, i.e. once everything older has completed.
